@@ -1,0 +1,329 @@
+"""Generate tests/golden/*.npz by RUNNING THE REFERENCE ITSELF (see _ref_import.py).
+
+    python tests/golden/gen_golden.py          # needs /root/reference (this container only)
+
+Every file stores the seeded inputs and what the unmodified reference code returned for them:
+  losses.npz    MSELoss / KnowledgeDistillationKLDivLoss over reductions, weights, avg_factor
+  boxes.npz     bbox_overlaps (iou/giou, aligned or not), Integral_average, box conversions
+  assign.npz    QualityFocalLossCost + BBoxL1Cost + IoUCost, GFLHungarianAssigner.assign,
+                filter_scores_and_topk, _get_bboxes_single(need_logits=True)
+  head_<mode>_<crit>.npz   GFLDeformableDETRHead_il.loss -> loss_corr, loss_fg_feature, the
+                assigned labels of all 6 layers, gradients w.r.t. student embeddings / features
+The oracle (oracle/) and the CUDA path are both checked against these.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import _ref_import  # noqa: E402
+
+_ref_import.install()
+
+from mmdet.models.losses.mse_loss import MSELoss  # noqa: E402
+from mmdet.models.losses.kd_loss import KnowledgeDistillationKLDivLoss  # noqa: E402
+from mmdet.models.losses.gfocal_loss import QualityFocalLoss, DistributionFocalLoss  # noqa: E402
+from mmdet.models.losses.smooth_l1_loss import L1Loss  # noqa: E402
+from mmdet.models.losses.iou_loss import GIoULoss  # noqa: E402
+from mmdet.core.bbox.iou_calculators.iou2d_calculator import bbox_overlaps  # noqa: E402
+from mmdet.core.bbox.transforms import bbox_cxcywh_to_xyxy, bbox_xyxy_to_cxcywh  # noqa: E402
+from mmdet.core.bbox.match_costs.match_cost import (BBoxL1Cost, IoUCost,  # noqa: E402
+                                                    QualityFocalLossCost)
+from mmdet.core.bbox.assigners.gfl_hungarian_assigner import GFLHungarianAssigner  # noqa: E402
+from mmdet.core.bbox.samplers.pseudo_sampler import PseudoSampler  # noqa: E402
+from mmdet.core.utils.misc import filter_scores_and_topk  # noqa: E402
+from mmdet.models.dense_heads.gfl_deformable_detr_head_il import (  # noqa: E402
+    GFLDeformableDETRHead_il, Integral_average)
+
+NUM_CLASSES, REG_MAX = 80, 16
+
+
+def npify(d):
+    out = {}
+    for k, v in d.items():
+        if isinstance(v, torch.Tensor):
+            out[k] = v.detach().cpu().numpy()
+        elif isinstance(v, (list, tuple)) and v and isinstance(v[0], torch.Tensor):
+            for i, t in enumerate(v):
+                out[f'{k}.{i}'] = t.detach().cpu().numpy()
+            out[f'{k}.len'] = np.int64(len(v))
+        else:
+            out[k] = np.asarray(v)
+    return out
+
+
+def save(name, d):
+    path = os.path.join(HERE, name)
+    np.savez_compressed(path, **npify(d))
+    print(f'{name}: {os.path.getsize(path) / 1024:.0f} KiB, {len(d)} keys')
+
+
+# ------------------------------------------------------------------------------ loss modules
+def gen_losses():
+    g = torch.Generator().manual_seed(11)
+    d = {}
+    pred = torch.randn(6, 9, 5, generator=g)
+    tgt = torch.randn(6, 9, 5, generator=g)
+    w = torch.rand(6, 9, 5, generator=g)
+    d.update(pred=pred, target=tgt, weight=w)
+    for red in ('none', 'mean', 'sum'):
+        for lw in (1.0, 0.37):
+            d[f'mse.{red}.{lw}'] = MSELoss(reduction=red, loss_weight=lw)(pred, tgt)
+            d[f'mse.{red}.{lw}.w'] = MSELoss(reduction=red, loss_weight=lw)(pred, tgt, weight=w)
+    d['mse.mean.avg7'] = MSELoss(reduction='mean')(pred, tgt, weight=w, avg_factor=7.0)
+    d['mse.none.avg7'] = MSELoss(reduction='none')(pred, tgt, avg_factor=7.0)
+    d['mse.override_sum'] = MSELoss(reduction='mean')(pred, tgt, reduction_override='sum')
+    p = pred.clone().requires_grad_(True)
+    t = tgt.clone().requires_grad_(True)
+    MSELoss(reduction='sum', loss_weight=0.37)(p, t, weight=w).backward()
+    d['mse.grad_pred'], d['mse.grad_target'] = p.grad, t.grad
+    # KD: dim=1 softmax on a [C,H,W]-like tensor, exactly how the head calls it
+    wk = torch.rand(6, 5, generator=g)
+    d['kd.weight'] = wk
+    for red in ('none', 'mean', 'sum'):
+        for T in (1, 2, 10):
+            d[f'kd.{red}.T{T}'] = KnowledgeDistillationKLDivLoss(reduction=red, loss_weight=1.5, T=T)(pred, tgt)
+    d['kd.sum.T2.w'] = KnowledgeDistillationKLDivLoss(reduction='sum', T=2)(pred, tgt, weight=wk)
+    d['kd.mean.T2.avg3'] = KnowledgeDistillationKLDivLoss(reduction='mean', T=2)(pred, tgt, avg_factor=3.0)
+    p = pred.clone().requires_grad_(True)
+    t = tgt.clone().requires_grad_(True)
+    KnowledgeDistillationKLDivLoss(reduction='sum', loss_weight=1.5, T=2)(p, t).backward()
+    d['kd.grad_pred'] = p.grad
+    d['kd.grad_target_is_none'] = np.bool_(t.grad is None)
+    # 2-D logits form [N, classes]
+    p2, t2 = torch.randn(17, 80, generator=g), torch.randn(17, 80, generator=g)
+    d.update(pred2=p2, target2=t2)
+    d['kd2.mean.T10'] = KnowledgeDistillationKLDivLoss(reduction='mean', T=10)(p2, t2)
+    save('losses.npz', d)
+
+
+# ------------------------------------------------------------------------------ boxes
+def rand_xyxy(g, n, w=1.0, h=1.0):
+    x1 = torch.rand(n, generator=g) * 0.7 * w
+    y1 = torch.rand(n, generator=g) * 0.7 * h
+    return torch.stack([x1, y1, x1 + torch.rand(n, generator=g) * 0.3 * w + 1e-3,
+                        y1 + torch.rand(n, generator=g) * 0.3 * h + 1e-3], 1)
+
+
+def gen_boxes():
+    g = torch.Generator().manual_seed(12)
+    a, b = rand_xyxy(g, 37, 1333, 800), rand_xyxy(g, 11, 1333, 800)
+    d = dict(a=a, b=b)
+    d['iou'] = bbox_overlaps(a, b, mode='iou')
+    d['giou'] = bbox_overlaps(a, b, mode='giou')
+    d['iou_aligned'] = bbox_overlaps(a[:11], b, mode='iou', is_aligned=True)
+    d['giou_aligned'] = bbox_overlaps(a[:11], b, mode='giou', is_aligned=True)
+    lrtb = torch.rand(23, 4 * (REG_MAX + 1), generator=g)
+    d['lrtb'] = lrtb
+    d['integral'] = Integral_average(REG_MAX)(lrtb)
+    d['to_cxcywh'] = bbox_xyxy_to_cxcywh(a)
+    d['to_xyxy'] = bbox_cxcywh_to_xyxy(bbox_xyxy_to_cxcywh(a))
+    save('boxes.npz', d)
+
+
+# ------------------------------------------------------------------------------ head
+def make_assigner(w_cls=2.0):
+    a = object.__new__(GFLHungarianAssigner)
+    a.cls_cost = QualityFocalLossCost(weight=w_cls)
+    a.reg_cost = BBoxL1Cost(weight=5.0, box_format='xywh')
+    a.iou_cost = IoUCost(iou_mode='giou', weight=2.0)
+    a.num_classes, a.reg_max = NUM_CLASSES, REG_MAX
+    return a
+
+
+def make_head(feats_distill, loss_fg_feature, loss_corr, w_cls=2.0):
+    """A GFLDeformableDETRHead_il instance with exactly the attributes `loss` touches; the
+    constructor is bypassed because it builds the (mmcv) transformer."""
+    h = object.__new__(GFLDeformableDETRHead_il)
+    torch.nn.Module.__init__(h)
+    h.num_classes = h.cls_out_channels = NUM_CLASSES
+    h.reg_max = REG_MAX
+    h.bg_cls_weight = 0.0
+    h.sync_cls_avg_factor = False
+    h.has_teacher = True
+    h.cates_distill = 'hard + teacher-first'
+    h.locat_distill = ''
+    h.memory_distill = ''
+    h.feats_distill = feats_distill
+    h.integral_average = Integral_average(REG_MAX)
+    h.assigner = make_assigner(w_cls)
+    h.sampler = PseudoSampler()
+    h.loss_cls = QualityFocalLoss(use_sigmoid=True, beta=2.0, loss_weight=2.0)
+    h.loss_dfl = DistributionFocalLoss(loss_weight=0.5)
+    h.loss_bbox = L1Loss(loss_weight=5.0)
+    h.loss_iou = GIoULoss(loss_weight=2.0)
+    h.loss_fg_feature = loss_fg_feature
+    h.loss_corr = loss_corr
+    h.test_cfg = dict(max_per_img=100, score_thr=0.0)
+    h.num_query = 300
+    return h
+
+
+def head_inputs(seed, N=2, Q=50, C=64, L=40, img_hw=(128, 208), levels=((16, 26), (8, 13), (4, 7), (2, 4)),
+                layers=3, t_shift=3.0):
+    g = torch.Generator().manual_seed(seed)
+    t_cls = torch.randn(layers, N, Q, NUM_CLASSES, generator=g) - t_shift
+    t_cls[..., L:] = -12.0                      # teacher only knows the previous classes
+    t_box = torch.rand(layers, N, Q, 2 + 4 * (REG_MAX + 1), generator=g)
+    s_cls = torch.randn(layers, N, Q, NUM_CLASSES, generator=g) - 2.0
+    s_box = torch.rand(layers, N, Q, 2 + 4 * (REG_MAX + 1), generator=g)
+    hs_s = torch.randn(layers, N, Q, C, generator=g)
+    hs_t = torch.randn(layers, N, Q, C, generator=g)
+    s_feats = [torch.randn(N, C, h, w, generator=g) for h, w in levels]
+    t_feats = [torch.randn(N, C, h, w, generator=g) for h, w in levels]
+    gt_b, gt_l = [], []
+    for _ in range(N):
+        n_gt = int(torch.randint(1, 5, (1,), generator=g))
+        gt_b.append(rand_xyxy(g, n_gt, img_hw[1], img_hw[0]))
+        gt_l.append(torch.randint(L, NUM_CLASSES, (n_gt,), generator=g))
+    return dict(t_cls=t_cls, t_box=t_box, s_cls=s_cls, s_box=s_box, hs_s=hs_s, hs_t=hs_t,
+                s_feats=s_feats, t_feats=t_feats, gt_bboxes=gt_b, gt_labels=gt_l,
+                img_hw=img_hw, levels=levels, L=L)
+
+
+_saved_inputs = set()
+
+
+def run_head(mode, crit, seed=21, L=40, w_cls=2.0, N=2, tag='', t_shift=3.0):
+    inp = head_inputs(seed, N=N, L=L, t_shift=t_shift)
+    N, Q = inp['s_cls'].shape[1:3]
+    C = inp['hs_s'].shape[-1]
+    img_metas = [dict(img_shape=(inp['img_hw'][0], inp['img_hw'][1], 3), scale_factor=1.0)] * N
+    if crit == 'mse':
+        fg = MSELoss(reduction='sum', loss_weight=1.0)
+    else:
+        fg = KnowledgeDistillationKLDivLoss(reduction='sum', loss_weight=1.0, T=2)
+    head = make_head(f'corr + fg_info + {mode}', fg, MSELoss(reduction='mean', loss_weight=1.0), w_cls)
+
+    # ---- teacher side: the detector's out_teacher (deformable_detr_il.py:116-154)
+    spatial_shapes = torch.tensor(inp['levels'], dtype=torch.long)
+    t_memory = torch.cat([f.flatten(2) for f in inp['t_feats']], 2).permute(2, 0, 1).contiguous()
+    s_memory = torch.cat([f.flatten(2) for f in inp['s_feats']], 2).permute(2, 0, 1).contiguous()
+    teacher_cfg = dict(min_bbox_size=0, score_thr=0.3, max_per_img=100)
+    outs = [head._get_bboxes_single(inp['t_cls'][-1][i], inp['t_box'][-1][i], img_metas[i]['img_shape'],
+                                    1.0, rescale=False, cfg=teacher_cfg, need_logits=True) for i in range(N)]
+    pred_bboxes = [o[0][:, 0:4].detach() for o in outs]
+    pred_scores = [o[0][:, 4:5].flatten().detach() for o in outs]
+    pred_labels = [o[1].detach() for o in outs]
+    pred_keepid = torch.cat([o[3].detach() + i * Q for i, o in enumerate(outs)])
+    teacher_info = dict(neck_feats=tuple(inp['t_feats']),
+                        head_outs=(inp['t_cls'], inp['t_box'], (t_memory, spatial_shapes), inp['hs_t']),
+                        pred_keepid=pred_keepid, pred_labels=pred_labels, pred_bboxes=pred_bboxes,
+                        pred_scores=pred_scores)
+
+    # ---- student side with gradients
+    hs_s = inp['hs_s'].clone().requires_grad_(True)
+    s_feats = [f.clone().requires_grad_(True) for f in inp['s_feats']]
+    s_mem = s_memory.clone().requires_grad_(True)
+    captured = {}
+    orig = head.loss_single_split
+
+    def spy(*a, **k):
+        r = orig(*a, **k)
+        captured.setdefault('teacher_only', []).append(r[5].clone())
+        captured.setdefault('labels', []).append(r[6].clone())
+        return r
+    head.loss_single_split = spy
+    task_labels = dict(prev=list(range(inp['L'])), curr=list(range(inp['L'], NUM_CLASSES)), next=[])
+    losses = head.loss(inp['s_cls'], inp['s_box'], (s_mem, spatial_shapes), hs_s,
+                       [b.clone() for b in inp['gt_bboxes']], [l.clone() for l in inp['gt_labels']],
+                       img_metas, gt_bboxes_ignore=None, student_feat=s_feats,
+                       teacher_info=teacher_info, task_labels=task_labels)
+    if seed not in _saved_inputs:          # inputs are shared by every mode run on this seed
+        _saved_inputs.add(seed)
+        shared = dict(inp)
+        shared.update(img_hw=np.asarray(inp['img_hw']), levels=np.asarray(inp['levels']),
+                      L=np.int64(inp['L']), w_cls=np.float64(w_cls))
+        save(f'head_inputs_seed{seed}.npz', shared)
+    out = dict(seed=np.int64(seed))
+    out.update(pred_bboxes=pred_bboxes, pred_scores=pred_scores, pred_labels=pred_labels,
+               pred_keepid=pred_keepid,
+               labels_layers=torch.stack(captured['labels']),
+               teacher_only_layers=torch.stack(captured['teacher_only']),
+               loss_corr=losses['loss_corr'], loss_fg_feature=losses['loss_fg_feature'])
+    g_corr = torch.autograd.grad(losses['loss_corr'], hs_s, retain_graph=True, allow_unused=True)[0]
+    out['corr.grad_hs'] = g_corr[-1] if g_corr is not None else torch.zeros(N, Q, C)
+    lf = losses['loss_fg_feature']
+    # NB: with MSELoss and N >= 2 the reference itself cannot back-propagate: the in-place slice
+    # assignment into the shared Mask_hs (head_il.py:706) for image i+1 bumps the version of the
+    # view saved by `features_pred[i] * Mask_hs[i]` (:709).  Recorded, not hidden.
+    try:
+        grads = torch.autograd.grad(lf, [hs_s, s_mem] + s_feats, allow_unused=True) if lf.requires_grad \
+            else [None] * (2 + len(s_feats))
+        out['fg.backward_raises'] = np.bool_(False)
+    except RuntimeError as e:
+        assert 'modified by an inplace operation' in str(e)
+        grads = [None] * (2 + len(s_feats))
+        out['fg.backward_raises'] = np.bool_(True)
+    out['fg.grad_hs'] = grads[0][-1] if grads[0] is not None else torch.zeros(N, Q, C)
+    out['fg.grad_hs_is_none'] = np.bool_(grads[0] is None)
+    out['fg.grad_mem_is_none'] = np.bool_(grads[1] is None)
+    if grads[1] is not None:
+        out['fg.grad_mem'] = grads[1]
+    out['fg.grad_feats_is_none'] = np.bool_(grads[2] is None)
+    if grads[2] is not None:
+        out['fg.grad_feats'] = list(grads[2:])
+    save(f'head_{mode}_{crit}{tag}.npz', out)
+
+
+# ------------------------------------------------------------------------------ assignment
+def gen_assign():
+    g = torch.Generator().manual_seed(13)
+    d = {}
+    Q = 100
+    img_shape = (800, 1333, 3)
+    ia = Integral_average(REG_MAX)
+    n_case = 0
+    for G, w_cls in ((0, 2.0), (1, 2.0), (7, 2.0), (33, 1.0), (60, 2.0)):
+        cls = torch.randn(Q, NUM_CLASSES, generator=g) - 2.0
+        box = torch.rand(Q, 2 + 4 * (REG_MAX + 1), generator=g)
+        cxcywh = torch.cat((box[:, :2], ia(box[:, 2:])), 1)
+        gt = rand_xyxy(g, G, 1333, 800) if G else torch.zeros(0, 4)
+        lab = torch.randint(0, NUM_CLASSES, (G,), generator=g)
+        asg = make_assigner(w_cls)
+        res = asg.assign(cxcywh, cls, gt, lab, box[:, 2:], dict(img_shape=img_shape))
+        p = f'case{n_case}.'
+        d.update({p + 'cls': cls, p + 'box': box, p + 'cxcywh': cxcywh, p + 'gt': gt, p + 'lab': lab,
+                  p + 'w_cls': np.float64(w_cls), p + 'gt_inds': res.gt_inds, p + 'labels': res.labels})
+        if G:
+            factor = gt.new_tensor([1333, 800, 1333, 800]).unsqueeze(0)
+            d[p + 'reg_cost'] = asg.reg_cost(cxcywh, gt / factor)
+            d[p + 'iou_cost'] = asg.iou_cost(bbox_cxcywh_to_xyxy(cxcywh) * factor, gt)
+            d[p + 'cls_cost'] = asg.cls_cost(cls, lab, bbox_cxcywh_to_xyxy(cxcywh), gt / factor)
+        n_case += 1
+    d['num_cases'] = np.int64(n_case)
+    # teacher decode (A1)
+    scores = torch.rand(Q, NUM_CLASSES, generator=g) ** 6
+    s, l, k, _ = filter_scores_and_topk(scores, 0.3, 100, results=None)
+    d.update({'topk.scores_in': scores, 'topk.scores': s, 'topk.labels': l, 'topk.keep': k})
+    head = make_head('', None, None)
+    head.loss_cls = QualityFocalLoss(use_sigmoid=True, beta=2.0, loss_weight=2.0)
+    t_cls = torch.randn(Q, NUM_CLASSES, generator=g) - 3.0
+    t_box = torch.rand(Q, 2 + 4 * (REG_MAX + 1), generator=g)
+    det, labels, logits, keep = head._get_bboxes_single(
+        t_cls, t_box, img_shape, 1.0, rescale=False,
+        cfg=dict(min_bbox_size=0, score_thr=0.3, max_per_img=100), need_logits=True)
+    d.update({'decode.cls': t_cls, 'decode.box': t_box, 'decode.det': det, 'decode.labels': labels,
+              'decode.keep': keep})
+    save('assign.npz', d)
+
+
+if __name__ == '__main__':
+    torch.manual_seed(0)
+    torch.set_num_threads(4)
+    gen_losses()
+    gen_boxes()
+    gen_assign()
+    run_head('decode_v1', 'mse')
+    run_head('decode_v1', 'mse', N=1, seed=23, tag='_n1')
+    run_head('decode_v1', 'kl', seed=24, L=70, w_cls=1.0, tag='_l70', t_shift=3.5)
+    run_head('decode_v1', 'kl')
+    run_head('decode_v2', 'mse')
+    run_head('decode_v2', 'mse', N=1, seed=23, tag='_n1')
+    run_head('sg_out', 'kl')
+    run_head('sg_out', 'mse')
+    run_head('fg_only', 'mse')

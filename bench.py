@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""Benchmark of the DSKD distillation hot path on B200 (see DESIGN.md section "Measurement").
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
+        --master-port 29500 bench.py --gpus 8 --steps 20 --warmup 5
+    python bench.py --impl reference --steps 3 --warmup 1        # the reference's CPU arithmetic
+
+One "step" = distillation loss forward + backward for one batch of synthetic COCO-shaped inputs:
+DSG-FD (decode_v1 mask, masked MSE) over 4-level 256-channel features + BCDD over the last-layer
+decoder embeddings, `images_per_gpu` 800x1333 images per rank (weak scaling; per-class prototype
+sums/counts are the only cross-rank state: one NCCL all-reduce).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'distill_loss_fwd_bwd_images_per_s'
+UNIT = 'images/s'
+BYTES_PER_IMAGE_MSE = 3 * 22223 * 256 * 4      # read S + read T + write dS  (SURVEY.md section 8d): 68.27 MB
+WORKLOAD = 'coco_40+40_dsgfd_mse+bcdd'
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='dskd_b200', choices=['dskd_b200', 'reference'])
+    ap.add_argument('--images-per-gpu', type=int, default=16,
+                    help='samples_per_gpu of the 40+40 config (chaosuan_..._40_r50_8x4_1x_qoqo_il.py:199)')
+    ap.add_argument('--num-prev', type=int, default=40)
+    ap.add_argument('--criterion', default='mse', choices=['mse', 'kl'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--cpu-sample-images', type=int, default=2)
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+
+    QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+             'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', f'--id={self.gpu_index}', f'--query-gpu={self.QUERY}',
+                 '--format=csv,noheader,nounits', '-lms', '100'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(',')]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+                power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(smax) if smax else None,
+                    power_w_max=max(power) if power else None, samples=len(sm), reasons=sorted(reasons))
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_step(cpu_inputs, criterion):
+    """One fwd+bwd of the reference's arithmetic (the oracle restatement) on the host cores."""
+    from oracle import bcdd as ob, dsgfd as od, losses as ol
+    a = cpu_inputs.assignments
+    shapes = [tuple(x) for x in a['img_shapes'].tolist()]
+    L = len(a['prev_labels'])
+    id_pred = torch.nonzero(a['student_labels'] < L).squeeze(1)
+    feats, hs = cpu_inputs.clone_student()
+    crit = ol.MSELoss('sum', 1.0) if criterion == 'mse' else ol.KnowledgeDistillationKLDivLoss('sum', 1.0, 2)
+    C = hs.shape[-1]
+    loss = od.decode_v1(feats, cpu_inputs.teacher_feats, hs, cpu_inputs.hs_teacher, a['teacher_keepid'], id_pred,
+                        a['teacher_bboxes'], shapes, crit)
+    loss = loss + ob.bcdd_loss(hs.reshape(-1, C), a['student_labels'], cpu_inputs.hs_teacher.reshape(-1, C),
+                               a['teacher_keepid'], a['teacher_labels'], a['prev_labels'], ol.MSELoss('mean', 1.0))
+    loss.backward()
+    return float(loss)
+
+
+def time_cpu_reference(args, steps, warmup):
+    from dskd_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n = args.cpu_sample_images
+    cpu_inputs = synth.make_distill_inputs(num_images=n, num_prev=args.num_prev, seed=1234)
+    for _ in range(warmup):
+        cpu_reference_step(cpu_inputs, args.criterion)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        cpu_reference_step(cpu_inputs, args.criterion)
+        times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return dict(value=n * steps / total, unit=UNIT, cores=cores, kind='port',
+                sample=f'{n} images/step x {steps} steps (+{warmup} warm-up) of the same workload, oracle '
+                       f'restatement of head_il.py:525-555,664-719,1197-1222, torch {torch.__version__} CPU fp32'), \
+        total / steps * 1e3
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    base, ms = time_cpu_reference(args, args.steps, args.warmup)
+    line = {'metric': METRIC, 'value': base['value'], 'unit': UNIT, 'impl': 'reference', 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'images_per_step': args.cpu_sample_images, 'num_prev': args.num_prev,
+                       'criterion': args.criterion, 'levels': [[100, 167], [50, 84], [25, 42], [13, 21]],
+                       'channels': 256, 'queries': 300},
+            'cpu_baseline': base,
+            'e2e': {'value': base['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def main():
+    args = parse_args()
+    if args.impl == 'reference':
+        run_reference_arm(args)
+        return
+    import torch.distributed as dist
+    import dskd_b200
+    from dskd_b200 import _lib, synth
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py --impl dskd_b200 needs a CUDA device (there is no CPU fallback)')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    lib = _lib.load()
+
+    N = args.images_per_gpu
+    inputs = synth.make_distill_inputs(num_images=N, num_prev=args.num_prev, seed=1234 + rank, device=dev)
+    dsg = dskd_b200.build_loss(dict(type='DSGFeatureDistillLoss', criterion=args.criterion, reduction='sum',
+                                    loss_weight=1.0, T=2.0, mask_mode='decode_v1', feature_source='neck'))
+    bcdd = dskd_b200.build_loss(dict(type='BetweenClassDistanceLoss', reduction='mean', loss_weight=1.0,
+                                     sync_prototypes=world > 1))
+    s_feats = [f.requires_grad_(True) for f in inputs.student_feats]
+    hs_s = inputs.hs_student.requires_grad_(True)
+
+    # roofline instrumentation: CUDA events around the dominant kernel's entry point, on its launch stream
+    kernel_events = []
+    orig_mse = lib.dskd_dsgfd_mse_fwd_bwd
+    orig_kl = lib.dskd_dsgfd_kl_fwd_bwd
+    record = {'on': False}
+
+    def timed(fn):
+        def wrapper(a, st):
+            if not record['on']:
+                return fn(a, st)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = fn(a, st)
+            e1.record()
+            kernel_events.append((e0, e1))
+            return rc
+        return wrapper
+    lib.dskd_dsgfd_mse_fwd_bwd = timed(orig_mse)
+    lib.dskd_dsgfd_kl_fwd_bwd = timed(orig_kl)
+
+    def step(feats, t_feats, hs, hs_t):
+        for f in feats:
+            f.grad = None
+        hs.grad = None
+        loss = dsg(feats, t_feats, (hs, hs_t), inputs.assignments) + bcdd(None, None, (hs, hs_t), inputs.assignments)
+        loss.backward()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput (`value`)
+    for _ in range(max(args.warmup, 3)):
+        step(s_feats, inputs.teacher_feats, hs_s, inputs.hs_teacher)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.dskd_launch_count()
+    record['on'] = True
+    e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e_start.record()
+    for _ in range(args.steps):
+        loss = step(s_feats, inputs.teacher_feats, hs_s, inputs.hs_teacher)
+    e_stop.record()
+    barrier()
+    record['on'] = False
+    launches = lib.dskd_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    elapsed_ms = e_start.elapsed_time(e_stop)
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    kernel_ms = statistics.mean(a.elapsed_time(b) for a, b in kernel_events) if kernel_events else float('nan')
+    loss_value = float(loss)
+
+    # ---------------- end-to-end through the module call with HOST buffers (`e2e`)
+    e2e = None
+    if not args.no_e2e:
+        host_s = [torch.empty(f.shape, dtype=f.dtype, pin_memory=True).copy_(f.detach()) for f in s_feats]
+        host_t = [torch.empty(f.shape, dtype=f.dtype, pin_memory=True).copy_(f) for f in inputs.teacher_feats]
+        host_hs = torch.empty(hs_s.shape, pin_memory=True).copy_(hs_s.detach())
+        host_ht = torch.empty(hs_s.shape, pin_memory=True).copy_(inputs.hs_teacher)
+        host_loss = torch.empty((), pin_memory=True)
+        h2d = sum(t_.numel() * 4 for t_ in host_s + host_t + [host_hs, host_ht])
+
+        def e2e_step():
+            fs = [h.to(dev, non_blocking=True).requires_grad_(True) for h in host_s]
+            ft = [h.to(dev, non_blocking=True) for h in host_t]
+            hs = host_hs.to(dev, non_blocking=True).requires_grad_(True)
+            ht = host_ht.to(dev, non_blocking=True)
+            l = step(fs, ft, hs, ht)
+            host_loss.copy_(l.detach(), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return float(host_loss)
+        e2e_steps = max(3, min(args.steps, 10))
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {'value': world * N * e2e_steps / float(tt.item()), 'unit': UNIT, 'h2d_bytes_per_step': h2d,
+               'd2h_bytes_per_step': 4, 'steps': e2e_steps, 'ms_per_step': float(tt.item()) / e2e_steps * 1e3}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = peaks()
+    if args.criterion == 'mse':
+        alg_bytes = BYTES_PER_IMAGE_MSE * N
+    else:
+        alg_bytes = 2 * 22223 * 256 * 4 * N
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    ms_per_step = elapsed_ms / args.steps
+    line = {
+        'metric': METRIC, 'value': world * N * args.steps / (elapsed_ms * 1e-3), 'unit': UNIT, 'n_gpus': world,
+        'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'images_per_gpu': N, 'global_batch': world * N, 'num_prev': args.num_prev,
+                   'criterion': args.criterion, 'levels': [[100, 167], [50, 84], [25, 42], [13, 21]], 'channels': 256,
+                   'queries': 300, 'parallelism': f'dp{world}', 'prototype_allreduce': world > 1,
+                   'cache': f'inputs larger than L2: {2 * N * 22.76:.0f} MB of features read per step vs 126 MB L2'},
+        'roofline': {'bound': 'hbm', 'kernel': 'dsgfd_mse_nchw_kernel' if args.criterion == 'mse' else 'dsgfd_kl_kernel',
+                     'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                     'frac_of_nominal_8000': achieved / 8000.0, 'peak_source': peak_src,
+                     'algorithmic_bytes_per_launch': alg_bytes, 'kernel_ms': kernel_ms,
+                     'kernel_share_of_step': kernel_ms / ms_per_step, 'traffic': None},
+        'e2e': e2e,
+        'gpu_launches': int(launches),
+        'clocks': clocks,
+        'loss': loss_value,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        base, _ = time_cpu_reference(args, steps=3, warmup=1)
+        line['cpu_baseline'] = base
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

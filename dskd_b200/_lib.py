@@ -1,0 +1,151 @@
+"""ctypes binding of libdskd_b200.so (the C ABI declared in include/dskd_b200.h).
+
+There is no fallback: if the shared library is missing or the device is not sm_100 the import /
+first call raises.  Nothing here imports the CPU oracle.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libdskd_b200.so')
+MAX_LEVELS = 8
+
+OK, EINVAL, ECUDA, EUNSUPPORTED_ARCH, EINFEASIBLE = 0, -1, -2, -3, -4
+LAYOUT_NCHW, LAYOUT_SNC = 0, 1
+MASK_DECODE_V1, MASK_DECODE_V2 = 0, 1
+RASTER_OWNER_EXCL, RASTER_BINARY_INCL, RASTER_AREA_INCL, RASTER_AREA_FGBK = 0, 1, 2, 3
+REDUCTION_MEAN, REDUCTION_SUM = 1, 2
+
+
+class DskdError(RuntimeError):
+    pass
+
+
+class Level(C.Structure):
+    _fields_ = [('H', C.c_int32), ('W', C.c_int32), ('cell_offset', C.c_int64)]
+
+
+_FP = C.c_void_p
+
+
+class DsgfdMseArgs(C.Structure):
+    _fields_ = [('layout', C.c_int32), ('num_levels', C.c_int32), ('N', C.c_int32), ('C', C.c_int32),
+                ('levels', Level * MAX_LEVELS),
+                ('d_student', _FP * MAX_LEVELS), ('d_teacher', _FP * MAX_LEVELS),
+                ('d_grad_student', _FP * MAX_LEVELS), ('scale', C.c_float * MAX_LEVELS),
+                ('cells_per_image', C.c_int64), ('d_owner', _FP), ('d_rows', _FP), ('d_energy', _FP),
+                ('num_pairs', C.c_int32), ('d_cell_weight', _FP), ('d_loss', _FP)]
+
+
+class DsgfdKlArgs(C.Structure):
+    _fields_ = [('num_levels', C.c_int32), ('N', C.c_int32), ('C', C.c_int32),
+                ('levels', Level * MAX_LEVELS),
+                ('d_student', _FP * MAX_LEVELS), ('d_teacher', _FP * MAX_LEVELS),
+                ('scale', C.c_float * MAX_LEVELS), ('temperature', C.c_float),
+                ('cells_per_image', C.c_int64), ('d_owner', _FP), ('d_rows', _FP), ('d_grad_rows', _FP),
+                ('num_pairs', C.c_int32), ('d_cell_weight', _FP), ('d_loss', _FP)]
+
+
+i32, i64, f32, vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
+
+# name -> argtypes; every entry point declared in include/dskd_b200.h (tests/test_abi.py checks both ways)
+SIGNATURES = {
+    'dskd_abi_version': [],
+    'dskd_check_device': [],
+    'dskd_mask_rows': [i32, vp, vp, vp, vp, i32, i32, vp, vp],
+    'dskd_mask_rows_bwd': [vp, vp, vp, vp, vp, vp, i32, i32, vp, vp],
+    'dskd_select_prev_queries': [vp, i32, vp, i32, i32, vp, vp, vp],
+    'dskd_raster_cells': [i32, vp, vp, vp, vp, vp, i32, i32, C.POINTER(Level), i32, i64, vp, vp],
+    'dskd_dsgfd_mse_fwd_bwd': [C.POINTER(DsgfdMseArgs), vp],
+    'dskd_dsgfd_mse_finish': [vp, vp, i32, i32, vp, vp, vp],
+    'dskd_dsgfd_kl_fwd_bwd': [C.POINTER(DsgfdKlArgs), vp],
+    'dskd_bcdd_prototypes': [vp, vp, i32, vp, vp, vp, i32, vp, i32, i32, vp, vp],
+    'dskd_bcdd_distance_loss': [vp, i32, i32, i32, i32, f32, f32, vp, vp, vp, vp],
+    'dskd_bcdd_scatter_grad': [vp, vp, i32, vp, i32, i32, vp, vp],
+    'dskd_cost_matrix': [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, i32, f32, f32, f32, vp, vp],
+    'dskd_assign_targets': [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
+    'dskd_lsap_f64': [vp, i32, i32, vp, vp],
+    'dskd_lsap_batch_f32': [vp, i32, i32, i32, vp, vp, i32],
+    'dskd_mse_elementwise': [vp, vp, vp, i64, f32, vp, vp, vp, vp, vp],
+    'dskd_kd_kl_rows': [vp, vp, i64, i32, i64, f32, vp, f32, vp, vp, vp, vp],
+    'dskd_scale_inplace': [vp, i64, vp, vp],
+    'dskd_f64_to_f32': [vp, vp, i32, f32, vp],
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library once; raise loudly when it is absent (no CPU / eager fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DskdError(
+            f'{LIB_PATH} is missing: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+            f'(nvcc, sm_100a).  dskd_b200 has no CPU or eager-PyTorch fallback.')
+    lib = C.CDLL(LIB_PATH)
+    lib.dskd_last_error.restype = C.c_char_p
+    lib.dskd_last_error.argtypes = []
+    lib.dskd_launch_count.restype = C.c_uint64
+    lib.dskd_launch_count.argtypes = []
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
+    if lib.dskd_abi_version() != 1:
+        raise DskdError(f'ABI version mismatch: library {lib.dskd_abi_version()} != binding 1')
+    _lib = lib
+    return lib
+
+
+def check(rc, what=''):
+    if rc != OK:
+        msg = load().dskd_last_error().decode('utf-8', 'replace')
+        raise DskdError(f'{what} failed with status {rc}: {msg}')
+
+
+_device_checked = set()
+
+
+def require_device(t: torch.Tensor):
+    """Every device entry point goes through here: CUDA tensor on an sm_100 device, or raise."""
+    if not t.is_cuda:
+        raise DskdError('dskd_b200 runs on CUDA (sm_100a) tensors only; there is no CPU path '
+                        f'(got a tensor on {t.device}).')
+    idx = t.device.index if t.device.index is not None else torch.cuda.current_device()
+    if idx not in _device_checked:
+        with torch.cuda.device(idx):
+            check(load().dskd_check_device(), 'dskd_check_device')
+        _device_checked.add(idx)
+    return idx
+
+
+def ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_of(t: torch.Tensor):
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def f32c(t: torch.Tensor):
+    """Contiguous fp32 view / copy (the reference runs this path under force_fp32, head_il.py:411)."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def levels_struct(shapes):
+    """shapes: iterable of (H, W) -> (ctypes array of Level, cells_per_image)."""
+    arr = (Level * MAX_LEVELS)()
+    off = 0
+    shapes = [(int(h), int(w)) for h, w in shapes]
+    if not 0 < len(shapes) <= MAX_LEVELS:
+        raise DskdError(f'between 1 and {MAX_LEVELS} feature levels are supported, got {len(shapes)}')
+    for l, (h, w) in enumerate(shapes):
+        arr[l].H, arr[l].W, arr[l].cell_offset = h, w, off
+        off += h * w
+    return arr, off

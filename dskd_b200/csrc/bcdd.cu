@@ -1,0 +1,200 @@
+// Between-Class Distance Distillation.
+// Reference: gfl_deformable_detr_head_il.py:525-552 (prototype sums / counts, Python loop with one
+// `+=` per query) and :1197-1222 (correlation_mat: 2*L^2 torch.dist calls + MSELoss / L).
+// The whole block is < 3 MFLOP and < 1 MB: latency-bound, so it is three small launches (prototypes,
+// distance+loss+gradient, scatter) with deterministic summation order; the distance uses the direct
+// difference in fp32 like torch.dist (a Gram-trick on tensor cores loses the diagonal).
+#include "common.cuh"
+
+namespace dskd {
+
+// grid (num_classes, 2): side 0 = teacher, 1 = student.  Entries are compacted in ascending index
+// order (ballot prefix) so every class sums its rows in the reference's loop order.
+__global__ void __launch_bounds__(256) bcdd_proto_kernel(const float* __restrict__ hs_s,
+                                                         const int64_t* __restrict__ s_labels, int n_s,
+                                                         const float* __restrict__ hs_t,
+                                                         const int64_t* __restrict__ t_keep,
+                                                         const int64_t* __restrict__ t_labels, int n_t,
+                                                         const uint8_t* __restrict__ prev_mask, int C,
+                                                         float* __restrict__ proto, int num_classes) {
+  __shared__ int64_t list[256];
+  __shared__ int warp_cnt[8];
+  const int cls = blockIdx.x, side = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* out = proto + ((int64_t)side * num_classes + cls) * (C + 1);
+  const int n = side ? n_s : n_t;
+  const int64_t* labels = side ? s_labels : t_labels;
+  const float* hs = side ? hs_s : hs_t;
+  const bool cls_on = side ? (prev_mask[cls] != 0) : true;
+  constexpr int kMaxPerThread = 4;  // supports C <= 1024
+  float acc[kMaxPerThread] = {0.f, 0.f, 0.f, 0.f};
+  int count = 0;
+  for (int base = 0; base < n && cls_on; base += blockDim.x) {
+    const int q = base + threadIdx.x;
+    const bool hit = (q < n) && (labels[q] == (int64_t)cls);
+    const unsigned b = __ballot_sync(0xffffffffu, hit);
+    if (lane == 0) warp_cnt[warp] = __popc(b);
+    __syncthreads();
+    int off = 0, total = 0;
+    for (int w = 0; w < 8; ++w) {
+      if (w < warp) off += warp_cnt[w];
+      total += warp_cnt[w];
+    }
+    if (hit) list[off + __popc(b & ((1u << lane) - 1u))] = side ? (int64_t)q : t_keep[q];
+    __syncthreads();
+    for (int e = 0; e < total; ++e) {
+      const float* row = hs + list[e] * (int64_t)C;
+#pragma unroll
+      for (int k = 0; k < kMaxPerThread; ++k) {
+        const int c = threadIdx.x + k * 256;
+        if (c < C) acc[k] += row[c];
+      }
+    }
+    count += total;
+    __syncthreads();
+  }
+#pragma unroll
+  for (int k = 0; k < kMaxPerThread; ++k) {
+    const int c = threadIdx.x + k * 256;
+    if (c < C) out[c] = acc[k];
+  }
+  if (threadIdx.x == 0) out[C] = (float)count;
+}
+
+// normalised prototype element (head_il.py:1198-1206): both sides divide only where the TEACHER count
+// is non-zero; the student divides by its own count (0/0 = NaN reproduces the reference's edge).
+__device__ __forceinline__ float proto_elem(const float* proto, int num_classes, int C, int side, int k, int c) {
+  const float* t_row = proto + (int64_t)k * (C + 1);
+  const float* row = proto + ((int64_t)side * num_classes + k) * (C + 1);
+  const float n_t = t_row[C];
+  return (n_t != 0.f) ? __fdiv_rn(row[c], row[C]) : row[c];
+}
+
+// grid L: CTA k computes row k of both distance matrices, then d loss / d (student sum row k).
+__global__ void __launch_bounds__(256) bcdd_distance_kernel(const float* __restrict__ proto, int num_classes,
+                                                            int C, int L, float gcoef, float grad_scale,
+                                                            float* __restrict__ dist,
+                                                            float* __restrict__ grad_proto_s) {
+  extern __shared__ float sm[];
+  float* ck_t = sm;            // [C] normalised teacher prototype k
+  float* ck_s = sm + C;        // [C] normalised student prototype k
+  float* coef = sm + 2 * C;    // [L]
+  const int k = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    ck_t[c] = proto_elem(proto, num_classes, C, 0, k, c);
+    ck_s[c] = proto_elem(proto, num_classes, C, 1, k, c);
+  }
+  __syncthreads();
+  for (int j = warp; j < L; j += nw) {
+    float st = 0.f, ss = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float dt = ck_t[c] - proto_elem(proto, num_classes, C, 0, j, c);
+      const float ds = ck_s[c] - proto_elem(proto, num_classes, C, 1, j, c);
+      st = fmaf(dt, dt, st);
+      ss = fmaf(ds, ds, ss);
+    }
+    st = warp_sum(st);
+    ss = warp_sum(ss);
+    if (lane == 0) {
+      const float d_t = sqrtf(st), d_s = sqrtf(ss);
+      dist[(int64_t)k * L + j] = d_t;
+      dist[(int64_t)L * L + (int64_t)k * L + j] = d_s;
+      // d loss / d D_S[k,j] = -gcoef * (D_T - D_S); row k and column k both carry c_k: factor 2.
+      // torch.dist backward yields 0 where the distance is 0 (diagonal, coincident prototypes).
+      coef[j] = (d_s > 0.f) ? (2.f * -gcoef * (d_t - d_s) / d_s) : ((d_s == 0.f) ? 0.f : d_s /*NaN*/);
+    }
+  }
+  if (grad_proto_s == nullptr) return;
+  __syncthreads();
+  const float n_t = proto[(int64_t)k * (C + 1) + C];
+  const float n_s = proto[((int64_t)num_classes + k) * (C + 1) + C];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float g = 0.f;
+    const float ck = ck_s[c];
+    for (int j = 0; j < L; ++j) g = fmaf(coef[j], ck - proto_elem(proto, num_classes, C, 1, j, c), g);
+    if (n_t != 0.f) g = __fdiv_rn(g, n_s);
+    grad_proto_s[(int64_t)k * (C + 1) + c] = g * grad_scale;
+  }
+}
+
+// loss = loss_weight * reduce((D_T - D_S)^2) / L, fixed summation order, double accumulation.
+__global__ void __launch_bounds__(256) bcdd_loss_kernel(const float* __restrict__ dist, int L, float factor,
+                                                        float* __restrict__ loss) {
+  __shared__ double red[32];
+  double acc = 0.0;
+  const int n = L * L;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double d = (double)dist[i] - (double)dist[n + i];
+    acc += d * d;
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) loss[0] = (float)(acc * (double)factor);
+}
+
+__global__ void __launch_bounds__(256) bcdd_scatter_kernel(const float* __restrict__ grad_proto_s,
+                                                           const int64_t* __restrict__ labels, int n,
+                                                           const uint8_t* __restrict__ prev_mask,
+                                                           int num_classes, int C, float* __restrict__ grad_hs) {
+  const int q = blockIdx.x;
+  const int64_t lab = labels[q];
+  const bool on = lab >= 0 && lab < num_classes && prev_mask[lab] != 0;
+  for (int c = threadIdx.x; c < C; c += blockDim.x)
+    grad_hs[(int64_t)q * C + c] = on ? grad_proto_s[lab * (int64_t)(C + 1) + c] : 0.f;
+}
+
+}  // namespace dskd
+
+using namespace dskd;
+
+extern "C" int dskd_bcdd_prototypes(const float* d_hs_student, const int64_t* d_student_labels,
+                                    int32_t num_student_rows, const float* d_hs_teacher,
+                                    const int64_t* d_teacher_keepid, const int64_t* d_teacher_labels,
+                                    int32_t num_teacher, const uint8_t* d_prev_mask, int32_t num_classes,
+                                    int32_t C, float* d_proto, void* stream) {
+  DSKD_REQUIRE(num_classes > 0 && C > 0 && C <= 1024 && num_student_rows >= 0 && num_teacher >= 0,
+               "dskd_bcdd_prototypes: bad sizes (C must be <= 1024)");
+  DSKD_REQUIRE(d_proto && d_prev_mask, "dskd_bcdd_prototypes: null pointer");
+  DSKD_REQUIRE(num_student_rows == 0 || (d_hs_student && d_student_labels), "dskd_bcdd_prototypes: null student input");
+  DSKD_REQUIRE(num_teacher == 0 || (d_hs_teacher && d_teacher_keepid && d_teacher_labels),
+               "dskd_bcdd_prototypes: null teacher input");
+  bcdd_proto_kernel<<<dim3(num_classes, 2), 256, 0, as_stream(stream)>>>(
+      d_hs_student, d_student_labels, num_student_rows, d_hs_teacher, d_teacher_keepid, d_teacher_labels,
+      num_teacher, d_prev_mask, C, d_proto, num_classes);
+  DSKD_LAUNCH_OK("bcdd_proto_kernel");
+  return DSKD_OK;
+}
+
+extern "C" int dskd_bcdd_distance_loss(const float* d_proto, int32_t num_classes, int32_t C, int32_t L,
+                                       int32_t reduction, float loss_weight, float grad_scale, float* d_dist,
+                                       float* d_loss, float* d_grad_proto_student, void* stream) {
+  DSKD_REQUIRE(d_proto && d_dist && d_loss, "dskd_bcdd_distance_loss: null pointer");
+  DSKD_REQUIRE(L > 0 && L <= num_classes && C > 0, "dskd_bcdd_distance_loss: need 0 < L <= num_classes");
+  DSKD_REQUIRE(reduction == 1 || reduction == 2, "dskd_bcdd_distance_loss: reduction must be 1 (mean) or 2 (sum)");
+  cudaStream_t st = as_stream(stream);
+  // loss = w * red * sum((D_T-D_S)^2) / L, red = 1/L^2 (mean) or 1 (sum)
+  const double red = (reduction == 1) ? 1.0 / ((double)L * (double)L) : 1.0;
+  const float factor = (float)((double)loss_weight * red / (double)L);
+  const float gcoef = 2.f * factor;  // d loss / d D_S = -gcoef * (D_T - D_S)
+  if (d_grad_proto_student != nullptr)
+    DSKD_CUDA_OK(cudaMemsetAsync(d_grad_proto_student, 0, sizeof(float) * (size_t)num_classes * (C + 1), st));
+  const size_t smem = sizeof(float) * (2 * (size_t)C + L);
+  bcdd_distance_kernel<<<L, 256, smem, st>>>(d_proto, num_classes, C, L, gcoef, grad_scale, d_dist, d_grad_proto_student);
+  DSKD_LAUNCH_OK("bcdd_distance_kernel");
+  bcdd_loss_kernel<<<1, 256, 0, st>>>(d_dist, L, factor, d_loss);
+  DSKD_LAUNCH_OK("bcdd_loss_kernel");
+  return DSKD_OK;
+}
+
+extern "C" int dskd_bcdd_scatter_grad(const float* d_grad_proto_student, const int64_t* d_student_labels,
+                                      int32_t num_student_rows, const uint8_t* d_prev_mask, int32_t num_classes,
+                                      int32_t C, float* d_grad_hs_student, void* stream) {
+  DSKD_REQUIRE(num_student_rows >= 0 && C > 0 && num_classes > 0, "dskd_bcdd_scatter_grad: bad sizes");
+  if (num_student_rows == 0) return DSKD_OK;
+  DSKD_REQUIRE(d_grad_proto_student && d_student_labels && d_prev_mask && d_grad_hs_student,
+               "dskd_bcdd_scatter_grad: null pointer");
+  bcdd_scatter_kernel<<<num_student_rows, 256, 0, as_stream(stream)>>>(
+      d_grad_proto_student, d_student_labels, num_student_rows, d_prev_mask, num_classes, C, d_grad_hs_student);
+  DSKD_LAUNCH_OK("bcdd_scatter_kernel");
+  return DSKD_OK;
+}

@@ -1,0 +1,244 @@
+// Mask construction for DSG-FD: per-pair channel rows (softmax of |hs_T - hs_S|), their backward,
+// and the cell rasters (last-writer-wins owner map, binary / area cell weights).
+// Reference: gfl_deformable_detr_head_il.py:685-706 (decode_v1), :742-756 (decode_v2),
+// :883-914 (sg_out), :1107-1122 (fg_only); gfl_deformable_detr_head_il_fg_bk.py:548-566 (fg_bk).
+#include "common.cuh"
+
+namespace dskd {
+
+// One CTA per (teacher, student) query pair.  C floats of dynamic shared memory.
+template <int MODE>
+__global__ void __launch_bounds__(128) mask_rows_kernel(const float* __restrict__ hs_t,
+                                                        const float* __restrict__ hs_s,
+                                                        const int64_t* __restrict__ id_soft,
+                                                        const int64_t* __restrict__ id_pred, int C,
+                                                        float* __restrict__ rows) {
+  extern __shared__ float a[];
+  __shared__ float red[32];
+  __shared__ float bcast;
+  const int p = blockIdx.x;
+  const float* t = hs_t + id_soft[p] * (int64_t)C;
+  const float* s = (MODE == DSKD_MASK_DECODE_V1) ? hs_s + id_pred[p] * (int64_t)C : nullptr;
+  float mx = -INFINITY;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float v = (MODE == DSKD_MASK_DECODE_V1) ? fabsf(t[c] - s[c]) : t[c];
+    a[c] = v;
+    mx = fmaxf(mx, v);
+  }
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = red[0];
+    for (int w = 1; w < (blockDim.x >> 5); ++w) m = fmaxf(m, red[w]);
+    bcast = m;
+  }
+  __syncthreads();
+  mx = bcast;
+  float sum = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float e = expf(a[c] - mx);
+    a[c] = e;
+    sum += e;
+  }
+  __syncthreads();
+  sum = block_sum(sum, red);
+  if (threadIdx.x == 0) bcast = sum;
+  __syncthreads();
+  sum = bcast;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) rows[(int64_t)p * C + c] = a[c] / sum;
+}
+
+// d a = A * (g - <g, A>),  d hs_S = -sign(hs_T - hs_S) * d a   (softmax, abs, and the minus of T - S).
+__global__ void __launch_bounds__(128) mask_rows_bwd_kernel(const float* __restrict__ hs_t,
+                                                            const float* __restrict__ hs_s,
+                                                            const int64_t* __restrict__ id_soft,
+                                                            const int64_t* __restrict__ id_pred,
+                                                            const float* __restrict__ rows,
+                                                            const float* __restrict__ grad_rows, int C,
+                                                            float* __restrict__ grad_hs_s) {
+  __shared__ float red[32];
+  __shared__ float bcast;
+  const int p = blockIdx.x;
+  const float* A = rows + (int64_t)p * C;
+  const float* g = grad_rows + (int64_t)p * C;
+  float dot = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) dot += A[c] * g[c];
+  dot = block_sum(dot, red);
+  if (threadIdx.x == 0) bcast = dot;
+  __syncthreads();
+  dot = bcast;
+  const int64_t qs = id_pred[p];
+  const float* t = hs_t + id_soft[p] * (int64_t)C;
+  const float* s = hs_s + qs * (int64_t)C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float da = A[c] * (g[c] - dot);
+    const float delta = t[c] - s[c];
+    const float sgn = (delta > 0.f) ? 1.f : ((delta < 0.f) ? -1.f : 0.f);
+    atomicAdd(grad_hs_s + qs * (int64_t)C + c, -sgn * da);
+  }
+}
+
+struct RasterParams {
+  DskdLevel levels[DSKD_MAX_LEVELS];
+  int num_levels;
+};
+
+struct Rect {
+  int wmin, wmax, hmin, hmax;  // as computed by the reference (before inclusive/exclusive use)
+  float area;
+};
+
+// head_il.py:688-696: x / img_w * W in fp32 (IEEE division, no contraction), floor / ceil, .int()
+__device__ __forceinline__ Rect make_rect(const float* b, int img_h, int img_w, int H, int W, bool swap_scale) {
+  const float sx = swap_scale ? (float)H : (float)W;
+  const float sy = swap_scale ? (float)W : (float)H;
+  Rect r;
+  r.wmin = (int)floorf(__fmul_rn(__fdiv_rn(b[0], (float)img_w), sx));
+  r.wmax = (int)ceilf(__fmul_rn(__fdiv_rn(b[2], (float)img_w), sx));
+  r.hmin = (int)floorf(__fmul_rn(__fdiv_rn(b[1], (float)img_h), sy));
+  r.hmax = (int)ceilf(__fmul_rn(__fdiv_rn(b[3], (float)img_h), sy));
+  // area = 1.0 / (hmax + 1 - hmin) / (wmax + 1 - wmin)   (head_il.py:1113-1114)
+  r.area = __fdiv_rn(__fdiv_rn(1.0f, (float)(r.hmax + 1 - r.hmin)), (float)(r.wmax + 1 - r.wmin));
+  return r;
+}
+
+// grid (cell tiles, N); dynamic smem: (boxes_i + gts_i) * num_levels Rects.
+template <int MODE>
+__global__ void __launch_bounds__(256) raster_kernel(const float* __restrict__ boxes,
+                                                     const int* __restrict__ box_start,
+                                                     const float* __restrict__ gt_boxes,
+                                                     const int* __restrict__ gt_start,
+                                                     const int* __restrict__ img_hw, RasterParams prm,
+                                                     int64_t cells_per_image, void* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Rect* rects = reinterpret_cast<Rect*>(smem_raw);
+  const int i = blockIdx.y;
+  const int b0 = box_start[i], nb = box_start[i + 1] - b0;
+  const int g0 = (MODE == DSKD_RASTER_BINARY_INCL) ? gt_start[i] : 0;
+  const int ng = (MODE == DSKD_RASTER_BINARY_INCL) ? gt_start[i + 1] - g0 : 0;
+  const int img_h = img_hw[2 * i], img_w = img_hw[2 * i + 1];
+  const int per_level = nb + ng;
+  for (int k = threadIdx.x; k < per_level * prm.num_levels; k += blockDim.x) {
+    const int l = k / per_level, j = k - l * per_level;
+    const float* b = (j < nb) ? boxes + (int64_t)(b0 + j) * 4 : gt_boxes + (int64_t)(g0 + j - nb) * 4;
+    rects[k] = make_rect(b, img_h, img_w, prm.levels[l].H, prm.levels[l].W, MODE == DSKD_RASTER_AREA_FGBK);
+  }
+  __syncthreads();
+  const int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= cells_per_image) return;
+  int l = 0;
+#pragma unroll
+  for (int k = 1; k < DSKD_MAX_LEVELS; ++k)
+    if (k < prm.num_levels && cell >= prm.levels[k].cell_offset) l = k;
+  const int W = prm.levels[l].W;
+  const int local = (int)(cell - prm.levels[l].cell_offset);
+  const int h = local / W, w = local - h * W;
+  const Rect* R = rects + l * per_level;
+  if (MODE == DSKD_RASTER_OWNER_EXCL) {
+    int owner = -1;
+    for (int j = nb - 1; j >= 0; --j) {
+      const Rect r = R[j];
+      if (h >= r.hmin && h < r.hmax && w >= r.wmin && w < r.wmax) { owner = b0 + j; break; }
+    }
+    reinterpret_cast<int*>(out)[(int64_t)i * cells_per_image + cell] = owner;
+  } else if (MODE == DSKD_RASTER_BINARY_INCL) {
+    float m = 0.f;
+    for (int j = 0; j < nb; ++j) {
+      const Rect r = R[j];
+      if (h >= r.hmin && h <= r.hmax && w >= r.wmin && w <= r.wmax) { m = 1.f; break; }
+    }
+    for (int j = nb; j < per_level && m != 0.f; ++j) {
+      const Rect r = R[j];
+      if (h >= r.hmin && h <= r.hmax && w >= r.wmin && w <= r.wmax) m = 0.f;
+    }
+    reinterpret_cast<float*>(out)[(int64_t)i * cells_per_image + cell] = m;  // sqrt(0/1) == itself
+  } else {
+    float m = 0.f;
+    for (int j = 0; j < nb; ++j) {
+      const Rect r = R[j];
+      if (h >= r.hmin && h <= r.hmax && w >= r.wmin && w <= r.wmax) m = fmaxf(m, r.area);
+    }
+    reinterpret_cast<float*>(out)[(int64_t)i * cells_per_image + cell] = sqrtf(m);
+  }
+}
+
+}  // namespace dskd
+
+using namespace dskd;
+
+extern "C" int dskd_mask_rows(int32_t mode, const float* d_hs_teacher, const float* d_hs_student,
+                              const int64_t* d_id_soft, const int64_t* d_id_pred, int32_t num_pairs,
+                              int32_t C, float* d_rows, void* stream) {
+  DSKD_REQUIRE(mode == DSKD_MASK_DECODE_V1 || mode == DSKD_MASK_DECODE_V2, "dskd_mask_rows: bad mode %d", mode);
+  DSKD_REQUIRE(num_pairs >= 0 && C > 0 && C <= 8192, "dskd_mask_rows: bad sizes pairs=%d C=%d", num_pairs, C);
+  if (num_pairs == 0) return DSKD_OK;
+  DSKD_REQUIRE(d_hs_teacher && d_id_soft && d_rows, "dskd_mask_rows: null pointer");
+  DSKD_REQUIRE(mode == DSKD_MASK_DECODE_V2 || (d_hs_student && d_id_pred), "dskd_mask_rows: decode_v1 needs the student side");
+  const size_t smem = (size_t)C * sizeof(float);
+  if (mode == DSKD_MASK_DECODE_V1)
+    mask_rows_kernel<DSKD_MASK_DECODE_V1><<<num_pairs, 128, smem, as_stream(stream)>>>(
+        d_hs_teacher, d_hs_student, d_id_soft, d_id_pred, C, d_rows);
+  else
+    mask_rows_kernel<DSKD_MASK_DECODE_V2><<<num_pairs, 128, smem, as_stream(stream)>>>(
+        d_hs_teacher, nullptr, d_id_soft, nullptr, C, d_rows);
+  DSKD_LAUNCH_OK("mask_rows_kernel");
+  return DSKD_OK;
+}
+
+extern "C" int dskd_mask_rows_bwd(const float* d_hs_teacher, const float* d_hs_student,
+                                  const int64_t* d_id_soft, const int64_t* d_id_pred, const float* d_rows,
+                                  const float* d_grad_rows, int32_t num_pairs, int32_t C,
+                                  float* d_grad_hs_student, void* stream) {
+  DSKD_REQUIRE(num_pairs >= 0 && C > 0, "dskd_mask_rows_bwd: bad sizes");
+  if (num_pairs == 0) return DSKD_OK;
+  DSKD_REQUIRE(d_hs_teacher && d_hs_student && d_id_soft && d_id_pred && d_rows && d_grad_rows && d_grad_hs_student,
+               "dskd_mask_rows_bwd: null pointer");
+  mask_rows_bwd_kernel<<<num_pairs, 128, 0, as_stream(stream)>>>(d_hs_teacher, d_hs_student, d_id_soft, d_id_pred,
+                                                                 d_rows, d_grad_rows, C, d_grad_hs_student);
+  DSKD_LAUNCH_OK("mask_rows_bwd_kernel");
+  return DSKD_OK;
+}
+
+extern "C" int dskd_raster_cells(int32_t mode, const float* d_boxes, const int32_t* d_box_start,
+                                 const float* d_gt_boxes, const int32_t* d_gt_start, const int32_t* d_img_hw,
+                                 int32_t N, int32_t max_boxes_per_image, const DskdLevel* levels,
+                                 int32_t num_levels, int64_t cells_per_image, void* d_out, void* stream) {
+  DSKD_REQUIRE(mode >= DSKD_RASTER_OWNER_EXCL && mode <= DSKD_RASTER_AREA_FGBK, "dskd_raster_cells: bad mode %d", mode);
+  DSKD_REQUIRE(N >= 0 && num_levels > 0 && num_levels <= DSKD_MAX_LEVELS && cells_per_image > 0 && levels,
+               "dskd_raster_cells: bad sizes");
+  if (N == 0) return DSKD_OK;
+  DSKD_REQUIRE(d_box_start && d_img_hw && d_out && (d_boxes || max_boxes_per_image == 0), "dskd_raster_cells: null pointer");
+  DSKD_REQUIRE(mode != DSKD_RASTER_BINARY_INCL || d_gt_start, "dskd_raster_cells: sg_out needs GT boxes");
+  RasterParams prm;
+  prm.num_levels = num_levels;
+  int64_t cells = 0;
+  for (int l = 0; l < num_levels; ++l) {
+    prm.levels[l] = levels[l];
+    DSKD_REQUIRE(levels[l].H > 0 && levels[l].W > 0 && levels[l].cell_offset == cells,
+                 "dskd_raster_cells: level %d is not densely packed", l);
+    cells += (int64_t)levels[l].H * levels[l].W;
+  }
+  DSKD_REQUIRE(cells == cells_per_image, "dskd_raster_cells: cells_per_image %lld != sum H*W %lld",
+               (long long)cells_per_image, (long long)cells);
+  const size_t smem = (size_t)max_boxes_per_image * num_levels * sizeof(Rect);
+  DSKD_REQUIRE(smem <= 200 * 1024, "dskd_raster_cells: too many boxes per image (%d)", max_boxes_per_image);
+  dim3 grid((unsigned)ceil_div(cells_per_image, 256), (unsigned)N);
+  cudaStream_t st = as_stream(stream);
+#define DSKD_RASTER_LAUNCH(M)                                                                              \
+  do {                                                                                                     \
+    if (smem > 48 * 1024)                                                                                  \
+      DSKD_CUDA_OK(cudaFuncSetAttribute(raster_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    raster_kernel<M><<<grid, 256, smem, st>>>(d_boxes, d_box_start, d_gt_boxes, d_gt_start, d_img_hw, prm,   \
+                                              cells_per_image, d_out);                                      \
+  } while (0)
+  switch (mode) {
+    case DSKD_RASTER_OWNER_EXCL: DSKD_RASTER_LAUNCH(DSKD_RASTER_OWNER_EXCL); break;
+    case DSKD_RASTER_BINARY_INCL: DSKD_RASTER_LAUNCH(DSKD_RASTER_BINARY_INCL); break;
+    case DSKD_RASTER_AREA_INCL: DSKD_RASTER_LAUNCH(DSKD_RASTER_AREA_INCL); break;
+    default: DSKD_RASTER_LAUNCH(DSKD_RASTER_AREA_FGBK); break;
+  }
+#undef DSKD_RASTER_LAUNCH
+  DSKD_LAUNCH_OK("raster_kernel");
+  return DSKD_OK;
+}

@@ -1,0 +1,602 @@
+"""Drop-in loss modules for DSKD's distillation hot path, backed by libdskd_b200.so (sm_100a).
+
+The reference computes both losses inline in `GFLDeformableDETRHead_il.loss`
+(mmdet/models/dense_heads/gfl_deformable_detr_head_il.py):
+  * DSG-FD  `decode_v1` :664-719 (+ `decode_v2` :721-772, `sg_out` :860-925, `fg_only` :1082-1129,
+    `_fg_bk.py:534-578,611-625`), reduced by `self.loss_fg_feature`
+  * BCDD    prototypes :525-552 + `correlation_mat` :1197-1222, reduced by `self.loss_corr`
+and reduces them with registry modules (mmdet/models/losses/mse_loss.py, kd_loss.py, utils.py).
+Here each loss is one registry module with the reference's ctor convention
+(`loss_weight`, `reduction`, `T`) and
+    forward(student_feats, teacher_feats, queries, assignments,
+            weight=None, avg_factor=None, reduction_override=None)
+All arithmetic runs in hand-written CUDA kernels through the C ABI (include/dskd_b200.h); PyTorch
+only owns the memory, the stream and autograd's bookkeeping.  There is no CPU path.
+"""
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from .registry import LOSSES
+
+_REDUCTIONS = (None, 'none', 'mean', 'sum')
+EPS32 = float(torch.finfo(torch.float32).eps)
+
+
+# ----------------------------------------------------------------------------------------------
+# small host helpers
+# ----------------------------------------------------------------------------------------------
+def _resolve_reduction(module_reduction, override, avg_factor):
+    """mse_loss.py:52-54 / kd_loss.py:82-84 / utils.py:42-59 semantics (asserts included)."""
+    assert override in _REDUCTIONS
+    reduction = override if override else module_reduction
+    if avg_factor is not None and reduction == 'sum':
+        raise ValueError('avg_factor can not be used with reduction="sum"')
+    return reduction
+
+
+class _PrevMaskCache:
+    """uint8[num_classes] device flag table for `task_labels['prev']` (head_il.py:530-532,1453-1455)."""
+
+    def __init__(self):
+        self._cache = {}
+
+    def get(self, prev_labels, num_classes, device):
+        key = (tuple(int(x) for x in prev_labels), int(num_classes), str(device))
+        t = self._cache.get(key)
+        if t is None:
+            host = torch.zeros(num_classes, dtype=torch.uint8)
+            for lab in key[0]:
+                if 0 <= lab < num_classes:
+                    host[lab] = 1
+            t = host.to(device)
+            self._cache[key] = t
+        return t
+
+
+_prev_masks = _PrevMaskCache()
+
+
+def _img_hw_list(assignments, n):
+    hw = assignments['img_shapes']
+    if isinstance(hw, torch.Tensor):
+        hw = hw.tolist()
+    hw = [(int(s[0]), int(s[1])) for s in hw]
+    if len(hw) != n:
+        raise L.DskdError(f'img_shapes has {len(hw)} entries for {n} images')
+    return hw
+
+
+def _box_meta(boxes: Sequence[torch.Tensor], img_hw, device, gt_boxes=None):
+    """Concatenate per-image boxes and upload the tiny int32 tables in ONE copy.
+
+    Returns (boxes[P,4], box_start[N+1], img_hw[N,2], max_per_image, gt[G,4] | None, gt_start | None)."""
+    n = len(boxes)
+    lens = [int(b.shape[0]) for b in boxes]
+    start = [0]
+    for k in lens:
+        start.append(start[-1] + k)
+    meta = list(start) + [v for hw in img_hw for v in hw]
+    max_per = max(lens) if lens else 0
+    gstart = None
+    if gt_boxes is not None:
+        glens = [int(b.shape[0]) for b in gt_boxes]
+        gstart = [0]
+        for k in glens:
+            gstart.append(gstart[-1] + k)
+        meta += gstart
+        max_per = max([a + b for a, b in zip(lens, glens)] or [0])
+    meta_t = torch.tensor(meta, dtype=torch.int32).to(device, non_blocking=True)
+    cat = L.f32c(torch.cat([b.reshape(-1, 4) for b in boxes], 0)) if n else torch.zeros(0, 4, device=device)
+    gt_cat = None
+    gt_start_t = None
+    if gt_boxes is not None:
+        gt_cat = L.f32c(torch.cat([b.reshape(-1, 4) for b in gt_boxes], 0))
+        gt_start_t = meta_t[3 * n + 1:]
+    return cat, meta_t[:n + 1], meta_t[n + 1:3 * n + 1], max_per, gt_cat, gt_start_t
+
+
+def _scale_by_grad_output(buf: Optional[torch.Tensor], grad_out: torch.Tensor):
+    if buf is None or buf.numel() == 0:
+        return
+    L.check(L.load().dskd_scale_inplace(L.ptr(buf), buf.numel(), L.ptr(grad_out), L.stream_of(buf)),
+            'dskd_scale_inplace')
+
+
+def _as_scalar_grad(grad_out: torch.Tensor):
+    g = grad_out.detach()
+    if g.dtype != torch.float32:
+        g = g.float()
+    return g.reshape(1).contiguous()
+
+
+# ----------------------------------------------------------------------------------------------
+# DSG-FD
+# ----------------------------------------------------------------------------------------------
+class _DsgfdPlan:
+    """Everything the fused kernels need besides the differentiable tensors."""
+    __slots__ = ('criterion', 'mask_mode', 'layout', 'shapes', 'N', 'C', 'scales', 'temperature',
+                 'keepid', 'labels', 'prev_mask', 'num_classes', 'boxes', 'box_start', 'img_hw',
+                 'max_boxes', 'gt_boxes', 'gt_start', 'num_pairs', 'validate')
+
+
+_ROW_MODES = {'decode_v1': L.MASK_DECODE_V1, 'decode_v2': L.MASK_DECODE_V2}
+_CELL_MODES = {'sg_out': L.RASTER_BINARY_INCL, 'fg_only': L.RASTER_AREA_INCL, 'fg_bk': L.RASTER_AREA_FGBK}
+
+
+class _DsgfdFn(torch.autograd.Function):
+    """Fused forward+backward: the kernels stage gradients for grad_output == 1 during forward and
+    `backward` rescales them in place on the device only when grad_output != 1 (no host sync)."""
+
+    @staticmethod
+    def forward(ctx, plan: _DsgfdPlan, hs_student, hs_teacher, *feats):
+        lib = L.load()
+        nl = len(feats) // 2
+        s_feats, t_feats = feats[:nl], feats[nl:]
+        dev = s_feats[0].device
+        st = L.stream_of(s_feats[0])
+        C, N = plan.C, plan.N
+        levels, cells = L.levels_struct(plan.shapes)
+        row_mode = plan.mask_mode in _ROW_MODES
+        want_feat_grad = plan.criterion == 'mse' and any(ctx.needs_input_grad[3:3 + nl])
+        want_hs_grad = plan.mask_mode == 'decode_v1' and ctx.needs_input_grad[1]
+
+        # ---- masks
+        rows = id_pred = owner = cellw = None
+        P = plan.num_pairs
+        if row_mode:
+            hs_s2 = hs_student.reshape(-1, C)
+            hs_t2 = hs_teacher.reshape(-1, C)
+            if plan.mask_mode == 'decode_v1':
+                id_pred = torch.empty(max(P, 1), dtype=torch.int64, device=dev)
+                count = torch.empty(1, dtype=torch.int32, device=dev)
+                L.check(lib.dskd_select_prev_queries(L.ptr(plan.labels), plan.labels.numel(), L.ptr(plan.prev_mask),
+                                                     plan.num_classes, P, L.ptr(id_pred), L.ptr(count), st),
+                        'dskd_select_prev_queries')
+                if plan.validate and int(count.item()) < P:      # the reference raises IndexError here (:705)
+                    raise IndexError(f'{int(count.item())} student queries carry a previous-task label but '
+                                     f'{P} teacher detections must be paired (head_il.py:705)')
+            rows = torch.empty(max(P, 1), C, dtype=torch.float32, device=dev)
+            L.check(lib.dskd_mask_rows(_ROW_MODES[plan.mask_mode], L.ptr(hs_t2), L.ptr(hs_s2), L.ptr(plan.keepid),
+                                       L.ptr(id_pred), P, C, L.ptr(rows), st), 'dskd_mask_rows')
+            owner = torch.empty(N, cells, dtype=torch.int32, device=dev)
+            L.check(lib.dskd_raster_cells(L.RASTER_OWNER_EXCL, L.ptr(plan.boxes), L.ptr(plan.box_start), None, None,
+                                          L.ptr(plan.img_hw), N, plan.max_boxes, levels, len(plan.shapes), cells,
+                                          L.ptr(owner), st), 'dskd_raster_cells')
+        else:
+            cellw = torch.empty(N, cells, dtype=torch.float32, device=dev)
+            L.check(lib.dskd_raster_cells(_CELL_MODES[plan.mask_mode], L.ptr(plan.boxes), L.ptr(plan.box_start),
+                                          L.ptr(plan.gt_boxes), L.ptr(plan.gt_start), L.ptr(plan.img_hw), N,
+                                          plan.max_boxes, levels, len(plan.shapes), cells, L.ptr(cellw), st),
+                    'dskd_raster_cells')
+
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        grad_feats: List[Optional[torch.Tensor]] = [None] * nl
+        grad_rows = None
+        if plan.criterion == 'mse':
+            a = L.DsgfdMseArgs()
+            a.layout, a.num_levels, a.N, a.C = plan.layout, len(plan.shapes), N, C
+            a.levels = levels
+            a.cells_per_image = cells
+            if want_feat_grad:
+                # one allocation for every level, each level 16-byte aligned
+                sizes = [f.numel() for f in s_feats]
+                offs, tot = [], 0
+                for s in sizes:
+                    offs.append(tot)
+                    tot += (s + 3) // 4 * 4
+                flat = torch.empty(tot, dtype=torch.float32, device=dev)
+                grad_feats = [flat[o:o + s].view_as(f) for o, s, f in zip(offs, sizes, s_feats)]
+            for l in range(nl):
+                a.d_student[l] = s_feats[l].data_ptr()
+                a.d_teacher[l] = t_feats[l].data_ptr()
+                a.d_grad_student[l] = grad_feats[l].data_ptr() if grad_feats[l] is not None else None
+            for l, s in enumerate(plan.scales):
+                a.scale[l] = s
+            if row_mode:
+                energy = torch.zeros(max(P, 1), C, dtype=torch.float32, device=dev)
+                a.d_owner, a.d_rows, a.d_energy, a.num_pairs = owner.data_ptr(), rows.data_ptr(), energy.data_ptr(), P
+                L.check(lib.dskd_dsgfd_mse_fwd_bwd(a, st), 'dskd_dsgfd_mse_fwd_bwd')
+                # loss = sum rows^2 * energy ; d loss / d rows = 2 * rows * energy (in place over energy)
+                L.check(lib.dskd_dsgfd_mse_finish(L.ptr(rows), L.ptr(energy), P, C, L.ptr(loss),
+                                                  L.ptr(energy) if want_hs_grad else None, st), 'dskd_dsgfd_mse_finish')
+                grad_rows = energy
+            else:
+                acc = torch.zeros(1, dtype=torch.float64, device=dev)
+                a.d_cell_weight, a.d_loss = cellw.data_ptr(), acc.data_ptr()
+                L.check(lib.dskd_dsgfd_mse_fwd_bwd(a, st), 'dskd_dsgfd_mse_fwd_bwd')
+                L.check(lib.dskd_f64_to_f32(L.ptr(acc), L.ptr(loss), 1, 1.0, st), 'dskd_f64_to_f32')
+        else:
+            a = L.DsgfdKlArgs()
+            a.num_levels, a.N, a.C = len(plan.shapes), N, C
+            a.levels = levels
+            a.cells_per_image = cells
+            a.temperature = plan.temperature
+            for l in range(nl):
+                a.d_student[l] = s_feats[l].data_ptr()
+                a.d_teacher[l] = t_feats[l].data_ptr()
+            for l, s in enumerate(plan.scales):
+                a.scale[l] = s
+            acc = torch.zeros(1, dtype=torch.float64, device=dev)
+            a.d_loss = acc.data_ptr()
+            if row_mode:
+                a.d_owner, a.d_rows, a.num_pairs = owner.data_ptr(), rows.data_ptr(), P
+                if want_hs_grad:
+                    grad_rows = torch.zeros(max(P, 1), C, dtype=torch.float32, device=dev)
+                    a.d_grad_rows = grad_rows.data_ptr()
+            else:
+                a.d_cell_weight = cellw.data_ptr()
+            L.check(lib.dskd_dsgfd_kl_fwd_bwd(a, st), 'dskd_dsgfd_kl_fwd_bwd')
+            L.check(lib.dskd_f64_to_f32(L.ptr(acc), L.ptr(loss), 1, 1.0, st), 'dskd_f64_to_f32')
+
+        grad_hs = None
+        if want_hs_grad:
+            grad_hs = torch.zeros_like(hs_student, dtype=torch.float32).contiguous()
+            L.check(lib.dskd_mask_rows_bwd(L.ptr(hs_t2), L.ptr(hs_s2), L.ptr(plan.keepid), L.ptr(id_pred), L.ptr(rows),
+                                           L.ptr(grad_rows), P, C, L.ptr(grad_hs), st), 'dskd_mask_rows_bwd')
+        ctx.staged = (grad_hs, grad_feats)
+        ctx.nl = nl
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        if ctx.staged is None:
+            raise RuntimeError('DSGFeatureDistillLoss: the staged gradients were already consumed; the fused '
+                               'forward+backward kernel supports a single backward pass per forward.')
+        grad_hs, grad_feats = ctx.staged
+        ctx.staged = None
+        g = _as_scalar_grad(grad_out)
+        _scale_by_grad_output(grad_hs, g)
+        if any(gf is not None for gf in grad_feats):
+            first = next(gf for gf in grad_feats if gf is not None)
+            base = first._base if first._base is not None else first
+            _scale_by_grad_output(base, g)
+        return (None, grad_hs, None, *grad_feats, *([None] * ctx.nl))
+
+
+@LOSSES.register_module()
+class DSGFeatureDistillLoss(nn.Module):
+    """Dynamically Semantic-Guided Feature Distillation (gfl_deformable_detr_head_il.py:664-719).
+
+    Args:
+        loss_weight (float): weight of the loss (mse_loss.py:24, kd_loss.py:55).
+        reduction (str): 'sum' (every shipped config) or 'mean' -- applied per (level, image) call
+            like the reference's `self.loss_fg_feature(fg_fea_s, fg_fea_t)` (:715).
+        criterion (str): 'mse' (`MSELoss`, mse_loss.py) or 'kl' (`KnowledgeDistillationKLDivLoss`
+            over the H axis, kd_loss.py:28-34 on [C,H,W]).
+        T (float): KL temperature (kd_loss.py:58 asserts T >= 1).
+        mask_mode (str): 'decode_v1' (:664-719), 'decode_v2' (:721-772), 'sg_out' (:860-925),
+            'fg_only' (:1082-1129), 'fg_bk' (_fg_bk.py:534-578).
+        feature_source (str): 'neck' -- 4 x [N,C,H,W] (:678-679); 'memory' -- ([S,N,C], spatial_shapes)
+            (:866-880).  decode_* + 'kl' supports 'neck' only.
+        validate (bool): read the matched-query count back (one host sync) and raise IndexError like
+            the reference (:705) when fewer student queries than teacher detections carry a previous label.
+    """
+
+    def __init__(self, loss_weight=1.0, reduction='sum', criterion='mse', T=2.0, mask_mode='decode_v1',
+                 feature_source='neck', validate=False):
+        super().__init__()
+        assert criterion in ('mse', 'kl'), criterion
+        assert mask_mode in _ROW_MODES or mask_mode in _CELL_MODES, mask_mode
+        assert feature_source in ('neck', 'memory'), feature_source
+        assert T >= 1
+        if mask_mode == 'fg_bk' and (criterion != 'mse' or feature_source != 'memory'):
+            raise ValueError("mask_mode='fg_bk' is the area-mask MSE on encoder memory (_fg_bk.py:534-578)")
+        if criterion == 'kl' and feature_source != 'neck':
+            raise NotImplementedError("criterion='kl' is implemented for the [N,C,H,W] layout "
+                                      "(pass the per-level views of the memory as feature_source='neck')")
+        self.loss_weight = loss_weight
+        self.reduction = reduction
+        self.criterion = criterion
+        self.T = float(T)
+        self.mask_mode = mask_mode
+        self.feature_source = feature_source
+        self.validate = validate
+
+    def extra_repr(self):
+        return (f'criterion={self.criterion}, mask_mode={self.mask_mode}, feature_source={self.feature_source}, '
+                f'reduction={self.reduction}, loss_weight={self.loss_weight}, T={self.T}')
+
+    def forward(self, student_feats, teacher_feats, queries, assignments, weight=None, avg_factor=None,
+                reduction_override=None):
+        reduction = _resolve_reduction(self.reduction, reduction_override, avg_factor)
+        if reduction == 'none':
+            raise NotImplementedError("reduction='none' cannot be accumulated over levels of different shapes "
+                                      '(the reference head would raise at head_il.py:715 as well)')
+        if weight is not None:
+            raise NotImplementedError('the head always calls loss_fg_feature with weight=None (head_il.py:715)')
+        hs_student, hs_teacher = queries
+        plan = _DsgfdPlan()
+        plan.criterion, plan.mask_mode = self.criterion, self.mask_mode
+        plan.temperature, plan.validate = self.T, self.validate
+
+        # ---- features
+        if self.feature_source == 'neck':
+            s_feats = [L.f32c(f) for f in student_feats]
+            t_feats = [L.f32c(f.detach()) for f in teacher_feats]
+            plan.layout = L.LAYOUT_NCHW
+            plan.shapes = [tuple(f.shape[2:]) for f in s_feats]
+            N, C = s_feats[0].shape[:2]
+            for fs, ft in zip(s_feats, t_feats):
+                if fs.shape != ft.shape or fs.shape[:2] != (N, C):
+                    raise L.DskdError(f'student / teacher feature shapes differ: {tuple(fs.shape)} vs {tuple(ft.shape)}')
+        else:
+            (s_mem, shapes), (t_mem, _) = student_feats, teacher_feats
+            s_feats, t_feats = [L.f32c(s_mem)], [L.f32c(t_mem.detach())]
+            if isinstance(shapes, torch.Tensor):
+                shapes = shapes.tolist()
+            plan.layout = L.LAYOUT_SNC
+            plan.shapes = [(int(h), int(w)) for h, w in shapes]
+            S, N, C = s_feats[0].shape
+            if S != sum(h * w for h, w in plan.shapes) or t_feats[0].shape != s_feats[0].shape:
+                raise L.DskdError('memory must be [sum(H*W), N, C] for both student and teacher')
+        dev = s_feats[0].device
+        L.require_device(s_feats[0])
+        plan.N, plan.C = int(N), int(C)
+
+        # ---- per-level scale: loss_weight, the 1/N of :716-717, the reduction and avg_factor
+        base = float(self.loss_weight) / float(N)
+        scales = []
+        total_cells = sum(h * w for h, w in plan.shapes)
+        for (h, w) in plan.shapes:
+            if reduction == 'sum':
+                r = 1.0
+            elif avg_factor is not None:
+                r = 1.0 / (float(avg_factor) + EPS32)
+            elif self.criterion == 'mse':
+                r = 1.0 / float(C * (total_cells if self.mask_mode == 'fg_bk' else h * w))
+            else:
+                r = 1.0 / float(C * w)          # kd loss tensor is [C, W] after .mean(1) (kd_loss.py:32-34)
+            if self.mask_mode == 'fg_bk':
+                r /= float(C)                    # `/ len(Mask_fg)` == C  (_fg_bk.py:620)
+            scales.append(base * r)
+        plan.scales = scales
+
+        # ---- assignments
+        img_hw = _img_hw_list(assignments, N)
+        gt = assignments.get('gt_bboxes') if self.mask_mode == 'sg_out' else None
+        if self.mask_mode == 'sg_out' and gt is None:
+            raise L.DskdError("mask_mode='sg_out' needs assignments['gt_bboxes'] (head_il.py:902-914)")
+        (plan.boxes, plan.box_start, plan.img_hw, plan.max_boxes, plan.gt_boxes, plan.gt_start) = _box_meta(
+            assignments['teacher_bboxes'], img_hw, dev, gt)
+        plan.num_pairs = int(plan.boxes.shape[0])
+        plan.keepid = plan.labels = plan.prev_mask = None
+        plan.num_classes = int(assignments.get('num_classes', 80))
+        if self.mask_mode in _ROW_MODES:
+            plan.keepid = assignments['teacher_keepid'].to(dev, torch.int64).contiguous()
+            if plan.keepid.numel() != plan.num_pairs:
+                raise L.DskdError(f'{plan.keepid.numel()} teacher keep-ids for {plan.num_pairs} teacher boxes')
+            if self.mask_mode == 'decode_v1':
+                plan.labels = assignments['student_labels'].to(dev, torch.int64).contiguous()
+                plan.prev_mask = _prev_masks.get(assignments['prev_labels'], plan.num_classes, dev)
+        hs_s = L.f32c(hs_student)
+        hs_t = L.f32c(hs_teacher.detach())
+        if hs_s.shape[-1] != C:
+            raise L.DskdError(f'embedding width {hs_s.shape[-1]} != feature channels {C} (head_il.py:706 broadcasts them)')
+        return _DsgfdFn.apply(plan, hs_s, hs_t, *s_feats, *t_feats)
+
+
+# ----------------------------------------------------------------------------------------------
+# BCDD
+# ----------------------------------------------------------------------------------------------
+class _BcddFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cfg, hs_student, hs_teacher):
+        lib = L.load()
+        (labels, keepid, t_labels, prev_mask, num_classes, num_prev, reduction, loss_weight, sync) = cfg
+        dev = hs_student.device
+        st = L.stream_of(hs_student)
+        C = hs_student.shape[-1]
+        hs_s2, hs_t2 = hs_student.reshape(-1, C), hs_teacher.reshape(-1, C)
+        proto = torch.empty(2, num_classes, C + 1, dtype=torch.float32, device=dev)
+        L.check(lib.dskd_bcdd_prototypes(L.ptr(hs_s2), L.ptr(labels), hs_s2.shape[0], L.ptr(hs_t2), L.ptr(keepid),
+                                         L.ptr(t_labels), keepid.numel(), L.ptr(prev_mask), num_classes, C,
+                                         L.ptr(proto), st), 'dskd_bcdd_prototypes')
+        grad_scale = 1.0
+        if sync and torch.distributed.is_available() and torch.distributed.is_initialized():
+            # the ONLY cross-rank state of the hot path: 2 x num_classes x (C+1) fp32 sums + counts
+            torch.distributed.all_reduce(proto, op=torch.distributed.ReduceOp.SUM)
+            grad_scale = float(torch.distributed.get_world_size())
+        want_grad = ctx.needs_input_grad[1]
+        dist = torch.empty(2, num_prev, num_prev, dtype=torch.float32, device=dev)
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        grad_proto = torch.empty(num_classes, C + 1, dtype=torch.float32, device=dev) if want_grad else None
+        L.check(lib.dskd_bcdd_distance_loss(L.ptr(proto), num_classes, C, num_prev, reduction, loss_weight, grad_scale,
+                                            L.ptr(dist), L.ptr(loss), L.ptr(grad_proto), st), 'dskd_bcdd_distance_loss')
+        grad_hs = None
+        if want_grad:
+            grad_hs = torch.empty_like(hs_student, dtype=torch.float32).contiguous()
+            L.check(lib.dskd_bcdd_scatter_grad(L.ptr(grad_proto), L.ptr(labels), hs_s2.shape[0], L.ptr(prev_mask),
+                                               num_classes, C, L.ptr(grad_hs), st), 'dskd_bcdd_scatter_grad')
+        ctx.staged = grad_hs
+        ctx.mark_non_differentiable(dist, proto)
+        return loss.reshape(()), dist, proto
+
+    @staticmethod
+    def backward(ctx, grad_out, _gd, _gp):
+        if ctx.staged is None and ctx.needs_input_grad[1]:
+            raise RuntimeError('BetweenClassDistanceLoss: staged gradients already consumed (single backward per forward)')
+        grad_hs = ctx.staged
+        ctx.staged = None
+        _scale_by_grad_output(grad_hs, _as_scalar_grad(grad_out))
+        return None, grad_hs, None
+
+
+@LOSSES.register_module()
+class BetweenClassDistanceLoss(nn.Module):
+    """Between-Class Distance Distillation (gfl_deformable_detr_head_il.py:525-555,1197-1222).
+
+    Args:
+        loss_weight, reduction: as `loss_corr=dict(type='MSELoss', loss_weight=1, reduction='mean')`
+            (chaosuan_..._40_...py:131); 'mean' and 'sum' are supported.
+        sync_prototypes (bool): all-reduce the per-class sums / counts over ranks before the distance
+            matrices.  False reproduces the reference's rank-local behaviour.
+    After a call `last_distances` ([2,L,L]: teacher, student) and `last_prototypes` ([2,classes,C+1]) hold
+    the intermediate results (detached).
+    """
+
+    def __init__(self, loss_weight=1.0, reduction='mean', sync_prototypes=False):
+        super().__init__()
+        self.loss_weight = loss_weight
+        self.reduction = reduction
+        self.sync_prototypes = sync_prototypes
+        self.last_distances = None
+        self.last_prototypes = None
+
+    def extra_repr(self):
+        return f'reduction={self.reduction}, loss_weight={self.loss_weight}, sync_prototypes={self.sync_prototypes}'
+
+    def forward(self, student_feats, teacher_feats, queries, assignments, weight=None, avg_factor=None,
+                reduction_override=None):
+        reduction = _resolve_reduction(self.reduction, reduction_override, avg_factor)
+        if reduction == 'none':
+            raise NotImplementedError("reduction='none' is not supported for BCDD (the head sums the scalar, :555)")
+        if weight is not None:
+            raise NotImplementedError('the head always calls loss_corr with weight=None (head_il.py:1220)')
+        hs_student, hs_teacher = queries
+        hs_s, hs_t = L.f32c(hs_student), L.f32c(hs_teacher.detach())
+        dev = hs_s.device
+        L.require_device(hs_s)
+        prev = list(assignments['prev_labels'])
+        num_classes = int(assignments.get('num_classes', 80))
+        num_prev = len(prev)
+        if num_prev == 0 or num_prev > num_classes:
+            raise L.DskdError(f'need 0 < len(prev_labels) <= num_classes, got {num_prev}')
+        loss_weight = float(self.loss_weight)
+        red = L.REDUCTION_SUM
+        if reduction == 'mean':
+            if avg_factor is None:
+                red = L.REDUCTION_MEAN
+            else:                                # utils.py:50-55: sum / (avg_factor + eps)
+                loss_weight = loss_weight / (float(avg_factor) + EPS32)
+        cfg = (assignments['student_labels'].to(dev, torch.int64).contiguous(),
+               assignments['teacher_keepid'].to(dev, torch.int64).contiguous(),
+               assignments['teacher_labels'].to(dev, torch.int64).contiguous(),
+               _prev_masks.get(prev, num_classes, dev), num_classes, num_prev, red, loss_weight,
+               bool(self.sync_prototypes))
+        loss, dist, proto = _BcddFn.apply(cfg, hs_s, hs_t)
+        self.last_distances, self.last_prototypes = dist, proto
+        return loss
+
+
+# ----------------------------------------------------------------------------------------------
+# The registry modules the reference head builds by config (R1-R3)
+# ----------------------------------------------------------------------------------------------
+class _ElementwiseFn(torch.autograd.Function):
+    """kind 'mse': (pred-target)^2 ; kind 'kd': KL rows over dim=1.  Returns the un-reduced loss
+    (elementwise weight applied) and its sum; gradients staged for d(sum) = 1."""
+
+    @staticmethod
+    def forward(ctx, kind, T, pred, target, weight):
+        lib = L.load()
+        ctx.set_materialize_grads(False)
+        st = L.stream_of(pred)
+        dev = pred.device
+        acc = torch.zeros(1, dtype=torch.float64, device=dev)
+        total = torch.empty(1, dtype=torch.float32, device=dev)
+        if kind == 'mse':
+            elem = torch.empty_like(pred)
+            gp = torch.empty_like(pred) if ctx.needs_input_grad[2] else None
+            gt = torch.empty_like(pred) if ctx.needs_input_grad[3] else None
+            L.check(lib.dskd_mse_elementwise(L.ptr(pred), L.ptr(target), L.ptr(weight), pred.numel(), 1.0, L.ptr(elem),
+                                             L.ptr(acc), L.ptr(gp), L.ptr(gt), st), 'dskd_mse_elementwise')
+        else:
+            outer, D = pred.shape[0], pred.shape[1]
+            inner = pred.numel() // max(outer * D, 1)
+            elem = torch.empty((outer,) + tuple(pred.shape[2:]), dtype=torch.float32, device=dev)
+            gp = torch.empty_like(pred) if ctx.needs_input_grad[2] else None
+            gt = None                                           # target is detached (kd_loss.py:29-30)
+            L.check(lib.dskd_kd_kl_rows(L.ptr(pred), L.ptr(target), outer, D, inner, T, L.ptr(weight), 1.0,
+                                        L.ptr(elem), L.ptr(acc), L.ptr(gp), st), 'dskd_kd_kl_rows')
+        L.check(lib.dskd_f64_to_f32(L.ptr(acc), L.ptr(total), 1, 1.0, st), 'dskd_f64_to_f32')
+        ctx.kind = kind
+        ctx.save_for_backward(*(t for t in (gp, gt) if t is not None))
+        ctx.has = (gp is not None, gt is not None)
+        ctx.elem_shape = elem.shape
+        ctx.pred_shape = pred.shape
+        return elem, total.reshape(())
+
+    @staticmethod
+    def backward(ctx, g_elem, g_total):
+        saved = list(ctx.saved_tensors)
+        gp = saved.pop(0) if ctx.has[0] else None
+        gt = saved.pop(0) if ctx.has[1] else None
+        # d/d elem arrives per row (kd) or per element (mse); d/d total is a scalar
+        coef = None
+        if g_elem is not None:
+            coef = g_elem if ctx.kind == 'mse' else g_elem.unsqueeze(1)
+        if g_total is not None:
+            coef = g_total if coef is None else coef + g_total
+        out_p = gp * coef if gp is not None and coef is not None else None
+        out_t = gt * coef if gt is not None and coef is not None else None
+        return None, None, out_p, out_t, None
+
+
+def _weighted_reduce(kind, T, pred, target, weight, reduction, avg_factor, loss_weight):
+    """utils.py:30-59 on top of the fused elementwise kernel."""
+    if pred.shape != target.shape:
+        raise AssertionError(f'pred {tuple(pred.shape)} and target {tuple(target.shape)} differ')   # kd_loss.py:27
+    L.require_device(pred)
+    pred_c, target_c = L.f32c(pred), L.f32c(target)
+    w = None
+    if weight is not None:
+        shape = pred.shape if kind == 'mse' else (pred.shape[0],) + tuple(pred.shape[2:])
+        w = L.f32c(weight.expand(shape)) if tuple(weight.shape) != tuple(shape) else L.f32c(weight)
+    if pred_c.numel() == 0:
+        elem = pred_c.new_zeros(pred.shape if kind == 'mse' else (pred.shape[0],) + tuple(pred.shape[2:]))
+        total = elem.sum()
+    else:
+        if kind == 'kd' and pred_c.dim() < 2:
+            raise L.DskdError('KnowledgeDistillationKLDivLoss needs at least 2 dims (softmax over dim=1)')
+        elem, total = _ElementwiseFn.apply(kind, float(T), pred_c, target_c, w)
+    if avg_factor is None:
+        if reduction == 'none':
+            out = elem
+        elif reduction == 'mean':
+            out = total / max(elem.numel(), 1) if elem.numel() else total * float('nan')
+        else:
+            out = total
+    else:
+        if reduction == 'mean':
+            out = total / (avg_factor + EPS32)
+        elif reduction == 'none':
+            out = elem
+        else:
+            raise ValueError('avg_factor can not be used with reduction="sum"')
+    return loss_weight * out
+
+
+@LOSSES.register_module()
+class MSELoss(nn.Module):
+    """mmdet/models/losses/mse_loss.py:15-57 on the CUDA kernel `dskd_mse_elementwise`."""
+
+    def __init__(self, reduction='mean', loss_weight=1.0):
+        super().__init__()
+        self.reduction = reduction
+        self.loss_weight = loss_weight
+
+    def forward(self, pred, target, weight=None, avg_factor=None, reduction_override=None):
+        assert reduction_override in _REDUCTIONS
+        reduction = reduction_override if reduction_override else self.reduction
+        return _weighted_reduce('mse', 1.0, pred, target, weight, reduction, avg_factor, self.loss_weight)
+
+
+@LOSSES.register_module()
+class KnowledgeDistillationKLDivLoss(nn.Module):
+    """mmdet/models/losses/kd_loss.py:46-94 on the CUDA kernel `dskd_kd_kl_rows` (softmax over dim=1,
+    target detached, `.mean(1) * T^2`)."""
+
+    def __init__(self, reduction='mean', loss_weight=1.0, T=10):
+        super().__init__()
+        assert T >= 1
+        self.reduction = reduction
+        self.loss_weight = loss_weight
+        self.T = T
+
+    def forward(self, pred, soft_label, weight=None, avg_factor=None, reduction_override=None):
+        assert reduction_override in _REDUCTIONS
+        reduction = reduction_override if reduction_override else self.reduction
+        return _weighted_reduce('kd', self.T, pred, soft_label.detach(), weight, reduction, avg_factor,
+                                self.loss_weight)

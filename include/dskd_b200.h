@@ -1,0 +1,253 @@
+/*
+ * dskd_b200 -- C ABI of the B200-native (sm_100a) DSKD distillation hot path.
+ *
+ * This is the drop-in boundary.  The reference (smilekitty7/DSKD) has no
+ * native code: its hot path is inline PyTorch inside
+ *   mmdet/models/dense_heads/gfl_deformable_detr_head_il.py  (`loss`, :412-1195)
+ * reduced by registry loss modules (mmdet/models/losses/{mse_loss,kd_loss,utils}.py) and fed by
+ *   mmdet/core/bbox/assigners/gfl_hungarian_assigner.py.
+ * Each entry point below names the reference lines it replaces.  The Python host side
+ * (dskd_b200/losses.py, assigner.py) binds these with ctypes; INTEGRATION.md shows the stub a
+ * reference maintainer adds.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch / C++ types cross the boundary.
+ *   - Every pointer named `d_*` is a DEVICE pointer, `h_*` a HOST pointer.  The caller owns and
+ *     allocates every input, output and workspace; the library never allocates across the
+ *     boundary and keeps no mutable global state except a thread-local error string.
+ *   - Device entry points are asynchronous on `stream` (a cudaStream_t passed as void*), never
+ *     synchronise, and are re-entrant.  Host entry points (dskd_lsap_*) are pure CPU.
+ *   - Return 0 on success, a negative DskdStatus otherwise; dskd_last_error() describes it.
+ *     No C++ exception crosses; the library never calls exit().
+ *   - All floating point is IEEE fp32 (the reference runs the loss under force_fp32,
+ *     head_il.py:411); indices are int32 / int64 as noted; LSAP is float64 like SciPy.
+ */
+#ifndef DSKD_B200_H_
+#define DSKD_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSKD_ABI_VERSION 1
+#define DSKD_MAX_LEVELS 8
+
+typedef enum {
+  DSKD_OK = 0,
+  DSKD_EINVAL = -1,            /* bad argument (null pointer, size, alignment, enum) */
+  DSKD_ECUDA = -2,             /* a CUDA runtime call / launch failed                */
+  DSKD_EUNSUPPORTED_ARCH = -3, /* current device is not compute capability 10.x      */
+  DSKD_EINFEASIBLE = -4,       /* LSAP: cost matrix infeasible / has NaN or -inf     */
+} DskdStatus;
+
+int dskd_abi_version(void);
+const char* dskd_last_error(void);
+/* Number of CUDA kernels this library has launched in this process (statistics for bench.py). */
+uint64_t dskd_launch_count(void);
+/* DSKD_OK iff the current CUDA device is sm_100 (B200).  There is no fallback arch. */
+int dskd_check_device(void);
+
+/* One pyramid level of the 4-level feature stack (head_il.py:680-682 `N,C,H,W = features.shape`). */
+typedef struct {
+  int32_t H, W;
+  int64_t cell_offset; /* first cell of this level inside a per-image cell axis (sum of H*W of lower levels);
+                          also the token offset inside encoder memory [S,N,C] (head_il.py:869-880) */
+} DskdLevel;
+
+/* Feature storage. */
+enum { DSKD_LAYOUT_NCHW = 0,   /* per level [N,C,H,W] contiguous: neck outputs (head_il.py:678-679)      */
+       DSKD_LAYOUT_SNC = 1 };  /* one [S,N,C] contiguous tensor: encoder memory (transformer.py:1053)    */
+
+/* ---------------------------------------------------------------------------------------------
+ * Mask construction (head_il.py:685-706, :742-756, :883-914, :1107-1122; _fg_bk.py:548-566)
+ * ------------------------------------------------------------------------------------------- */
+enum { DSKD_MASK_DECODE_V1 = 0,  /* row = softmax_c(|hs_T[id_soft] - hs_S[id_pred]|)  head_il.py:705-706 */
+       DSKD_MASK_DECODE_V2 = 1 };/* row = softmax_c(hs_T[id_soft])                     head_il.py:754     */
+
+/* d_rows[p,:] for p < num_pairs.  d_hs_*: [num_rows, C]; d_id_*: int64 [num_pairs] (id_pred unused for V2). */
+int dskd_mask_rows(int32_t mode, const float* d_hs_teacher, const float* d_hs_student,
+                   const int64_t* d_id_soft, const int64_t* d_id_pred, int32_t num_pairs, int32_t C,
+                   float* d_rows, void* stream);
+
+/* Backward of dskd_mask_rows (DECODE_V1 only): given d_grad_rows = dLoss/d rows [num_pairs,C], adds
+ * dLoss/d hs_S into d_grad_hs_student[id_pred[p],:] (caller zero-fills it; id_pred entries are distinct). */
+int dskd_mask_rows_bwd(const float* d_hs_teacher, const float* d_hs_student, const int64_t* d_id_soft,
+                       const int64_t* d_id_pred, const float* d_rows, const float* d_grad_rows,
+                       int32_t num_pairs, int32_t C, float* d_grad_hs_student, void* stream);
+
+/* Matched student ids (head_il.py:1453-1455 + :672): ascending indices q < n whose assigned label is
+ * flagged in d_prev_mask (uint8[num_classes]); the first max_out of them go to d_ids (int64, the rest
+ * of d_ids is set to 0), the total count to d_count[0] (int32).  Replaces `nonzero()` without a host sync:
+ * callers that want the reference's IndexError on count < max_out read d_count back. */
+int dskd_select_prev_queries(const int64_t* d_labels, int32_t n, const uint8_t* d_prev_mask, int32_t num_classes,
+                             int32_t max_out, int64_t* d_ids, int32_t* d_count, void* stream);
+
+/* Cell raster semantics. */
+enum { DSKD_RASTER_OWNER_EXCL = 0, /* int32 owner = LAST box (highest pair index) whose half-open rect
+                                      [floor(y1/img_h*H), ceil(y2/img_h*H)) x [floor(x1..), ceil(x2..)) holds the
+                                      cell, -1 if none: the overwrite order of head_il.py:706               */
+       DSKD_RASTER_BINARY_INCL = 1,/* float 1 inside any teacher box (inclusive +1 ends), 0 inside any GT box,
+                                      sqrt: sg_out, head_il.py:898-914                                        */
+       DSKD_RASTER_AREA_INCL = 2,  /* float sqrt(max_j 1/((dh+1)(dw+1))) inclusive ends: fg_only :1107-1119  */
+       DSKD_RASTER_AREA_FGBK = 3 };/* as AREA_INCL but x scaled by H and y by W: _fg_bk.py:550-553 (sic)     */
+
+/* d_boxes: fp32 [num_boxes,4] pixel xyxy, concatenated over images; d_box_start: int32 [N+1] prefix offsets;
+ * d_gt_boxes/d_gt_start: same for the GT boxes (BINARY_INCL only, else NULL); d_img_hw: int32 [N,2] (h,w).
+ * Output d_out: int32 (OWNER_EXCL) or fp32 (others) laid out [N, cells_per_image]; cells_per_image =
+ * sum_l H_l*W_l and cell index = levels[l].cell_offset + h*W_l + w. */
+int dskd_raster_cells(int32_t mode, const float* d_boxes, const int32_t* d_box_start,
+                      const float* d_gt_boxes, const int32_t* d_gt_start, const int32_t* d_img_hw,
+                      int32_t N, int32_t max_boxes_per_image, const DskdLevel* levels, int32_t num_levels,
+                      int64_t cells_per_image, void* d_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * DSG-FD, masked MSE, fused forward + backward (head_il.py:707-718 with MSELoss, mse_loss.py:9-57)
+ *   loss = sum_{l,i,c,h,w} scale_l * M^2 * (T - S)^2,   dS = -2 * scale_l * M^2 * (T - S)
+ * scale_l carries loss_weight, the 1/N of head_il.py:716-717 and the reduction ('sum': 1, 'mean':
+ * 1/(C*H_l*W_l)).  Row-mask mode (owner + rows): also accumulates energy[p,c] = sum over the cells
+ * box p owns of scale_l*(T-S)^2, from which loss = sum rows^2*energy and dLoss/d rows = 2*rows*energy.
+ * Cell-mask mode (cell_weight): M = weight[i,cell]; the loss is accumulated into d_loss[0] (double).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t layout;               /* DSKD_LAYOUT_*                                                      */
+  int32_t num_levels, N, C;
+  DskdLevel levels[DSKD_MAX_LEVELS];
+  const float* d_student[DSKD_MAX_LEVELS]; /* NCHW: one pointer per level; SNC: [0] only             */
+  const float* d_teacher[DSKD_MAX_LEVELS];
+  float* d_grad_student[DSKD_MAX_LEVELS];  /* same shapes; fully overwritten; NULL = forward only      */
+  float scale[DSKD_MAX_LEVELS];
+  int64_t cells_per_image;
+  const int32_t* d_owner;       /* [N,cells_per_image] from DSKD_RASTER_OWNER_EXCL, or NULL           */
+  const float* d_rows;          /* [num_pairs,C] from dskd_mask_rows (row-mask mode)                   */
+  float* d_energy;              /* [num_pairs,C], caller zero-fills                                     */
+  int32_t num_pairs;
+  const float* d_cell_weight;   /* [N,cells_per_image] (cell-mask mode), or NULL                       */
+  double* d_loss;               /* [1] cell-mask mode: loss accumulator, caller zero-fills             */
+} DskdDsgfdMseArgs;
+
+int dskd_dsgfd_mse_fwd_bwd(const DskdDsgfdMseArgs* args, void* stream);
+
+/* Row-mask finish: loss[0] = sum_p,c rows^2*energy; d_grad_rows = 2*rows*energy (may alias energy). */
+int dskd_dsgfd_mse_finish(const float* d_rows, const float* d_energy, int32_t num_pairs, int32_t C,
+                          float* d_loss, float* d_grad_rows, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * DSG-FD, KL-over-H (the shipped config: KnowledgeDistillationKLDivLoss(T, 'sum'), kd_loss.py:12-43
+ * applied to [C,H,W] so softmax runs over H; target = student*mask, detached; pred = teacher*mask).
+ *   loss = sum_{l,i,c,w} scale_l * T^2/H_l * sum_h t_h (log t_h - logp_h)
+ * No gradient reaches the student features; row-mask mode accumulates
+ * d_grad_rows[p,c] = dLoss/d rows directly.  NCHW layout only.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t num_levels, N, C;
+  DskdLevel levels[DSKD_MAX_LEVELS];
+  const float* d_student[DSKD_MAX_LEVELS];
+  const float* d_teacher[DSKD_MAX_LEVELS];
+  float scale[DSKD_MAX_LEVELS];
+  float temperature;
+  int64_t cells_per_image;
+  const int32_t* d_owner;
+  const float* d_rows;
+  float* d_grad_rows;           /* [num_pairs,C], caller zero-fills; NULL = forward only               */
+  int32_t num_pairs;
+  const float* d_cell_weight;   /* cell-mask mode (no gradient at all)                                  */
+  double* d_loss;               /* [1], caller zero-fills                                               */
+} DskdDsgfdKlArgs;
+
+int dskd_dsgfd_kl_fwd_bwd(const DskdDsgfdKlArgs* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * BCDD (head_il.py:525-555, :1197-1222)
+ * ------------------------------------------------------------------------------------------- */
+/* Prototype sums + counts.  d_proto: [2, num_classes, C+1] (0 = teacher, 1 = student; last column =
+ * count), fully overwritten.  Student rows: every q < num_student_rows whose label is flagged in
+ * d_prev_mask (uint8[num_classes]) (:530-539); teacher rows: hs_T[keepid[i]] into class tlabel[i] (:548-551).
+ * Sums run in ascending index order per class, like the reference's Python loops. */
+int dskd_bcdd_prototypes(const float* d_hs_student, const int64_t* d_student_labels, int32_t num_student_rows,
+                         const float* d_hs_teacher, const int64_t* d_teacher_keepid,
+                         const int64_t* d_teacher_labels, int32_t num_teacher,
+                         const uint8_t* d_prev_mask, int32_t num_classes, int32_t C,
+                         float* d_proto, void* stream);
+
+/* correlation_mat (:1197-1222) + MSELoss, fused with its backward.  L = number of previous classes
+ * (rows 0..L-1).  reduction: 0 none (loss not reduced; d_dist only), 1 mean, 2 sum.
+ *   d_dist:  [2,L,L] (teacher, student) distance matrices (direct difference, fp32)
+ *   d_loss:  [1]  = loss_weight * reduce((D_T - D_S)^2) / L
+ *   d_grad_proto_student: [num_classes, C+1] dLoss/d(student sums) (count column 0); NULL = forward only.
+ * grad_scale multiplies the gradient: pass world_size when d_proto was all-reduced (sum) over ranks
+ * (every rank holds the same loss, so the all-reduce's adjoint is a local x world_size which DDP's
+ * gradient mean then cancels -- SURVEY.md section 8e); 1.0f otherwise. */
+int dskd_bcdd_distance_loss(const float* d_proto, int32_t num_classes, int32_t C, int32_t L,
+                            int32_t reduction, float loss_weight, float grad_scale, float* d_dist,
+                            float* d_loss, float* d_grad_proto_student, void* stream);
+
+/* d_grad_hs_student[q,:] = d_grad_proto_student[label[q], :C] for flagged q, else 0 (fully overwritten). */
+int dskd_bcdd_scatter_grad(const float* d_grad_proto_student, const int64_t* d_student_labels,
+                           int32_t num_student_rows, const uint8_t* d_prev_mask, int32_t num_classes,
+                           int32_t C, float* d_grad_hs_student, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Assignment (gfl_hungarian_assigner.py:102-160; match_cost.py:34-51,215-230,460-476;
+ * iou2d_calculator.py:213-260; head_il.py:54-59,1427-1432)
+ * ------------------------------------------------------------------------------------------- */
+/* All (layer,image) problems in one launch.  d_cls: [P,Q,num_classes] logits, d_box: [P,Q,2+4*(reg_max+1)]
+ * sigmoid outputs (reg_max == 0: d_box is [P,Q,4] already-decoded normalised cxcywh, the form
+ * GFLHungarianAssigner.assign receives), P = num_problems; problem p uses the GT set of image (p % N).  d_gt_boxes fp32 [G_total,4]
+ * px xyxy, d_gt_labels int64 [G_total], d_gt_start int32 [N+1], d_img_hw int32 [N,2].
+ * Output d_cost: fp32, problem p at d_cost + p*Q*max_gt, row-major [Q, G_img] with row stride max_gt. */
+int dskd_cost_matrix(const float* d_cls, const float* d_box, int32_t num_problems, int32_t N, int32_t Q,
+                     int32_t num_classes, int32_t reg_max, const float* d_gt_boxes,
+                     const int64_t* d_gt_labels, const int32_t* d_gt_start, const int32_t* d_img_hw,
+                     int32_t max_gt, float w_cls, float w_reg, float w_iou, float* d_cost, void* stream);
+
+/* Targets from the matching (head_il.py:1765-1797, pseudo_sampler.py:35-41, sampling_result.py:35):
+ * d_assigned_gt int64 [P,Q] (1-based GT index within the image's GT set, 0 = background) ->
+ * d_labels int64 [P,Q] (bg = num_classes), d_bbox_targets fp32 [P,Q,4] (normalised cxcywh of the matched
+ * GT, 0 elsewhere), d_bbox_weights fp32 [P,Q,4] (1 on positives), d_teacher_only fp32 [P,Q] (1 where the
+ * label is flagged in d_prev_mask, :1453-1455).  Any output may be NULL. */
+int dskd_assign_targets(const int64_t* d_assigned_gt, int32_t num_problems, int32_t N, int32_t Q,
+                        int32_t num_classes, const float* d_gt_boxes, const int64_t* d_gt_labels,
+                        const int32_t* d_gt_start, const int32_t* d_img_hw, const uint8_t* d_prev_mask,
+                        int64_t* d_labels, float* d_bbox_targets, float* d_bbox_weights, float* d_teacher_only,
+                        void* stream);
+
+/* scipy.optimize.linear_sum_assignment (rectangular_lsap, modified Jonker-Volgenant), float64, minimise.
+ * h_cost row-major [rows, cols]; writes k = min(rows, cols) pairs sorted by row.  Bit-exact with SciPy. */
+int dskd_lsap_f64(const double* h_cost, int32_t rows, int32_t cols, int64_t* h_row_ind, int64_t* h_col_ind);
+
+/* Batch over fp32 cost matrices as produced by dskd_cost_matrix (host copy): problem p is
+ * [rows, h_cols[p]] with row stride `ld` at h_cost + p*rows*ld; writes h_assigned_gt[p*rows + r] =
+ * 1-based matched column or 0 (gfl_hungarian_assigner.py:153-158).  num_threads <= 0: hardware conc. */
+int dskd_lsap_batch_f32(const float* h_cost, int32_t num_problems, int32_t rows, int32_t ld,
+                        const int32_t* h_cols, int64_t* h_assigned_gt, int32_t num_threads);
+
+/* ---------------------------------------------------------------------------------------------
+ * Registry loss modules (mse_loss.py, kd_loss.py, utils.py) -- generic tensors
+ * ------------------------------------------------------------------------------------------- */
+/* elementwise (pred-target)^2 * weight (weight may be NULL); d_elem (n) optional; d_sum[1] (double,
+ * caller zero-fills) optional; grads (n each, optional) = +-2*(pred-target)*weight*grad_scale. */
+int dskd_mse_elementwise(const float* d_pred, const float* d_target, const float* d_weight, int64_t n,
+                         float grad_scale, float* d_elem, double* d_sum, float* d_grad_pred,
+                         float* d_grad_target, void* stream);
+
+/* knowledge_distillation_kl_div_loss on [outer, D, inner] with softmax over D (dim=1 of the
+ * reference's [N,D] or [C,H,W] inputs): d_rowloss [outer*inner] = T^2/D * sum_d t(log t - logp);
+ * optional d_row_weight[outer*inner] scales loss & grad; d_grad_pred (same shape as pred, optional)
+ * = grad_scale * w * (T/D)(softmax(pred/T) - t). */
+int dskd_kd_kl_rows(const float* d_pred, const float* d_soft, int64_t outer, int32_t D, int64_t inner,
+                    float temperature, const float* d_row_weight, float grad_scale, float* d_rowloss,
+                    double* d_sum, float* d_grad_pred, void* stream);
+
+/* x[i] *= *d_factor for i<n, skipped entirely when *d_factor == 1.0f (read on the device: no host
+ * sync).  Used by autograd backward to apply grad_output to gradients staged by the fused kernels. */
+int dskd_scale_inplace(float* d_x, int64_t n, const float* d_factor, void* stream);
+
+/* sum of doubles -> float (deterministic order), helper for partial-sum buffers. */
+int dskd_f64_to_f32(const double* d_in, float* d_out, int32_t n, float scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSKD_B200_H_ */

@@ -1,0 +1,57 @@
+"""CPU-only: the C-ABI library loads, exports every symbol include/dskd_b200.h declares, the ctypes
+binding table matches the header, and the host-only entry points validate their arguments."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from dskd_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, 'include', 'dskd_b200.h')
+
+
+def declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    return sorted(set(re.findall(r'\b(dskd_[a-z0-9_]+)\s*\(', src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    names = declared_functions()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f'{n} is declared in the header but not exported'
+
+
+def test_binding_table_matches_header():
+    names = set(declared_functions())
+    bound = set(_lib.SIGNATURES) | {'dskd_last_error', 'dskd_launch_count'}
+    assert names == bound, (sorted(names - bound), sorted(bound - names))
+
+
+def test_header_cites_reference_lines():
+    src = open(HEADER).read()
+    for cite in ('head_il.py:664', 'head_il.py:525', 'gfl_hungarian_assigner.py', 'mse_loss.py', 'kd_loss.py',
+                 'match_cost.py'):
+        assert cite.split(':')[0] in src
+
+
+def test_abi_version_and_error_string():
+    lib = _lib.load()
+    assert lib.dskd_abi_version() == 1
+    rc = lib.dskd_lsap_f64(None, 3, 3, None, None)
+    assert rc == _lib.EINVAL
+    assert b'dskd_lsap_f64' in lib.dskd_last_error()
+    with pytest.raises(_lib.DskdError):
+        _lib.check(rc, 'dskd_lsap_f64')
+
+
+def test_struct_layout_matches_c():
+    # DskdLevel is {int32, int32, int64}; the arg structs start with 4 (mse) / 3 (kl) int32 then the level table
+    assert ctypes.sizeof(_lib.Level) == 16
+    assert _lib.DsgfdMseArgs.levels.offset == 16
+    assert _lib.DsgfdKlArgs.levels.offset == 16
+    assert _lib.DsgfdMseArgs.d_student.offset == 16 + 16 * _lib.MAX_LEVELS

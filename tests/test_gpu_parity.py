@@ -1,0 +1,467 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and against the reference's own
+outputs (tests/golden).  Tolerances are the ones BASELINE.json's north_star states: rtol 1e-4 on
+losses, 1e-3 on gradients (atol = 1e-6 * max|ref| for near-zero gradients), indices bit-exact."""
+import pytest
+import torch
+
+import dskd_b200
+from dskd_b200 import synth
+from oracle import assign as oa
+from oracle import bcdd as ob
+from oracle import dsgfd as od
+from oracle import losses as ol
+from conftest import Golden, load_head_case
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+LOSS_RTOL, GRAD_RTOL = 1e-4, 1e-3
+
+
+def assert_loss(got, ref):
+    torch.testing.assert_close(got.detach().cpu().double(), ref.detach().double(), rtol=LOSS_RTOL, atol=1e-12)
+
+
+def assert_grad(got, ref):
+    ref = ref.detach()
+    atol = 1e-6 * float(ref.abs().max()) + 1e-30
+    torch.testing.assert_close(got.detach().cpu(), ref, rtol=GRAD_RTOL, atol=atol)
+
+
+def crit_oracle(crit, reduction='sum', w=1.0, T=2):
+    return ol.MSELoss(reduction, w) if crit == 'mse' else ol.KnowledgeDistillationKLDivLoss(reduction, w, T)
+
+
+SMALL = dict(levels=((24, 40), (12, 20), (6, 10), (3, 5)), img_hw=(192, 320), num_query=100, k_range=(3, 9))
+ODD = dict(levels=((25, 42), (13, 21), (7, 11), (4, 6)), img_hw=(200, 333), num_query=60, k_range=(2, 7))
+
+
+def oracle_decode(cpu, crit_mod, version=1, feats=None, hs=None):
+    a = cpu.assignments
+    shapes = [tuple(x) for x in a['img_shapes'].tolist()]
+    id_pred = torch.nonzero(a['student_labels'] < len(a['prev_labels'])).squeeze(1)
+    if version == 1:
+        return od.decode_v1(feats, cpu.teacher_feats, hs, cpu.hs_teacher, a['teacher_keepid'], id_pred,
+                            a['teacher_bboxes'], shapes, crit_mod)
+    return od.decode_v2(feats, cpu.teacher_feats, cpu.hs_teacher, a['teacher_keepid'], a['teacher_bboxes'],
+                        shapes, crit_mod)
+
+
+@pytest.mark.parametrize('cfg', [SMALL, ODD], ids=['vec4', 'scalar'])
+@pytest.mark.parametrize('channels', [64, 256])
+@pytest.mark.parametrize('reduction', ['sum', 'mean'])
+def test_dsgfd_decode_v1_mse_neck(cfg, channels, reduction):
+    cpu = synth.make_distill_inputs(num_images=3, num_prev=40, seed=3, channels=channels, **cfg)
+    gpu = cpu.to(DEV)
+    mod = dskd_b200.DSGFeatureDistillLoss(loss_weight=0.7, reduction=reduction, criterion='mse')
+    feats, hs = gpu.clone_student()
+    loss = mod(feats, gpu.teacher_feats, (hs, gpu.hs_teacher), gpu.assignments)
+    loss.backward()
+    o_feats, o_hs = cpu.clone_student()
+    ref = oracle_decode(cpu, crit_oracle('mse', reduction, 0.7), 1, o_feats, o_hs)
+    ref.backward()
+    assert_loss(loss, ref)
+    assert_grad(hs.grad, o_hs.grad)
+    for g, r in zip(feats, o_feats):
+        assert_grad(g.grad, r.grad)
+
+
+@pytest.mark.parametrize('channels', [64, 256])
+def test_dsgfd_decode_v1_mse_memory_layout(channels):
+    """Same numbers through the [S,N,C] encoder-memory layout (head_il.py:866-880 views)."""
+    cpu = synth.make_distill_inputs(num_images=2, num_prev=40, seed=5, channels=channels, **ODD)
+    gpu = cpu.to(DEV)
+    s_mem, t_mem = gpu.memory()
+    s_mem.requires_grad_(True)
+    _, hs = gpu.clone_student()
+    mod = dskd_b200.DSGFeatureDistillLoss(criterion='mse', feature_source='memory')
+    loss = mod((s_mem, gpu.spatial_shapes), (t_mem, gpu.spatial_shapes), (hs, gpu.hs_teacher), gpu.assignments)
+    loss.backward()
+    o_feats, o_hs = cpu.clone_student()
+    ref = oracle_decode(cpu, crit_oracle('mse'), 1, o_feats, o_hs)
+    ref.backward()
+    assert_loss(loss, ref)
+    assert_grad(hs.grad, o_hs.grad)
+    ref_mem_grad = torch.cat([f.grad.flatten(2) for f in o_feats], 2).permute(2, 0, 1)
+    assert_grad(s_mem.grad, ref_mem_grad.contiguous())
+
+
+@pytest.mark.parametrize('cfg', [SMALL, ODD], ids=['vec4', 'scalar'])
+@pytest.mark.parametrize('reduction', ['sum', 'mean'])
+def test_dsgfd_decode_v1_kl(cfg, reduction):
+    cpu = synth.make_distill_inputs(num_images=2, num_prev=40, seed=4, channels=64, **cfg)
+    gpu = cpu.to(DEV)
+    mod = dskd_b200.DSGFeatureDistillLoss(loss_weight=1.3, reduction=reduction, criterion='kl', T=2.0)
+    feats, hs = gpu.clone_student()
+    loss = mod(feats, gpu.teacher_feats, (hs, gpu.hs_teacher), gpu.assignments)
+    loss.backward()
+    o_feats, o_hs = cpu.clone_student()
+    ref = oracle_decode(cpu, crit_oracle('kl', reduction, 1.3, 2), 1, o_feats, o_hs)
+    ref.backward()
+    assert_loss(loss, ref)
+    assert_grad(hs.grad, o_hs.grad)
+    assert all(f.grad is None for f in feats) and all(f.grad is None for f in o_feats)
+
+
+@pytest.mark.parametrize('crit', ['mse', 'kl'])
+def test_dsgfd_decode_v2(crit):
+    cpu = synth.make_distill_inputs(num_images=2, num_prev=40, seed=6, channels=64, **SMALL)
+    gpu = cpu.to(DEV)
+    mod = dskd_b200.DSGFeatureDistillLoss(criterion=crit, mask_mode='decode_v2')
+    feats, hs = gpu.clone_student()
+    loss = mod(feats, gpu.teacher_feats, (hs, gpu.hs_teacher), gpu.assignments)
+    o_feats, o_hs = cpu.clone_student()
+    ref = oracle_decode(cpu, crit_oracle(crit), 2, o_feats, o_hs)
+    assert_loss(loss, ref)
+    if crit == 'mse':
+        loss.backward()
+        ref.backward()
+        for g, r in zip(feats, o_feats):
+            assert_grad(g.grad, r.grad)
+        assert hs.grad is None or float(hs.grad.abs().max()) == 0.0
+    else:
+        assert not ref.requires_grad                      # constant mask, teacher pred, detached target
+
+
+@pytest.mark.parametrize('mode', ['sg_out', 'fg_only', 'fg_bk'])
+def test_dsgfd_cell_masks_mse_memory(mode):
+    cpu = synth.make_distill_inputs(num_images=2, num_prev=40, seed=8, channels=64, **ODD)
+    gpu = cpu.to(DEV)
+    a = cpu.assignments
+    shapes = [tuple(x) for x in a['img_shapes'].tolist()]
+    s_mem, t_mem = gpu.memory()
+    s_mem.requires_grad_(True)
+    mod = dskd_b200.DSGFeatureDistillLoss(criterion='mse', mask_mode=mode, feature_source='memory', loss_weight=2.0)
+    loss = mod((s_mem, gpu.spatial_shapes), (t_mem, gpu.spatial_shapes), (gpu.hs_student, gpu.hs_teacher), gpu.assignments)
+    loss.backward()
+    o_s, o_t = cpu.memory()
+    o_s.requires_grad_(True)
+    crit = ol.MSELoss('sum', 2.0)
+    if mode == 'sg_out':
+        ref = od.sg_out(o_s, o_t, cpu.levels, a['teacher_bboxes'], a['gt_bboxes'], shapes, crit)
+    elif mode == 'fg_only':
+        ref = od.fg_only(o_s, o_t, cpu.levels, a['teacher_bboxes'], shapes, crit)
+    else:
+        ref = od.fg_bk(o_s, o_t, cpu.levels, a['teacher_bboxes'], shapes, crit)
+    ref.backward()
+    assert_loss(loss, ref)
+    assert_grad(s_mem.grad, o_s.grad)
+
+
+@pytest.mark.parametrize('mode', ['sg_out', 'fg_only'])
+def test_dsgfd_cell_masks_neck_mse_and_kl(mode):
+    cpu = synth.make_distill_inputs(num_images=2, num_prev=40, seed=9, channels=64, **SMALL)
+    gpu = cpu.to(DEV)
+    a = cpu.assignments
+    shapes = [tuple(x) for x in a['img_shapes'].tolist()]
+    o_s, o_t = cpu.memory()
+    for crit in ('mse', 'kl'):
+        mod = dskd_b200.DSGFeatureDistillLoss(criterion=crit, mask_mode=mode, feature_source='neck')
+        feats, _ = gpu.clone_student()
+        loss = mod(feats, gpu.teacher_feats, (gpu.hs_student, gpu.hs_teacher), gpu.assignments)
+        c = crit_oracle(crit)
+        ref = od.sg_out(o_s, o_t, cpu.levels, a['teacher_bboxes'], a['gt_bboxes'], shapes, c) if mode == 'sg_out' \
+            else od.fg_only(o_s, o_t, cpu.levels, a['teacher_bboxes'], shapes, c)
+        assert_loss(loss, ref)
+
+
+@pytest.mark.parametrize('num_prev', [40, 70])
+@pytest.mark.parametrize('reduction', ['mean', 'sum'])
+def test_bcdd_vs_oracle(num_prev, reduction):
+    cpu = synth.make_distill_inputs(num_images=4, num_prev=num_prev, seed=10, **SMALL)
+    gpu = cpu.to(DEV)
+    a = cpu.assignments
+    mod = dskd_b200.BetweenClassDistanceLoss(loss_weight=1.5, reduction=reduction)
+    _, hs = gpu.clone_student()
+    loss = mod(None, None, (hs, gpu.hs_teacher), gpu.assignments)
+    loss.backward()
+    _, o_hs = cpu.clone_student()
+    C = o_hs.shape[-1]
+    corr_t, corr_s = ob.prototypes(o_hs.reshape(-1, C), a['student_labels'], cpu.hs_teacher.reshape(-1, C),
+                                   a['teacher_keepid'], a['teacher_labels'], a['prev_labels'])
+    # prototype sums run in the reference's loop order: bit-exact
+    assert torch.equal(mod.last_prototypes[0].cpu(), corr_t.detach())
+    assert torch.equal(mod.last_prototypes[1].cpu(), corr_s.detach())
+    ref = ob.correlation_loss(corr_t, corr_s, num_prev, ol.MSELoss(reduction, 1.5))
+    ref.backward()
+    assert_loss(loss, ref)
+    assert_grad(hs.grad, o_hs.grad)
+    d_t, d_s = ob.distance_matrices(*[c.detach().clone() for c in ob.prototypes(
+        o_hs.detach().reshape(-1, C), a['student_labels'], cpu.hs_teacher.reshape(-1, C), a['teacher_keepid'],
+        a['teacher_labels'], a['prev_labels'])], num_prev)
+    torch.testing.assert_close(mod.last_distances[0].cpu(), d_t, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(mod.last_distances[1].cpu(), d_s, rtol=1e-5, atol=1e-6)
+
+
+def test_bcdd_nan_edge_matches_reference_semantics():
+    """A class with teacher hits but no student hits divides 0/0 in the reference (head_il.py:1205)."""
+    cpu = synth.make_distill_inputs(num_images=2, num_prev=40, seed=11, **SMALL)
+    a = dict(cpu.assignments)
+    lab = a['student_labels'].clone()
+    victim = int(a['teacher_labels'][0])
+    lab[lab == victim] = 80
+    a['student_labels'] = lab
+    C = cpu.hs_student.shape[-1]
+    ref = ob.bcdd_loss(cpu.hs_student.reshape(-1, C), lab, cpu.hs_teacher.reshape(-1, C), a['teacher_keepid'],
+                       a['teacher_labels'], a['prev_labels'], ol.MSELoss('mean', 1.0))
+    gpu = cpu.to(DEV)
+    ga = dict(gpu.assignments)
+    ga['student_labels'] = lab.to(DEV)
+    loss = dskd_b200.BetweenClassDistanceLoss()(None, None, (gpu.hs_student, gpu.hs_teacher), ga)
+    assert torch.isnan(ref) and torch.isnan(loss.cpu())
+
+
+# ------------------------------------------------------------------ against the reference's own outputs
+def _gpu_assignments_from_golden(inp, out):
+    N, Q = inp.t('s_cls').shape[1:3]
+    img_hw = tuple(inp.t('img_hw').tolist())
+    L = inp.v('L')
+    return dict(student_labels=out.t('labels_layers')[-1].to(DEV), teacher_keepid=out.t('pred_keepid').to(DEV),
+                teacher_labels=torch.cat(out.lst('pred_labels')).to(DEV),
+                teacher_bboxes=[b.to(DEV) for b in out.lst('pred_bboxes')],
+                gt_bboxes=[b.to(DEV) for b in inp.lst('gt_bboxes')],
+                img_shapes=[img_hw] * N, prev_labels=list(range(L)), num_classes=80), N, Q
+
+
+GOLDEN_CASES = [('head_decode_v1_mse.npz', 'decode_v1', 'mse', 'neck'),
+                ('head_decode_v1_mse_n1.npz', 'decode_v1', 'mse', 'neck'),
+                ('head_decode_v1_kl.npz', 'decode_v1', 'kl', 'neck'),
+                ('head_decode_v1_kl_l70.npz', 'decode_v1', 'kl', 'neck'),
+                ('head_decode_v2_mse_n1.npz', 'decode_v2', 'mse', 'neck'),
+                ('head_sg_out_mse.npz', 'sg_out', 'mse', 'memory'),
+                ('head_sg_out_kl.npz', 'sg_out', 'kl', 'neck'),
+                ('head_fg_only_mse.npz', 'fg_only', 'mse', 'memory')]
+
+
+@pytest.mark.parametrize('name,mode,crit,source', GOLDEN_CASES)
+def test_cuda_path_vs_reference_outputs(name, mode, crit, source):
+    inp, out = load_head_case(name)
+    a, N, Q = _gpu_assignments_from_golden(inp, out)
+    hs_s = inp.t('hs_s')[-1].to(DEV).requires_grad_(True)
+    hs_t = inp.t('hs_t')[-1].to(DEV)
+    s_feats = [f.to(DEV).requires_grad_(True) for f in inp.lst('s_feats')]
+    t_feats = [f.to(DEV) for f in inp.lst('t_feats')]
+    # BCDD
+    corr = dskd_b200.BetweenClassDistanceLoss(reduction='mean')(None, None, (hs_s, hs_t), a)
+    assert_loss(corr, out.t('loss_corr'))
+    g, = torch.autograd.grad(corr, hs_s)
+    assert_grad(g, out.t('corr.grad_hs'))
+    # DSG-FD
+    mod = dskd_b200.DSGFeatureDistillLoss(criterion=crit, mask_mode=mode, feature_source=source, validate=True)
+    if source == 'neck':
+        loss = mod(s_feats, t_feats, (hs_s, hs_t), a)
+        leaves = s_feats
+    else:
+        shapes = inp.t('levels')
+        s_mem = torch.cat([f.detach().flatten(2) for f in s_feats], 2).permute(2, 0, 1).contiguous().requires_grad_(True)
+        t_mem = torch.cat([f.flatten(2) for f in t_feats], 2).permute(2, 0, 1).contiguous()
+        loss = mod((s_mem, shapes), (t_mem, shapes), (hs_s, hs_t), a)
+        leaves = [s_mem]
+    assert_loss(loss, out.t('loss_fg_feature'))
+    if out.v('fg.backward_raises') or not loss.requires_grad:
+        return
+    grads = torch.autograd.grad(loss, [hs_s] + leaves, allow_unused=True)
+    if not out.v('fg.grad_hs_is_none'):
+        assert_grad(grads[0], out.t('fg.grad_hs'))
+    if source == 'memory' and not out.v('fg.grad_mem_is_none'):
+        assert_grad(grads[1], out.t('fg.grad_mem'))
+    if source == 'neck' and not out.v('fg.grad_feats_is_none'):
+        for got, ref in zip(grads[1:], out.lst('fg.grad_feats')):
+            assert_grad(got, ref)
+
+
+def test_assignment_vs_reference_outputs():
+    g = Golden('assign.npz')
+    asg = dskd_b200.GFLHungarianAssigner()
+    for c in range(g.v('num_cases')):
+        p = f'case{c}.'
+        asg.w_cls = g.v(p + 'w_cls')
+        res = asg.assign(g.t(p + 'cxcywh').to(DEV), g.t(p + 'cls').to(DEV), g.t(p + 'gt').to(DEV),
+                         g.t(p + 'lab').to(DEV), None, dict(img_shape=(800, 1333, 3)))
+        assert torch.equal(res.gt_inds.cpu(), g.t(p + 'gt_inds')), p
+        assert torch.equal(res.labels.cpu(), g.t(p + 'labels')), p
+        if g.t(p + 'lab').numel():
+            cost, cols, _ = asg.cost_matrices(g.t(p + 'cls').to(DEV)[None], g.t(p + 'cxcywh').to(DEV)[None],
+                                              [g.t(p + 'gt').to(DEV)], [g.t(p + 'lab').to(DEV)], [(800, 1333)],
+                                              decoded=True)
+            ref = g.t(p + 'cls_cost') + g.t(p + 'reg_cost') + g.t(p + 'iou_cost')
+            torch.testing.assert_close(cost[0, :, :cols[0]].cpu(), ref, rtol=2e-6, atol=2e-6)
+
+
+@pytest.mark.parametrize('name', ['head_decode_v1_mse.npz', 'head_decode_v1_kl_l70.npz'])
+def test_batched_assignment_all_layers_vs_reference(name):
+    inp, out = load_head_case(name)
+    N, Q = inp.t('s_cls').shape[1:3]
+    img_hw = tuple(inp.t('img_hw').tolist())
+    gt_b = [torch.cat([t, g]) for t, g in zip(out.lst('pred_bboxes'), inp.lst('gt_bboxes'))]
+    gt_l = [torch.cat([t, g]) for t, g in zip(out.lst('pred_labels'), inp.lst('gt_labels'))]
+    asg = dskd_b200.GFLHungarianAssigner(cls_cost=dict(type='QualityFocalLossCost', weight=inp.v('w_cls')))
+    res = asg.assign_batch(inp.t('s_cls').to(DEV), inp.t('s_box').to(DEV), [b.to(DEV) for b in gt_b],
+                           [l.to(DEV) for l in gt_l], [img_hw] * N, prev_labels=list(range(inp.v('L'))))
+    layers = inp.t('s_cls').shape[0]
+    assert torch.equal(res['labels'].cpu().view(layers, N * Q), out.t('labels_layers'))
+    assert torch.equal(res['teacher_only_weights'].cpu().view(layers, N * Q), out.t('teacher_only_layers'))
+
+
+def test_batched_assignment_vs_oracle_coco_shape():
+    ai = synth.make_assign_inputs(num_images=4, seed=21)
+    asg = dskd_b200.GFLHungarianAssigner()
+    res = asg.assign_batch(ai.cls_logits.to(DEV), ai.box_pred.to(DEV), [g.to(DEV) for g in ai.gt_bboxes],
+                           [l.to(DEV) for l in ai.gt_labels], ai.img_shapes, prev_labels=list(range(40)))
+    shapes = [tuple(x) for x in ai.img_shapes.tolist()]
+    ref = [oa.layer_targets(ai.cls_logits[k], ai.box_pred[k], ai.gt_bboxes, ai.gt_labels, shapes, list(range(40)))
+           for k in range(6)]
+    for key in ('labels', 'teacher_only_weights', 'bbox_weights'):
+        assert torch.equal(res[key].cpu(), torch.cat([r[key] for r in ref])), key
+    assert torch.equal(res['assigned_gt_inds'].cpu(), torch.cat([r['gt_inds'] for r in ref]))
+    torch.testing.assert_close(res['bbox_targets'].cpu(), torch.cat([r['bbox_targets'] for r in ref]), rtol=0, atol=0)
+
+
+# ------------------------------------------------------------------ registry loss modules
+def test_registry_loss_modules_vs_reference_outputs():
+    g = Golden('losses.npz')
+    pred, tgt, w = g.t('pred').to(DEV), g.t('target').to(DEV), g.t('weight').to(DEV)
+
+    def close(a, b):
+        torch.testing.assert_close(a.detach().cpu(), b, rtol=1e-5, atol=1e-6)
+    for red in ('none', 'mean', 'sum'):
+        for lw in (1.0, 0.37):
+            close(dskd_b200.MSELoss(red, lw)(pred, tgt), g.t(f'mse.{red}.{lw}'))
+            close(dskd_b200.MSELoss(red, lw)(pred, tgt, weight=w), g.t(f'mse.{red}.{lw}.w'))
+        for T in (1, 2, 10):
+            close(dskd_b200.KnowledgeDistillationKLDivLoss(red, 1.5, T)(pred, tgt), g.t(f'kd.{red}.T{T}'))
+    close(dskd_b200.MSELoss('mean')(pred, tgt, weight=w, avg_factor=7.0), g.t('mse.mean.avg7'))
+    close(dskd_b200.KnowledgeDistillationKLDivLoss('sum', 1.0, 2)(pred, tgt, weight=g.t('kd.weight').to(DEV)), g.t('kd.sum.T2.w'))
+    close(dskd_b200.KnowledgeDistillationKLDivLoss('mean', 1.0, 2)(pred, tgt, avg_factor=3.0), g.t('kd.mean.T2.avg3'))
+    close(dskd_b200.KnowledgeDistillationKLDivLoss('mean', 1.0, 10)(g.t('pred2').to(DEV), g.t('target2').to(DEV)), g.t('kd2.mean.T10'))
+    p, t = pred.clone().requires_grad_(True), tgt.clone().requires_grad_(True)
+    dskd_b200.MSELoss('sum', 0.37)(p, t, weight=w).backward()
+    close(p.grad, g.t('mse.grad_pred'))
+    close(t.grad, g.t('mse.grad_target'))
+    p, t = pred.clone().requires_grad_(True), tgt.clone().requires_grad_(True)
+    dskd_b200.KnowledgeDistillationKLDivLoss('sum', 1.5, 2)(p, t).backward()
+    close(p.grad, g.t('kd.grad_pred'))
+    assert t.grad is None
+
+
+def test_registry_loss_module_known_answers():
+    # the reference's tests/test_metrics/test_losses.py:82-109 and tests/test_models/test_loss.py:28-88
+    with pytest.raises(AssertionError):
+        dskd_b200.build_loss(dict(type='KnowledgeDistillationKLDivLoss', loss_weight=1.0, T=0.5))
+    kd = dskd_b200.build_loss(dict(type='KnowledgeDistillationKLDivLoss', loss_weight=1.0, T=1))
+    with pytest.raises(AssertionError):
+        kd(torch.Tensor([[5, -5, 0]]).to(DEV), torch.Tensor([[1, 0]]).to(DEV))
+    z = kd(torch.Tensor([[1, 2, 0]]).to(DEV), torch.Tensor([[1, 2, 0]]).to(DEV))
+    assert torch.allclose(z.cpu(), torch.tensor(0.0), atol=1e-7)
+    pred, tgt = torch.rand(1, 4, device=DEV), torch.rand(1, 4, device=DEV)
+    mse = dskd_b200.build_loss(dict(type='MSELoss'))
+    with pytest.raises(ValueError):
+        mse(pred, tgt, avg_factor=10, reduction_override='sum')
+    with pytest.raises(AssertionError):
+        mse(pred, tgt, reduction_override=True)
+    mse(torch.rand(0, 4, device=DEV), torch.rand(0, 4, device=DEV))
+    assert isinstance(mse(pred, tgt, avg_factor=10, reduction_override='mean'), torch.Tensor)
+
+
+# ------------------------------------------------------------------ edge cases & autograd contract
+def test_images_without_teacher_boxes_and_empty_batch_of_boxes():
+    cpu = synth.make_distill_inputs(num_images=3, num_prev=40, seed=12, channels=64, **SMALL)
+    a = cpu.assignments
+    # drop every teacher detection of image 1 (ragged), keep the student labels consistent
+    n0, n1 = len(a['teacher_bboxes'][0]), len(a['teacher_bboxes'][1])
+    keep = torch.ones(a['teacher_keepid'].numel(), dtype=torch.bool)
+    keep[n0:n0 + n1] = False
+    lab = a['student_labels'].clone()
+    Q = cpu.hs_student.shape[1]
+    seg = lab[Q:2 * Q]
+    seg[seg < 40] = 80
+    a2 = dict(a, teacher_bboxes=[a['teacher_bboxes'][0], a['teacher_bboxes'][1][:0], a['teacher_bboxes'][2]],
+              teacher_keepid=a['teacher_keepid'][keep], teacher_labels=a['teacher_labels'][keep], student_labels=lab)
+    cpu.assignments = a2
+    gpu = cpu.to(DEV)
+    for crit in ('mse', 'kl'):
+        mod = dskd_b200.DSGFeatureDistillLoss(criterion=crit, validate=True)
+        feats, hs = gpu.clone_student()
+        loss = mod(feats, gpu.teacher_feats, (hs, gpu.hs_teacher), gpu.assignments)
+        loss.backward()
+        o_feats, o_hs = cpu.clone_student()
+        ref = oracle_decode(cpu, crit_oracle(crit), 1, o_feats, o_hs)
+        ref.backward()
+        assert_loss(loss, ref)
+        assert_grad(hs.grad, o_hs.grad)
+    # no boxes at all: loss 0, zero gradients
+    a3 = dict(a2, teacher_bboxes=[b[:0] for b in a['teacher_bboxes']], teacher_keepid=a['teacher_keepid'][:0],
+              teacher_labels=a['teacher_labels'][:0], student_labels=torch.full_like(lab, 80))
+    cpu.assignments = a3
+    gpu = cpu.to(DEV)
+    feats, hs = gpu.clone_student()
+    loss = dskd_b200.DSGFeatureDistillLoss(criterion='mse')(feats, gpu.teacher_feats, (hs, gpu.hs_teacher), gpu.assignments)
+    loss.backward()
+    assert float(loss) == 0.0 and all(float(f.grad.abs().max()) == 0.0 for f in feats)
+
+
+def test_validate_raises_like_reference_when_pairs_are_missing():
+    cpu = synth.make_distill_inputs(num_images=2, num_prev=40, seed=13, channels=64, **SMALL)
+    gpu = cpu.to(DEV)
+    a = dict(gpu.assignments)
+    a['student_labels'] = torch.full_like(a['student_labels'], 80)
+    with pytest.raises(IndexError):
+        dskd_b200.DSGFeatureDistillLoss(validate=True)(gpu.student_feats, gpu.teacher_feats,
+                                                       (gpu.hs_student, gpu.hs_teacher), a)
+
+
+def test_grad_output_scaling_and_single_backward():
+    cpu = synth.make_distill_inputs(num_images=2, num_prev=40, seed=14, channels=64, **SMALL)
+    gpu = cpu.to(DEV)
+    mod = dskd_b200.DSGFeatureDistillLoss(criterion='mse')
+    feats, hs = gpu.clone_student()
+    mod(feats, gpu.teacher_feats, (hs, gpu.hs_teacher), gpu.assignments).backward()
+    feats3, hs3 = gpu.clone_student()
+    loss3 = mod(feats3, gpu.teacher_feats, (hs3, gpu.hs_teacher), gpu.assignments)
+    (loss3 * 3.0).backward(retain_graph=True)
+    torch.testing.assert_close(hs3.grad, hs.grad * 3.0, rtol=1e-6, atol=0)
+    torch.testing.assert_close(feats3[0].grad, feats[0].grad * 3.0, rtol=1e-6, atol=0)
+    with pytest.raises(RuntimeError):
+        (loss3 * 3.0).backward()
+    # loss_weight is linear
+    l1 = dskd_b200.DSGFeatureDistillLoss(loss_weight=1.0)(gpu.student_feats, gpu.teacher_feats, (gpu.hs_student, gpu.hs_teacher), gpu.assignments)
+    l2 = dskd_b200.DSGFeatureDistillLoss(loss_weight=2.5)(gpu.student_feats, gpu.teacher_feats, (gpu.hs_student, gpu.hs_teacher), gpu.assignments)
+    torch.testing.assert_close(l2, l1 * 2.5, rtol=1e-6, atol=0)
+
+
+def test_cpu_tensors_are_refused():
+    cpu = synth.make_distill_inputs(num_images=1, num_prev=40, seed=15, channels=64, **SMALL)
+    with pytest.raises(dskd_b200._lib.DskdError):
+        dskd_b200.DSGFeatureDistillLoss()(cpu.student_feats, cpu.teacher_feats, (cpu.hs_student, cpu.hs_teacher), cpu.assignments)
+
+
+# ------------------------------------------------------------------ BASELINE full size
+@pytest.mark.parametrize('crit', ['mse', 'kl'])
+def test_full_size_coco_batch2_vs_oracle(crit):
+    """BASELINE.json configs[0]: batch 2, 800x1333, 4-level 256-channel features, L = 40."""
+    cpu = synth.make_distill_inputs(num_images=2, num_prev=40, seed=1234)
+    gpu = cpu.to(DEV)
+    mod = dskd_b200.DSGFeatureDistillLoss(criterion=crit)
+    feats, hs = gpu.clone_student()
+    loss = mod(feats, gpu.teacher_feats, (hs, gpu.hs_teacher), gpu.assignments)
+    loss.backward()
+    o_feats, o_hs = cpu.clone_student()
+    ref = oracle_decode(cpu, crit_oracle(crit), 1, o_feats, o_hs)
+    ref.backward()
+    assert_loss(loss, ref)
+    assert_grad(hs.grad, o_hs.grad)
+    if crit == 'mse':
+        for g, r in zip(feats, o_feats):
+            assert_grad(g.grad, r.grad)
+
+
+def test_full_size_properties_batch16():
+    """Size-independent checks at the bench's size (16 images): the gradient w.r.t. the student features is
+    -2*w/N*M^2*(T-S), so <grad, S - T> == 2 * loss, and it vanishes outside the teacher boxes."""
+    gpu = synth.make_distill_inputs(num_images=16, num_prev=40, seed=99, device=DEV)
+    feats, hs = gpu.clone_student()
+    loss = dskd_b200.DSGFeatureDistillLoss(criterion='mse')(feats, gpu.teacher_feats, (hs, gpu.hs_teacher), gpu.assignments)
+    loss.backward()
+    inner = sum(((f.grad.double()) * (f.detach().double() - t.double())).sum() for f, t in zip(feats, gpu.teacher_feats))
+    torch.testing.assert_close(inner, 2.0 * loss.detach().double(), rtol=1e-5, atol=0)
+    frac = sum(int((f.grad != 0).sum()) for f in feats) / sum(f.numel() for f in feats)
+    assert 0.05 < frac < 0.95

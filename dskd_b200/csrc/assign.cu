@@ -214,7 +214,7 @@ extern "C" int dskd_cost_matrix(const float* d_cls, const float* d_box, int32_t 
                                 int32_t num_classes, int32_t reg_max, const float* d_gt_boxes,
                                 const int64_t* d_gt_labels, const int32_t* d_gt_start, const int32_t* d_img_hw,
                                 int32_t max_gt, float w_cls, float w_reg, float w_iou, float* d_cost, void* stream) {
-  DSKD_REQUIRE(num_problems >= 0 && N > 0 && Q > 0 && num_classes > 0 && reg_max > 0 && max_gt >= 0,
+  DSKD_REQUIRE(num_problems >= 0 && N > 0 && Q > 0 && num_classes > 0 && reg_max >= 0 && max_gt >= 0,
                "dskd_cost_matrix: bad sizes");
   if (num_problems == 0 || max_gt == 0) return DSKD_OK;
   DSKD_REQUIRE(d_cls && d_box && d_gt_boxes && d_gt_labels && d_gt_start && d_img_hw && d_cost,

@@ -41,7 +41,9 @@ struct OnlineLse {  // running max / sum of exp for a softmax over H
       sum += expf(x - mx);
     }
   }
-  __device__ __forceinline__ float lse() const { return mx + logf(sum); }
+  // log-sum-exp in double: the KL below is a second-order quantity (sum_h t_h (log t_h - log p_h) with both
+  // log-softmaxes ~ -log H), so an fp32 logf here (abs. error ~3e-7) would be ~1 % of a column's KL.
+  __device__ __forceinline__ double lse() const { return (double)mx + log((double)sum); }
 };
 
 template <bool CELL>
@@ -107,12 +109,15 @@ __global__ void __launch_bounds__(32 * kKlWarps) dsgfd_kl_kernel(const __grid_co
       }
     }
     // pass 2: KL terms and d loss / d mask, accumulated per owning box along the column
-    float lse_s[kKlChan], lse_t[kKlChan], kl[kKlChan], acc[kKlChan];
+    float lse_s[kKlChan], lse_t[kKlChan], acc[kKlChan];
+    double dl[kKlChan], kl[kKlChan];  // dl = lse_s - lse_t
 #pragma unroll
     for (int k = 0; k < kKlChan; ++k) {
-      lse_s[k] = any ? ls[k].lse() : 0.f;
-      lse_t[k] = any ? lt[k].lse() : 0.f;
-      kl[k] = 0.f;
+      const double a = any ? ls[k].lse() : 0.0, b = any ? lt[k].lse() : 0.0;
+      lse_s[k] = (float)a;
+      lse_t[k] = (float)b;
+      dl[k] = a - b;
+      kl[k] = 0.0;
       acc[k] = 0.f;
     }
     const float gcoef = scale * Temp / (float)H;  // d loss / d pred = scale * (T/H) * (p - t)
@@ -159,13 +164,14 @@ __global__ void __launch_bounds__(32 * kKlWarps) dsgfd_kl_kernel(const __grid_co
         const float log_t = xs[k] - lse_s[k];
         const float log_p = xt[k] - lse_t[k];
         const float t = expf(log_t);
-        kl[k] = fmaf(t, log_t - log_p, kl[k]);
+        // log t - log p = (xs - xt) - (lse_s - lse_t), the difference of the small parts taken first
+        kl[k] += (double)t * ((double)(xs[k] - xt[k]) - dl[k]);
         if (o >= 0) acc[k] = fmaf(tf[k], gcoef * (expf(log_p) - t), acc[k]);
       }
     }
     if (any) {
 #pragma unroll
-      for (int k = 0; k < kKlChan; ++k) kl_total += (double)kl[k];
+      for (int k = 0; k < kKlChan; ++k) kl_total += kl[k];
     }
   }
   // loss = scale * T^2 / H * sum over columns of sum_h t (log t - log p)

@@ -11,7 +11,7 @@
 
 namespace dskd {
 
-constexpr int kMaxOwners = 4;   // distinct owners handled by the warp-uniform fast path
+constexpr int kMaxOwners = 16;  // distinct boxes per warp run handled by the shared-memory fast path
 constexpr int kChanChunk = 32;  // channels per CTA (NCHW kernel) = lanes of the final red.global
 
 struct MseParams {
@@ -55,9 +55,16 @@ struct Vec<1> {
 // channels; the 8 warps of a CTA cover 8 adjacent cell runs so each channel step touches one
 // contiguous 4 KB (VEC=4) piece of the plane.
 // ------------------------------------------------------------------------------------------------
+struct NchwSmem {
+  float rows[8][kMaxOwners][kChanChunk + 4];  // per warp: mask-row slice of each box it touches (+4: bank spread)
+  int owner[8][kMaxOwners];
+  double red[32];
+};
+
 template <int VEC, bool CELL>
-__device__ __forceinline__ void nchw_tile(const MseParams& prm, const int lvl, double* red) {
+__device__ __forceinline__ void nchw_tile(const MseParams& prm, const int lvl, NchwSmem& sm) {
   constexpr int U = 4;  // channels in flight per thread: 2*U independent 128-bit loads
+  static_assert(U == 4 && kChanChunk == 32, "the transposed reduction below is written for 4 x 8 channels");
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int HW = prm.levels[lvl].H * prm.levels[lvl].W;
   const int nchunks = prm.C / kChanChunk;
@@ -98,32 +105,31 @@ __device__ __forceinline__ void nchw_tile(const MseParams& prm, const int lvl, d
   }
   const bool mine = lmax >= 0;  // this lane has at least one masked-in cell: it must read S and T
 
-  // ---- warp-uniform list of distinct owners (row-mask mode)
-  int od[kMaxOwners];
+  // ---- row-mask mode: warp-uniform list of the distinct boxes owning these 32*VEC cells (descending
+  // pair index), their mask-row slices staged in shared memory, and each cell's slot in that list
   int D = 0;
   bool overflow = false;
+  int slot[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) slot[k] = -1;
   if (!CELL) {
     int cur = __reduce_max_sync(0xffffffffu, lmax);
+    while (cur >= 0 && D < kMaxOwners) {
+      if (lane == 0) sm.owner[warp][D] = cur;
+      sm.rows[warp][D][lane] = __ldg(prm.rows + (int64_t)cur * prm.C + c0 + lane);  // coalesced 128 B
+      int nxt = -1;
 #pragma unroll
-    for (int d = 0; d < kMaxOwners; ++d) {
-      od[d] = -1;
-      if (cur >= 0) {
-        od[d] = cur;
-        D = d + 1;
-        int nxt = -1;
-#pragma unroll
-        for (int k = 0; k < VEC; ++k)
-          if (own[k] < cur) nxt = max(nxt, own[k]);
-        cur = __reduce_max_sync(0xffffffffu, nxt);
+      for (int k = 0; k < VEC; ++k) {
+        if (own[k] == cur) slot[k] = D;
+        if (own[k] < cur) nxt = max(nxt, own[k]);
       }
+      ++D;
+      cur = __reduce_max_sync(0xffffffffu, nxt);
     }
-    overflow = cur >= 0;
+    overflow = cur >= 0;  // more than kMaxOwners boxes inside one warp's run of cells: per-cell atomics
+    __syncwarp();
   }
   const bool warp_active = CELL ? (__any_sync(0xffffffffu, mine) != 0) : (D > 0);
-
-  float keep[kMaxOwners];
-#pragma unroll
-  for (int d = 0; d < kMaxOwners; ++d) keep[d] = 0.f;
   float loss_acc = 0.f;
 
   if (!warp_active) {
@@ -136,6 +142,7 @@ __device__ __forceinline__ void nchw_tile(const MseParams& prm, const int lvl, d
       for (int cc = 0; cc < kChanChunk; ++cc) z.store(G + plane0 + (int64_t)cc * HW);
     }
   } else {
+    const bool hi16 = lane & 16, hi8 = lane & 8;
     for (int cb = 0; cb < kChanChunk; cb += U) {
       Vec<VEC> s[U], t[U];
 #pragma unroll
@@ -148,56 +155,76 @@ __device__ __forceinline__ void nchw_tile(const MseParams& prm, const int lvl, d
           for (int k = 0; k < VEC; ++k) s[u].v[k] = t[u].v[k] = 0.f;
         }
       }
+      // mask value of every cell for the U channels of this step: one 128-bit shared load per cell
+      float m[VEC][U];
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        if (CELL) {
+#pragma unroll
+          for (int u = 0; u < U; ++u) m[k][u] = wgt[k];
+        } else if (overflow) {
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+            m[k][u] = own[k] >= 0 ? __ldg(prm.rows + (int64_t)own[k] * prm.C + c0 + cb + u) : 0.f;
+        } else {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (slot[k] >= 0) v = *reinterpret_cast<const float4*>(&sm.rows[warp][slot[k]][cb]);
+          m[k][0] = v.x; m[k][1] = v.y; m[k][2] = v.z; m[k][3] = v.w;
+        }
+      }
+      float dsq[VEC][U];  // (T - S)^2, kept for the per-box energy sums
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const int c = c0 + cb + u;
-        float m[VEC], dd[VEC];
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) {
-          dd[k] = t[u].v[k] - s[u].v[k];
-          m[k] = CELL ? wgt[k] : 0.f;
-        }
-        if (!CELL) {
-          if (!overflow) {
-#pragma unroll
-            for (int d = 0; d < kMaxOwners; ++d) {
-              if (d < D) {
-                const float a = __ldg(prm.rows + (int64_t)od[d] * prm.C + c);  // uniform address: broadcast
-                float e = 0.f;
-#pragma unroll
-                for (int k = 0; k < VEC; ++k)
-                  if (own[k] == od[d]) { m[k] = a; e = fmaf(dd[k], dd[k], e); }
-                e = warp_sum(e);
-                if (lane == cb + u) keep[d] = e;
-              }
-            }
-          } else {  // > kMaxOwners boxes meet inside one warp's cells: rare, per-cell atomics
-#pragma unroll
-            for (int k = 0; k < VEC; ++k)
-              if (own[k] >= 0) {
-                m[k] = __ldg(prm.rows + (int64_t)own[k] * prm.C + c);
-                atomicAdd(prm.energy + (int64_t)own[k] * prm.C + c, scale * dd[k] * dd[k]);
-              }
-          }
-        }
         Vec<VEC> g;
 #pragma unroll
         for (int k = 0; k < VEC; ++k) {
-          const float m2 = m[k] * m[k];
-          g.v[k] = -2.f * scale * m2 * dd[k];
-          if (CELL) loss_acc = fmaf(m2 * dd[k], dd[k], loss_acc);
+          const float dd = t[u].v[k] - s[u].v[k];
+          const float m2 = m[k][u] * m[k][u];
+          dsq[k][u] = dd * dd;
+          g.v[k] = -2.f * scale * m2 * dd;
+          if (CELL) loss_acc = fmaf(m2, dsq[k][u], loss_acc);
         }
         if (G != nullptr && in_range) g.store(G + plane0 + (int64_t)(cb + u) * HW);
       }
-    }
-    if (!CELL && !overflow) {
+      if (!CELL) {
+        if (!overflow) {
+          // energy[box, channel] += sum over this warp's cells owned by the box.  Transposed warp reduction:
+          // 6 shuffles give the totals of 4 channels (lanes 8u..8u+7 hold channel cb+u), then one 4-lane red.
+          for (int d = 0; d < D; ++d) {
+            float e[U];
 #pragma unroll
-      for (int d = 0; d < kMaxOwners; ++d)
-        if (d < D) atomicAdd(prm.energy + (int64_t)od[d] * prm.C + c0 + lane, scale * keep[d]);
+            for (int u = 0; u < U; ++u) {
+              e[u] = 0.f;
+#pragma unroll
+              for (int k = 0; k < VEC; ++k) e[u] += (slot[k] == d) ? dsq[k][u] : 0.f;
+            }
+            float x0 = hi16 ? e[2] : e[0], y0 = hi16 ? e[0] : e[2];
+            float x1 = hi16 ? e[3] : e[1], y1 = hi16 ? e[1] : e[3];
+            x0 += __shfl_xor_sync(0xffffffffu, y0, 16);
+            x1 += __shfl_xor_sync(0xffffffffu, y1, 16);
+            float z = hi8 ? x1 : x0;
+            const float w = hi8 ? x0 : x1;
+            z += __shfl_xor_sync(0xffffffffu, w, 8);
+            z += __shfl_xor_sync(0xffffffffu, z, 4);
+            z += __shfl_xor_sync(0xffffffffu, z, 2);
+            z += __shfl_xor_sync(0xffffffffu, z, 1);
+            if ((lane & 7) == 0)
+              atomicAdd(prm.energy + (int64_t)sm.owner[warp][d] * prm.C + c0 + cb + (lane >> 3), scale * z);
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < VEC; ++k)
+            if (own[k] >= 0) {
+#pragma unroll
+              for (int u = 0; u < U; ++u)
+                atomicAdd(prm.energy + (int64_t)own[k] * prm.C + c0 + cb + u, scale * dsq[k][u]);
+            }
+        }
+      }
     }
   }
   if (CELL) {
-    double tot = block_sum((double)loss_acc * (double)scale, red);
+    double tot = block_sum((double)loss_acc * (double)scale, sm.red);
     if (threadIdx.x == 0 && tot != 0.0) atomicAdd(prm.loss, tot);
   }
 }
@@ -206,13 +233,13 @@ __device__ __forceinline__ void nchw_tile(const MseParams& prm, const int lvl, d
 // the others (25x42 and 13x21 at 800x1333: 6 % of the bytes) the 32-bit path; the choice is CTA-uniform.
 template <bool CELL>
 __global__ void __launch_bounds__(256) dsgfd_mse_nchw_kernel(const __grid_constant__ MseParams prm) {
-  __shared__ double red[32];
+  __shared__ NchwSmem sm;
   int lvl = 0;
 #pragma unroll
   for (int k = 1; k < DSKD_MAX_LEVELS; ++k)
     if (k < prm.num_levels && (int)blockIdx.x >= prm.block_start[k]) lvl = k;
-  if (prm.vec4[lvl]) nchw_tile<4, CELL>(prm, lvl, red);
-  else nchw_tile<1, CELL>(prm, lvl, red);
+  if (prm.vec4[lvl]) nchw_tile<4, CELL>(prm, lvl, sm);
+  else nchw_tile<1, CELL>(prm, lvl, sm);
 }
 
 // ------------------------------------------------------------------------------------------------

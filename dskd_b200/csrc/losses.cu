@@ -61,19 +61,23 @@ __global__ void __launch_bounds__(256) kd_kl_rows_kernel(const float* __restrict
       ss += expf(__fdiv_rn(s[(int64_t)d * inner], Temp) - ms);
     }
     if (WARP_ROW) { sp = warp_sum(sp); ss = warp_sum(ss); }
-    const float lse_p = mp + logf(sp), lse_s = ms + logf(ss);
+    // double log-sum-exp and difference: KL is second order in (pred - soft), see dsgfd_kl.cu
+    const double lse_pd = (double)mp + log((double)sp), lse_sd = (double)ms + log((double)ss);
+    const float lse_p = (float)lse_pd, lse_s = (float)lse_sd;
+    const double dl = lse_sd - lse_pd;
     const float w = row_weight ? row_weight[r] : 1.f;
     const float gc = grad_scale * w * Temp / (float)D;
-    float kl = 0.f;
+    double kl = 0.0;
     for (int d = d0; d < D; d += dstep) {
-      const float log_p = __fdiv_rn(p[(int64_t)d * inner], Temp) - lse_p;
-      const float log_t = __fdiv_rn(s[(int64_t)d * inner], Temp) - lse_s;
+      const float xp = __fdiv_rn(p[(int64_t)d * inner], Temp), xs = __fdiv_rn(s[(int64_t)d * inner], Temp);
+      const float log_p = xp - lse_p;
+      const float log_t = xs - lse_s;
       const float t = expf(log_t);
-      kl = fmaf(t, log_t - log_p, kl);
+      kl += (double)t * ((double)(xs - xp) - dl);
       if (gp) gp[o * D * inner + (int64_t)d * inner + in] = gc * (expf(log_p) - t);
     }
     if (WARP_ROW) kl = warp_sum(kl);
-    const float rl = kl * (Temp * Temp) / (float)D * w;  // .mean(1) * T^2, then elementwise weight
+    const float rl = (float)(kl * (double)(Temp * Temp) / (double)D) * w;  // .mean(1) * T^2, then elementwise weight
     if (!WARP_ROW || lane == 0) {
       if (rowloss) rowloss[r] = rl;
       acc += (double)rl;

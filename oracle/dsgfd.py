@@ -46,7 +46,7 @@ def _decode_loss(student_feats, teacher_feats, hs_student, hs_teacher, id_soft, 
         # The reference fills one shared [N,C,H,W] tensor in place (head_il.py:683,706); a
         # separate tensor per image holds the same numbers and keeps autograd's saved views
         # valid (the reference's own MSE backward raises for N >= 2 because of that sharing).
-        mask = [torch.zeros((C, H, W), device=f_s.device) for _ in range(N)]
+        mask = [torch.zeros((C, H, W), device=f_s.device, dtype=f_s.dtype) for _ in range(N)]
         idx = 0
         for i in range(N):
             wmin, wmax, hmin, hmax = box_cells(teacher_bboxes[i], img_shapes[i], H, W)

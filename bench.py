@@ -44,6 +44,7 @@ def parse_args():
     ap.add_argument('--criterion', default='mse', choices=['mse', 'kl'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='time eager launches only')
     ap.add_argument('--cpu-sample-images', type=int, default=2)
     return ap.parse_args()
 
@@ -199,25 +200,7 @@ def main():
     s_feats = [f.requires_grad_(True) for f in inputs.student_feats]
     hs_s = inputs.hs_student.requires_grad_(True)
 
-    # roofline instrumentation: CUDA events around the dominant kernel's entry point, on its launch stream
-    kernel_events = []
-    orig_mse = lib.dskd_dsgfd_mse_fwd_bwd
-    orig_kl = lib.dskd_dsgfd_kl_fwd_bwd
-    record = {'on': False}
-
-    def timed(fn):
-        def wrapper(a, st):
-            if not record['on']:
-                return fn(a, st)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            rc = fn(a, st)
-            e1.record()
-            kernel_events.append((e0, e1))
-            return rc
-        return wrapper
-    lib.dskd_dsgfd_mse_fwd_bwd = timed(orig_mse)
-    lib.dskd_dsgfd_kl_fwd_bwd = timed(orig_kl)
+    from dskd_b200 import profiling
 
     def step(feats, t_feats, hs, hs_t):
         for f in feats:
@@ -232,7 +215,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- device-resident throughput (`value`)
+    # ---------------- device-resident throughput, eager launches (host-issue bound for this small step)
     for _ in range(max(args.warmup, 3)):
         step(s_feats, inputs.teacher_feats, hs_s, inputs.hs_teacher)
     barrier()
@@ -240,7 +223,7 @@ def main():
     if rank == 0:
         sampler.start()
     launches0 = lib.dskd_launch_count()
-    record['on'] = True
+    profiling.start()       # C side records an event pair around the streaming kernel of every step
     e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e_start.record()
@@ -248,16 +231,56 @@ def main():
         loss = step(s_feats, inputs.teacher_feats, hs_s, inputs.hs_teacher)
     e_stop.record()
     barrier()
-    record['on'] = False
+    kernel_times = profiling.stop()
     launches = lib.dskd_launch_count() - launches0
+    eager_ms = e_start.elapsed_time(e_stop)
+    loss_value = float(loss.detach())
+
+    # ---------------- the same step captured once in a CUDA graph and replayed (`value`): identical kernels,
+    # identical inputs, no per-launch host cost.  Falls back to the eager number if capture is not possible.
+    graph_ms = None
+    graph_err = None
+    if not args.no_graph:
+        try:
+            # fresh leaves: their AccumulateGrad nodes must first be used on the capture (side) stream
+            g_feats = [f.detach().clone().requires_grad_(True) for f in s_feats]
+            g_hs = hs_s.detach().clone().requires_grad_(True)
+            torch.cuda.synchronize()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    step(g_feats, inputs.teacher_feats, g_hs, inputs.hs_teacher)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            for f in g_feats:
+                f.grad = None
+            g_hs.grad = None
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                graph_loss = step(g_feats, inputs.teacher_feats, g_hs, inputs.hs_teacher)
+            for _ in range(max(args.warmup, 3)):
+                graph.replay()
+            barrier()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            for _ in range(args.steps):
+                graph.replay()
+            g1.record()
+            barrier()
+            graph_ms = g0.elapsed_time(g1)
+            if abs(float(graph_loss.detach()) - loss_value) > 1e-3 * abs(loss_value):
+                raise RuntimeError(f'graph replay loss {float(graph_loss.detach())} != eager loss {loss_value}')
+        except Exception as exc:                    # noqa: BLE001 -- report, do not hide
+            graph_err = f'{type(exc).__name__}: {exc}'
+            graph_ms = None
     clocks = sampler.stop() if rank == 0 else None
-    elapsed_ms = e_start.elapsed_time(e_stop)
-    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    elapsed_ms = graph_ms if graph_ms is not None else eager_ms
+    t = torch.tensor([elapsed_ms, eager_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(t.item())
-    kernel_ms = statistics.mean(a.elapsed_time(b) for a, b in kernel_events) if kernel_events else float('nan')
-    loss_value = float(loss)
+    elapsed_ms, eager_ms = float(t[0].item()), float(t[1].item())
+    kernel_ms = statistics.mean(kernel_times) if kernel_times else float('nan')
 
     # ---------------- end-to-end through the module call with HOST buffers (`e2e`)
     e2e = None
@@ -312,6 +335,7 @@ def main():
         'config': {'workload': WORKLOAD, 'images_per_gpu': N, 'global_batch': world * N, 'num_prev': args.num_prev,
                    'criterion': args.criterion, 'levels': [[100, 167], [50, 84], [25, 42], [13, 21]], 'channels': 256,
                    'queries': 300, 'parallelism': f'dp{world}', 'prototype_allreduce': world > 1,
+                   'launch': 'cuda_graph_replay' if graph_ms is not None else 'eager',
                    'cache': f'inputs larger than L2: {2 * N * 22.76:.0f} MB of features read per step vs 126 MB L2'},
         'roofline': {'bound': 'hbm', 'kernel': 'dsgfd_mse_nchw_kernel' if args.criterion == 'mse' else 'dsgfd_kl_kernel',
                      'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
@@ -320,6 +344,8 @@ def main():
                      'kernel_share_of_step': kernel_ms / ms_per_step, 'traffic': None},
         'e2e': e2e,
         'gpu_launches': int(launches),
+        'eager': {'value': world * N * args.steps / (eager_ms * 1e-3), 'unit': UNIT, 'ms_per_step': eager_ms / args.steps,
+                  'note': 'same step issued kernel by kernel from Python; host-issue bound', 'graph_error': graph_err},
         'clocks': clocks,
         'loss': loss_value,
     }

@@ -48,6 +48,26 @@ class DsgfdKlArgs(C.Structure):
                 ('num_pairs', C.c_int32), ('d_cell_weight', _FP), ('d_loss', _FP)]
 
 
+class DsgfdStepArgs(C.Structure):
+    _fields_ = [('criterion', C.c_int32), ('mask_mode', C.c_int32), ('layout', C.c_int32),
+                ('num_levels', C.c_int32), ('N', C.c_int32), ('C', C.c_int32),
+                ('levels', Level * MAX_LEVELS),
+                ('d_student', _FP * MAX_LEVELS), ('d_teacher', _FP * MAX_LEVELS),
+                ('d_grad_student', _FP * MAX_LEVELS), ('scale', C.c_float * MAX_LEVELS),
+                ('temperature', C.c_float), ('cells_per_image', C.c_int64),
+                ('d_hs_student', _FP), ('d_hs_teacher', _FP), ('d_grad_hs_student', _FP),
+                ('num_query_rows', C.c_int32),
+                ('d_teacher_keepid', _FP), ('d_student_labels', _FP), ('d_prev_mask', _FP),
+                ('num_classes', C.c_int32),
+                ('d_boxes', _FP), ('d_box_start', _FP), ('d_gt_boxes', _FP), ('d_gt_start', _FP), ('d_img_hw', _FP),
+                ('num_pairs', C.c_int32), ('max_boxes_per_image', C.c_int32),
+                ('d_loss', _FP), ('d_matched_count', _FP), ('d_workspace', _FP), ('workspace_bytes', C.c_int64),
+                ('ev_kernel_begin', _FP), ('ev_kernel_end', _FP)]
+
+
+CRIT_MSE, CRIT_KL = 0, 1
+MODE_DECODE_V1, MODE_DECODE_V2, MODE_SG_OUT, MODE_FG_ONLY, MODE_FG_BK = 0, 1, 2, 3, 4
+
 i32, i64, f32, vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
 
 # name -> argtypes; every entry point declared in include/dskd_b200.h (tests/test_abi.py checks both ways)
@@ -61,6 +81,9 @@ SIGNATURES = {
     'dskd_dsgfd_mse_fwd_bwd': [C.POINTER(DsgfdMseArgs), vp],
     'dskd_dsgfd_mse_finish': [vp, vp, i32, i32, vp, vp, vp],
     'dskd_dsgfd_kl_fwd_bwd': [C.POINTER(DsgfdKlArgs), vp],
+    'dskd_dsgfd_rows_finish': [i32, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp],
+    'dskd_dsgfd_step': [C.POINTER(DsgfdStepArgs), vp],
+    'dskd_bcdd_loss_and_grad': [vp, i32, i32, i32, i32, f32, f32, vp, i32, vp, vp, vp, vp, vp, vp],
     'dskd_bcdd_prototypes': [vp, vp, i32, vp, vp, vp, i32, vp, i32, i32, vp, vp],
     'dskd_bcdd_distance_loss': [vp, i32, i32, i32, i32, f32, f32, vp, vp, vp, vp],
     'dskd_bcdd_scatter_grad': [vp, vp, i32, vp, i32, i32, vp, vp],
@@ -91,6 +114,8 @@ def load():
     lib.dskd_last_error.argtypes = []
     lib.dskd_launch_count.restype = C.c_uint64
     lib.dskd_launch_count.argtypes = []
+    lib.dskd_dsgfd_step_workspace_bytes.restype = C.c_int64
+    lib.dskd_dsgfd_step_workspace_bytes.argtypes = [C.c_int32, C.c_int64, C.c_int32, C.c_int32]
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes

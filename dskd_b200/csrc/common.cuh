@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <string.h>
+
 #include <algorithm>
 
 #include "../../include/dskd_b200.h"

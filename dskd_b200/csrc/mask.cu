@@ -79,6 +79,52 @@ __global__ void __launch_bounds__(128) mask_rows_bwd_kernel(const float* __restr
   }
 }
 
+// Row-mask finish, one CTA per pair p:  (mse) loss += sum_c rows^2 * energy, g = 2 * rows * energy;
+// (kl) g = grad_rows as accumulated by the KL kernel.  Then, if requested, the softmax / abs backward of
+// mask_rows_bwd_kernel into grad_hs_s.  Replaces the single-CTA dsgfd_mse_finish + mask_rows_bwd pair.
+template <bool MSE>
+__global__ void __launch_bounds__(128) rows_finish_kernel(const float* __restrict__ hs_t, const float* __restrict__ hs_s,
+                                                          const int64_t* __restrict__ id_soft,
+                                                          const int64_t* __restrict__ id_pred,
+                                                          const float* __restrict__ rows, const float* __restrict__ eg,
+                                                          int C, double* __restrict__ loss_acc,
+                                                          float* __restrict__ grad_hs_s) {
+  __shared__ float red[32];
+  __shared__ double dred[32];
+  __shared__ float bcast;
+  const int p = blockIdx.x;
+  const float* A = rows + (int64_t)p * C;
+  const float* E = eg + (int64_t)p * C;
+  float dot = 0.f;
+  double part = 0.0;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float a = A[c], e = E[c];
+    const float g = MSE ? 2.f * a * e : e;
+    if (MSE) part += (double)a * (double)a * (double)e;
+    dot += a * g;
+  }
+  if (MSE) {
+    part = block_sum(part, dred);
+    if (threadIdx.x == 0 && part != 0.0) atomicAdd(loss_acc, part);
+  }
+  if (grad_hs_s == nullptr) return;
+  dot = block_sum(dot, red);
+  if (threadIdx.x == 0) bcast = dot;
+  __syncthreads();
+  dot = bcast;
+  const int64_t qs = id_pred[p];
+  const float* t = hs_t + id_soft[p] * (int64_t)C;
+  const float* sv = hs_s + qs * (int64_t)C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float a = A[c], e = E[c];
+    const float g = MSE ? 2.f * a * e : e;
+    const float da = a * (g - dot);
+    const float delta = t[c] - sv[c];
+    const float sgn = (delta > 0.f) ? 1.f : ((delta < 0.f) ? -1.f : 0.f);
+    atomicAdd(grad_hs_s + qs * (int64_t)C + c, -sgn * da);
+  }
+}
+
 struct RasterParams {
   DskdLevel levels[DSKD_MAX_LEVELS];
   int num_levels;
@@ -197,6 +243,29 @@ extern "C" int dskd_mask_rows_bwd(const float* d_hs_teacher, const float* d_hs_s
   mask_rows_bwd_kernel<<<num_pairs, 128, 0, as_stream(stream)>>>(d_hs_teacher, d_hs_student, d_id_soft, d_id_pred,
                                                                  d_rows, d_grad_rows, C, d_grad_hs_student);
   DSKD_LAUNCH_OK("mask_rows_bwd_kernel");
+  return DSKD_OK;
+}
+
+extern "C" int dskd_dsgfd_rows_finish(int32_t criterion, const float* d_hs_teacher, const float* d_hs_student,
+                                      const int64_t* d_id_soft, const int64_t* d_id_pred, const float* d_rows,
+                                      const float* d_energy_or_grad_rows, int32_t num_pairs, int32_t C,
+                                      double* d_loss_acc, float* d_grad_hs_student, void* stream) {
+  DSKD_REQUIRE(criterion == 0 || criterion == 1, "dskd_dsgfd_rows_finish: criterion must be 0 (mse) or 1 (kl)");
+  DSKD_REQUIRE(num_pairs >= 0 && C > 0, "dskd_dsgfd_rows_finish: bad sizes");
+  if (num_pairs == 0) return DSKD_OK;
+  DSKD_REQUIRE(d_rows && d_energy_or_grad_rows && (criterion == 1 || d_loss_acc), "dskd_dsgfd_rows_finish: null pointer");
+  DSKD_REQUIRE(d_grad_hs_student == nullptr || (d_hs_teacher && d_hs_student && d_id_soft && d_id_pred),
+               "dskd_dsgfd_rows_finish: the embedding gradient needs hs / ids");
+  if (criterion == 1 && d_grad_hs_student == nullptr) return DSKD_OK;
+  if (criterion == 0)
+    rows_finish_kernel<true><<<num_pairs, 128, 0, as_stream(stream)>>>(d_hs_teacher, d_hs_student, d_id_soft, d_id_pred,
+                                                                       d_rows, d_energy_or_grad_rows, C, d_loss_acc,
+                                                                       d_grad_hs_student);
+  else
+    rows_finish_kernel<false><<<num_pairs, 128, 0, as_stream(stream)>>>(d_hs_teacher, d_hs_student, d_id_soft, d_id_pred,
+                                                                        d_rows, d_energy_or_grad_rows, C, d_loss_acc,
+                                                                        d_grad_hs_student);
+  DSKD_LAUNCH_OK("rows_finish_kernel");
   return DSKD_OK;
 }
 

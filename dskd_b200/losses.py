@@ -19,6 +19,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib as L
+from . import profiling
 from .registry import LOSSES
 
 _REDUCTIONS = (None, 'none', 'mean', 'sum')
@@ -69,6 +70,21 @@ def _img_hw_list(assignments, n):
     return hw
 
 
+_meta_cache: Dict[tuple, torch.Tensor] = {}
+
+
+def _meta_tensor(meta, device):
+    """int32 table on the device; identical tables (same box counts / image sizes) are uploaded once."""
+    key = (tuple(meta), str(device))
+    t = _meta_cache.get(key)
+    if t is None:
+        if len(_meta_cache) > 256:
+            _meta_cache.clear()
+        t = torch.tensor(meta, dtype=torch.int32).to(device)
+        _meta_cache[key] = t
+    return t
+
+
 def _box_meta(boxes: Sequence[torch.Tensor], img_hw, device, gt_boxes=None):
     """Concatenate per-image boxes and upload the tiny int32 tables in ONE copy.
 
@@ -88,7 +104,7 @@ def _box_meta(boxes: Sequence[torch.Tensor], img_hw, device, gt_boxes=None):
             gstart.append(gstart[-1] + k)
         meta += gstart
         max_per = max([a + b for a, b in zip(lens, glens)] or [0])
-    meta_t = torch.tensor(meta, dtype=torch.int32).to(device, non_blocking=True)
+    meta_t = _meta_tensor(meta, device)
     cat = L.f32c(torch.cat([b.reshape(-1, 4) for b in boxes], 0)) if n else torch.zeros(0, 4, device=device)
     gt_cat = None
     gt_start_t = None
@@ -126,9 +142,14 @@ _ROW_MODES = {'decode_v1': L.MASK_DECODE_V1, 'decode_v2': L.MASK_DECODE_V2}
 _CELL_MODES = {'sg_out': L.RASTER_BINARY_INCL, 'fg_only': L.RASTER_AREA_INCL, 'fg_bk': L.RASTER_AREA_FGBK}
 
 
+_MODE_IDS = {'decode_v1': L.MODE_DECODE_V1, 'decode_v2': L.MODE_DECODE_V2, 'sg_out': L.MODE_SG_OUT,
+             'fg_only': L.MODE_FG_ONLY, 'fg_bk': L.MODE_FG_BK}
+
+
 class _DsgfdFn(torch.autograd.Function):
-    """Fused forward+backward: the kernels stage gradients for grad_output == 1 during forward and
-    `backward` rescales them in place on the device only when grad_output != 1 (no host sync)."""
+    """Fused forward+backward through ONE C-ABI call (`dskd_dsgfd_step`): the kernels stage gradients for
+    grad_output == 1 during forward and `backward` rescales them in place on the device only when
+    grad_output != 1 (no host sync)."""
 
     @staticmethod
     def forward(ctx, plan: _DsgfdPlan, hs_student, hs_teacher, *feats):
@@ -137,108 +158,68 @@ class _DsgfdFn(torch.autograd.Function):
         s_feats, t_feats = feats[:nl], feats[nl:]
         dev = s_feats[0].device
         st = L.stream_of(s_feats[0])
-        C, N = plan.C, plan.N
+        C, N, P = plan.C, plan.N, plan.num_pairs
         levels, cells = L.levels_struct(plan.shapes)
-        row_mode = plan.mask_mode in _ROW_MODES
         want_feat_grad = plan.criterion == 'mse' and any(ctx.needs_input_grad[3:3 + nl])
         want_hs_grad = plan.mask_mode == 'decode_v1' and ctx.needs_input_grad[1]
 
-        # ---- masks
-        rows = id_pred = owner = cellw = None
-        P = plan.num_pairs
-        if row_mode:
-            hs_s2 = hs_student.reshape(-1, C)
-            hs_t2 = hs_teacher.reshape(-1, C)
-            if plan.mask_mode == 'decode_v1':
-                id_pred = torch.empty(max(P, 1), dtype=torch.int64, device=dev)
-                count = torch.empty(1, dtype=torch.int32, device=dev)
-                L.check(lib.dskd_select_prev_queries(L.ptr(plan.labels), plan.labels.numel(), L.ptr(plan.prev_mask),
-                                                     plan.num_classes, P, L.ptr(id_pred), L.ptr(count), st),
-                        'dskd_select_prev_queries')
-                if plan.validate and int(count.item()) < P:      # the reference raises IndexError here (:705)
-                    raise IndexError(f'{int(count.item())} student queries carry a previous-task label but '
-                                     f'{P} teacher detections must be paired (head_il.py:705)')
-            rows = torch.empty(max(P, 1), C, dtype=torch.float32, device=dev)
-            L.check(lib.dskd_mask_rows(_ROW_MODES[plan.mask_mode], L.ptr(hs_t2), L.ptr(hs_s2), L.ptr(plan.keepid),
-                                       L.ptr(id_pred), P, C, L.ptr(rows), st), 'dskd_mask_rows')
-            owner = torch.empty(N, cells, dtype=torch.int32, device=dev)
-            L.check(lib.dskd_raster_cells(L.RASTER_OWNER_EXCL, L.ptr(plan.boxes), L.ptr(plan.box_start), None, None,
-                                          L.ptr(plan.img_hw), N, plan.max_boxes, levels, len(plan.shapes), cells,
-                                          L.ptr(owner), st), 'dskd_raster_cells')
-        else:
-            cellw = torch.empty(N, cells, dtype=torch.float32, device=dev)
-            L.check(lib.dskd_raster_cells(_CELL_MODES[plan.mask_mode], L.ptr(plan.boxes), L.ptr(plan.box_start),
-                                          L.ptr(plan.gt_boxes), L.ptr(plan.gt_start), L.ptr(plan.img_hw), N,
-                                          plan.max_boxes, levels, len(plan.shapes), cells, L.ptr(cellw), st),
-                    'dskd_raster_cells')
-
-        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        a = L.DsgfdStepArgs()
+        a.criterion = L.CRIT_MSE if plan.criterion == 'mse' else L.CRIT_KL
+        a.mask_mode, a.layout = _MODE_IDS[plan.mask_mode], plan.layout
+        a.num_levels, a.N, a.C = len(plan.shapes), N, C
+        a.levels = levels
+        a.cells_per_image = cells
+        a.temperature = plan.temperature
         grad_feats: List[Optional[torch.Tensor]] = [None] * nl
-        grad_rows = None
-        if plan.criterion == 'mse':
-            a = L.DsgfdMseArgs()
-            a.layout, a.num_levels, a.N, a.C = plan.layout, len(plan.shapes), N, C
-            a.levels = levels
-            a.cells_per_image = cells
-            if want_feat_grad:
-                # one allocation for every level, each level 16-byte aligned
-                sizes = [f.numel() for f in s_feats]
-                offs, tot = [], 0
-                for s in sizes:
-                    offs.append(tot)
-                    tot += (s + 3) // 4 * 4
-                flat = torch.empty(tot, dtype=torch.float32, device=dev)
-                grad_feats = [flat[o:o + s].view_as(f) for o, s, f in zip(offs, sizes, s_feats)]
-            for l in range(nl):
-                a.d_student[l] = s_feats[l].data_ptr()
-                a.d_teacher[l] = t_feats[l].data_ptr()
-                a.d_grad_student[l] = grad_feats[l].data_ptr() if grad_feats[l] is not None else None
-            for l, s in enumerate(plan.scales):
-                a.scale[l] = s
-            if row_mode:
-                energy = torch.zeros(max(P, 1), C, dtype=torch.float32, device=dev)
-                a.d_owner, a.d_rows, a.d_energy, a.num_pairs = owner.data_ptr(), rows.data_ptr(), energy.data_ptr(), P
-                L.check(lib.dskd_dsgfd_mse_fwd_bwd(a, st), 'dskd_dsgfd_mse_fwd_bwd')
-                # loss = sum rows^2 * energy ; d loss / d rows = 2 * rows * energy (in place over energy)
-                L.check(lib.dskd_dsgfd_mse_finish(L.ptr(rows), L.ptr(energy), P, C, L.ptr(loss),
-                                                  L.ptr(energy) if want_hs_grad else None, st), 'dskd_dsgfd_mse_finish')
-                grad_rows = energy
-            else:
-                acc = torch.zeros(1, dtype=torch.float64, device=dev)
-                a.d_cell_weight, a.d_loss = cellw.data_ptr(), acc.data_ptr()
-                L.check(lib.dskd_dsgfd_mse_fwd_bwd(a, st), 'dskd_dsgfd_mse_fwd_bwd')
-                L.check(lib.dskd_f64_to_f32(L.ptr(acc), L.ptr(loss), 1, 1.0, st), 'dskd_f64_to_f32')
-        else:
-            a = L.DsgfdKlArgs()
-            a.num_levels, a.N, a.C = len(plan.shapes), N, C
-            a.levels = levels
-            a.cells_per_image = cells
-            a.temperature = plan.temperature
-            for l in range(nl):
-                a.d_student[l] = s_feats[l].data_ptr()
-                a.d_teacher[l] = t_feats[l].data_ptr()
-            for l, s in enumerate(plan.scales):
-                a.scale[l] = s
-            acc = torch.zeros(1, dtype=torch.float64, device=dev)
-            a.d_loss = acc.data_ptr()
-            if row_mode:
-                a.d_owner, a.d_rows, a.num_pairs = owner.data_ptr(), rows.data_ptr(), P
-                if want_hs_grad:
-                    grad_rows = torch.zeros(max(P, 1), C, dtype=torch.float32, device=dev)
-                    a.d_grad_rows = grad_rows.data_ptr()
-            else:
-                a.d_cell_weight = cellw.data_ptr()
-            L.check(lib.dskd_dsgfd_kl_fwd_bwd(a, st), 'dskd_dsgfd_kl_fwd_bwd')
-            L.check(lib.dskd_f64_to_f32(L.ptr(acc), L.ptr(loss), 1, 1.0, st), 'dskd_f64_to_f32')
-
+        if want_feat_grad:
+            # one allocation for every level, each level 16-byte aligned
+            sizes = [f.numel() for f in s_feats]
+            offs, tot = [], 0
+            for sz in sizes:
+                offs.append(tot)
+                tot += (sz + 3) // 4 * 4
+            flat = torch.empty(tot, dtype=torch.float32, device=dev)
+            grad_feats = [flat[o:o + sz].view_as(f) for o, sz, f in zip(offs, sizes, s_feats)]
+        for l in range(nl):
+            a.d_student[l] = s_feats[l].data_ptr()
+            a.d_teacher[l] = t_feats[l].data_ptr()
+            a.d_grad_student[l] = grad_feats[l].data_ptr() if grad_feats[l] is not None else None
+        for l, sc in enumerate(plan.scales):
+            a.scale[l] = sc
         grad_hs = None
-        if want_hs_grad:
-            grad_hs = torch.zeros_like(hs_student, dtype=torch.float32).contiguous()
-            L.check(lib.dskd_mask_rows_bwd(L.ptr(hs_t2), L.ptr(hs_s2), L.ptr(plan.keepid), L.ptr(id_pred), L.ptr(rows),
-                                           L.ptr(grad_rows), P, C, L.ptr(grad_hs), st), 'dskd_mask_rows_bwd')
+        if plan.mask_mode in _ROW_MODES:
+            a.d_hs_teacher = hs_teacher.data_ptr()
+            a.d_teacher_keepid = plan.keepid.data_ptr()
+            a.num_query_rows = hs_teacher.numel() // C
+            if plan.mask_mode == 'decode_v1':
+                a.d_hs_student = hs_student.data_ptr()
+                a.d_student_labels = plan.labels.data_ptr()
+                a.d_prev_mask = plan.prev_mask.data_ptr()
+                if want_hs_grad:
+                    grad_hs = torch.empty(hs_student.shape, dtype=torch.float32, device=dev)
+                    a.d_grad_hs_student = grad_hs.data_ptr()
+        a.num_classes = plan.num_classes
+        a.d_boxes, a.d_box_start, a.d_img_hw = plan.boxes.data_ptr(), plan.box_start.data_ptr(), plan.img_hw.data_ptr()
+        if plan.gt_boxes is not None:
+            a.d_gt_boxes, a.d_gt_start = plan.gt_boxes.data_ptr(), plan.gt_start.data_ptr()
+        a.num_pairs, a.max_boxes_per_image = P, plan.max_boxes
+        out = torch.empty(2, dtype=torch.float32, device=dev)          # [loss, matched count (int32 bits)]
+        a.d_loss = out.data_ptr()
+        a.d_matched_count = out.data_ptr() + 4
+        nbytes = lib.dskd_dsgfd_step_workspace_bytes(N, cells, P, C)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        a.d_workspace, a.workspace_bytes = ws.data_ptr(), nbytes
+        if profiling.enabled:
+            a.ev_kernel_begin, a.ev_kernel_end = profiling.new_event_pair(dev)
+        L.check(lib.dskd_dsgfd_step(a, st), 'dskd_dsgfd_step')
+        if plan.validate and plan.mask_mode == 'decode_v1':
+            count = int(out[1:].view(torch.int32).item())               # one host sync, opt-in
+            if count < P:                                               # the reference raises IndexError here (:705)
+                raise IndexError(f'{count} student queries carry a previous-task label but {P} teacher '
+                                 f'detections must be paired (head_il.py:705)')
         ctx.staged = (grad_hs, grad_feats)
         ctx.nl = nl
-        return loss.reshape(())
+        return out[0]
 
     @staticmethod
     def backward(ctx, grad_out):
@@ -403,13 +384,10 @@ class _BcddFn(torch.autograd.Function):
         dist = torch.empty(2, num_prev, num_prev, dtype=torch.float32, device=dev)
         loss = torch.empty(1, dtype=torch.float32, device=dev)
         grad_proto = torch.empty(num_classes, C + 1, dtype=torch.float32, device=dev) if want_grad else None
-        L.check(lib.dskd_bcdd_distance_loss(L.ptr(proto), num_classes, C, num_prev, reduction, loss_weight, grad_scale,
-                                            L.ptr(dist), L.ptr(loss), L.ptr(grad_proto), st), 'dskd_bcdd_distance_loss')
-        grad_hs = None
-        if want_grad:
-            grad_hs = torch.empty_like(hs_student, dtype=torch.float32).contiguous()
-            L.check(lib.dskd_bcdd_scatter_grad(L.ptr(grad_proto), L.ptr(labels), hs_s2.shape[0], L.ptr(prev_mask),
-                                               num_classes, C, L.ptr(grad_hs), st), 'dskd_bcdd_scatter_grad')
+        grad_hs = torch.empty(hs_student.shape, dtype=torch.float32, device=dev) if want_grad else None
+        L.check(lib.dskd_bcdd_loss_and_grad(L.ptr(proto), num_classes, C, num_prev, reduction, loss_weight, grad_scale,
+                                            L.ptr(labels), hs_s2.shape[0], L.ptr(prev_mask), L.ptr(dist), L.ptr(loss),
+                                            L.ptr(grad_proto), L.ptr(grad_hs), st), 'dskd_bcdd_loss_and_grad')
         ctx.staged = grad_hs
         ctx.mark_non_differentiable(dist, proto)
         return loss.reshape(()), dist, proto

@@ -52,8 +52,8 @@ class DistillInputs:
     def to(self, device):
         dev = torch.device(device)
         a = dict(self.assignments)
-        for k in ('student_labels', 'teacher_keepid', 'teacher_labels', 'img_shapes'):
-            a[k] = a[k].to(dev)
+        for k in ('student_labels', 'teacher_keepid', 'teacher_labels'):      # img_shapes stays on the host,
+            a[k] = a[k].to(dev)                                               # like mmdet's img_metas
         for k in ('teacher_bboxes', 'gt_bboxes'):
             a[k] = [b.to(dev) for b in a[k]]
         return DistillInputs(tuple(f.to(dev) for f in self.student_feats),
@@ -120,7 +120,7 @@ def make_distill_inputs(num_images: int = 2, num_prev: int = 40, seed: int = 123
         teacher_labels=torch.cat(t_labels).to(dev),
         teacher_bboxes=[b.to(dev) for b in t_boxes],
         gt_bboxes=[b.to(dev) for b in gt_boxes],
-        img_shapes=torch.tensor([list(img_hw)] * N, dtype=torch.int64, device=dev),
+        img_shapes=torch.tensor([list(img_hw)] * N, dtype=torch.int64),      # host side (img_metas)
         prev_labels=list(range(num_prev)),
         num_classes=num_classes,
     )

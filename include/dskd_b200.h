@@ -133,6 +133,15 @@ int dskd_dsgfd_mse_fwd_bwd(const DskdDsgfdMseArgs* args, void* stream);
 int dskd_dsgfd_mse_finish(const float* d_rows, const float* d_energy, int32_t num_pairs, int32_t C,
                           float* d_loss, float* d_grad_rows, void* stream);
 
+/* Row-mask finish in one launch (one CTA per pair): criterion 0 (mse): d_loss_acc[0] (double, caller
+ * zero-fills) += sum rows^2*energy and g = 2*rows*energy; criterion 1 (kl): g = d_energy_or_grad_rows as
+ * accumulated by dskd_dsgfd_kl_fwd_bwd.  If d_grad_hs_student != NULL, adds the softmax/abs backward of g
+ * (as dskd_mask_rows_bwd) into it. */
+int dskd_dsgfd_rows_finish(int32_t criterion, const float* d_hs_teacher, const float* d_hs_student,
+                           const int64_t* d_id_soft, const int64_t* d_id_pred, const float* d_rows,
+                           const float* d_energy_or_grad_rows, int32_t num_pairs, int32_t C,
+                           double* d_loss_acc, float* d_grad_hs_student, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * DSG-FD, KL-over-H (the shipped config: KnowledgeDistillationKLDivLoss(T, 'sum'), kd_loss.py:12-43
  * applied to [C,H,W] so softmax runs over H; target = student*mask, detached; pred = teacher*mask).
@@ -159,6 +168,50 @@ typedef struct {
 int dskd_dsgfd_kl_fwd_bwd(const DskdDsgfdKlArgs* args, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * DSG-FD in ONE call: everything gfl_deformable_detr_head_il.py:664-719 (or the sibling mask of
+ * mask_mode) does for a batch, forward + backward, as a fixed sequence of launches on `stream`:
+ * matched ids -> mask rows -> cell raster -> streaming kernel -> row finish.  This is what the
+ * `DSGFeatureDistillLoss` module calls; the fine-grained entry points above remain for tests/tools.
+ * ------------------------------------------------------------------------------------------- */
+enum { DSKD_CRIT_MSE = 0, DSKD_CRIT_KL = 1 };
+enum { DSKD_MODE_DECODE_V1 = 0, DSKD_MODE_DECODE_V2 = 1, DSKD_MODE_SG_OUT = 2, DSKD_MODE_FG_ONLY = 3,
+       DSKD_MODE_FG_BK = 4 };
+typedef struct {
+  int32_t criterion, mask_mode, layout;
+  int32_t num_levels, N, C;
+  DskdLevel levels[DSKD_MAX_LEVELS];
+  const float* d_student[DSKD_MAX_LEVELS];
+  const float* d_teacher[DSKD_MAX_LEVELS];
+  float* d_grad_student[DSKD_MAX_LEVELS]; /* NULL entries: no feature gradient (always for KL)           */
+  float scale[DSKD_MAX_LEVELS];
+  float temperature;
+  int64_t cells_per_image;
+  const float* d_hs_student;     /* [num_query_rows, C] (decode_v1)                                      */
+  const float* d_hs_teacher;     /* [num_query_rows, C] (decode_v1 / v2)                                 */
+  float* d_grad_hs_student;      /* [num_query_rows, C], fully overwritten; NULL = not needed            */
+  int32_t num_query_rows;
+  const int64_t* d_teacher_keepid;   /* [num_pairs] (decode_*)                                           */
+  const int64_t* d_student_labels;   /* [num_query_rows] (decode_v1)                                     */
+  const uint8_t* d_prev_mask;        /* [num_classes]   (decode_v1)                                      */
+  int32_t num_classes;
+  const float* d_boxes;          /* [num_pairs, 4] px xyxy, concatenated over images                     */
+  const int32_t* d_box_start;    /* [N+1]                                                                */
+  const float* d_gt_boxes;       /* sg_out only                                                          */
+  const int32_t* d_gt_start;     /* sg_out only                                                          */
+  const int32_t* d_img_hw;       /* [N,2]                                                                */
+  int32_t num_pairs, max_boxes_per_image;
+  float* d_loss;                 /* [1]                                                                  */
+  int32_t* d_matched_count;      /* [1] decode_v1: number of student queries with a previous label       */
+  void* d_workspace;             /* >= dskd_dsgfd_step_workspace_bytes(...) bytes, 256-byte aligned       */
+  int64_t workspace_bytes;
+  void* ev_kernel_begin;         /* optional cudaEvent_t pair recorded on `stream` right before / after   */
+  void* ev_kernel_end;           /* the streaming kernel (bench.py's roofline timing); NULL = off         */
+} DskdDsgfdStepArgs;
+
+int64_t dskd_dsgfd_step_workspace_bytes(int32_t N, int64_t cells_per_image, int32_t num_pairs, int32_t C);
+int dskd_dsgfd_step(const DskdDsgfdStepArgs* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * BCDD (head_il.py:525-555, :1197-1222)
  * ------------------------------------------------------------------------------------------- */
 /* Prototype sums + counts.  d_proto: [2, num_classes, C+1] (0 = teacher, 1 = student; last column =
@@ -182,6 +235,13 @@ int dskd_bcdd_prototypes(const float* d_hs_student, const int64_t* d_student_lab
 int dskd_bcdd_distance_loss(const float* d_proto, int32_t num_classes, int32_t C, int32_t L,
                             int32_t reduction, float loss_weight, float grad_scale, float* d_dist,
                             float* d_loss, float* d_grad_proto_student, void* stream);
+
+/* dskd_bcdd_distance_loss followed by dskd_bcdd_scatter_grad in one call (what the module uses after the
+ * optional all-reduce of d_proto).  d_grad_proto_student is a [num_classes, C+1] workspace. */
+int dskd_bcdd_loss_and_grad(const float* d_proto, int32_t num_classes, int32_t C, int32_t L, int32_t reduction,
+                            float loss_weight, float grad_scale, const int64_t* d_student_labels,
+                            int32_t num_student_rows, const uint8_t* d_prev_mask, float* d_dist, float* d_loss,
+                            float* d_grad_proto_student, float* d_grad_hs_student, void* stream);
 
 /* d_grad_hs_student[q,:] = d_grad_proto_student[label[q], :C] for flagged q, else 0 (fully overwritten). */
 int dskd_bcdd_scatter_grad(const float* d_grad_proto_student, const int64_t* d_student_labels,

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_binding_table_matches_header():
     names = set(declared_functions())
-    bound = set(_lib.SIGNATURES) | {'dskd_last_error', 'dskd_launch_count'}
+    bound = set(_lib.SIGNATURES) | {'dskd_last_error', 'dskd_launch_count', 'dskd_dsgfd_step_workspace_bytes'}
     assert names == bound, (sorted(names - bound), sorted(bound - names))
 
 
@@ -55,3 +55,5 @@ def test_struct_layout_matches_c():
     assert _lib.DsgfdMseArgs.levels.offset == 16
     assert _lib.DsgfdKlArgs.levels.offset == 16
     assert _lib.DsgfdMseArgs.d_student.offset == 16 + 16 * _lib.MAX_LEVELS
+    assert _lib.DsgfdStepArgs.levels.offset == 24
+    assert _lib.load().dskd_dsgfd_step_workspace_bytes(2, 22223, 50, 256) % 256 == 0

@@ -354,7 +354,7 @@ def test_registry_loss_modules_vs_reference_outputs():
             close(dskd_b200.MSELoss(red, lw)(pred, tgt), g.t(f'mse.{red}.{lw}'))
             close(dskd_b200.MSELoss(red, lw)(pred, tgt, weight=w), g.t(f'mse.{red}.{lw}.w'))
         for T in (1, 2, 10):
-            XX
+            close(dskd_b200.KnowledgeDistillationKLDivLoss(red, 1.5, T)(pred, tgt), g.t(f'kd.{red}.T{T}'), kd_rtol)
     close(dskd_b200.MSELoss('mean')(pred, tgt, weight=w, avg_factor=7.0), g.t('mse.mean.avg7'))
     close(dskd_b200.KnowledgeDistillationKLDivLoss('sum', 1.0, 2)(pred, tgt, weight=g.t('kd.weight').to(DEV)), g.t('kd.sum.T2.w'), kd_rtol)
     close(dskd_b200.KnowledgeDistillationKLDivLoss('mean', 1.0, 2)(pred, tgt, avg_factor=3.0), g.t('kd.mean.T2.avg3'), kd_rtol)

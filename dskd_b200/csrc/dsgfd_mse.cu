@@ -143,8 +143,10 @@ __device__ __forceinline__ void nchw_tile(const MseParams& prm, const int lvl, N
     }
   } else {
     const bool hi16 = lane & 16, hi8 = lane & 8;
-    for (int cb = 0; cb < kChanChunk; cb += U) {
-      Vec<VEC> s[U], t[U];
+    // Software pipeline: the loads of step cb+U are issued as soon as step cb's features have been consumed,
+    // so they are in flight while the per-box energy reduction of step cb runs.
+    Vec<VEC> s[U], t[U];
+    auto issue_loads = [&](int cb) {
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         if (mine) {
@@ -155,6 +157,9 @@ __device__ __forceinline__ void nchw_tile(const MseParams& prm, const int lvl, N
           for (int k = 0; k < VEC; ++k) s[u].v[k] = t[u].v[k] = 0.f;
         }
       }
+    };
+    issue_loads(0);
+    for (int cb = 0; cb < kChanChunk; cb += U) {
       // mask value of every cell for the U channels of this step: one 128-bit shared load per cell
       float m[VEC][U];
 #pragma unroll
@@ -186,6 +191,7 @@ __device__ __forceinline__ void nchw_tile(const MseParams& prm, const int lvl, N
         }
         if (G != nullptr && in_range) g.store(G + plane0 + (int64_t)(cb + u) * HW);
       }
+      if (cb + U < kChanChunk) issue_loads(cb + U);
       if (!CELL) {
         if (!overflow) {
           // energy[box, channel] += sum over this warp's cells owned by the box.  Transposed warp reduction:

@@ -202,11 +202,20 @@ def main():
 
     from dskd_b200 import profiling
 
+    bcdd_stream = torch.cuda.Stream()
+
     def step(feats, t_feats, hs, hs_t):
         for f in feats:
             f.grad = None
         hs.grad = None
-        loss = dsg(feats, t_feats, (hs, hs_t), inputs.assignments) + bcdd(None, None, (hs, hs_t), inputs.assignments)
+        # BCDD (latency-bound, and the only collective) runs on a side stream behind the HBM-bound DSG-FD kernel
+        cur = torch.cuda.current_stream()
+        bcdd_stream.wait_stream(cur)
+        with torch.cuda.stream(bcdd_stream):
+            loss_corr = bcdd(None, None, (hs, hs_t), inputs.assignments)
+        loss_fg = dsg(feats, t_feats, (hs, hs_t), inputs.assignments)
+        cur.wait_stream(bcdd_stream)
+        loss = loss_fg + loss_corr
         loss.backward()
         return loss
 

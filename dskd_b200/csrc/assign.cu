@@ -143,39 +143,54 @@ __global__ void __launch_bounds__(256) assign_targets_kernel(const int64_t* __re
   if (teacher_only) teacher_only[t] = (prev_mask && lab >= 0 && lab < num_classes && prev_mask[lab]) ? 1.f : 0.f;
 }
 
-// Single CTA ordered compaction (n is a few thousand): ids of the queries whose label is a previous-task label.
+// Single CTA ordered compaction (n is a few thousand): ids of the queries whose label is a previous-task
+// label.  Each of the 32 warps compacts a contiguous 256-label segment with ballots, a shuffle scan orders the
+// segments, then every warp copies its hits to their final slots: 2 block barriers per 8192 labels.
+constexpr int kSelSeg = 256;
+constexpr int kSelChunk = 32 * kSelSeg;
+
 __global__ void __launch_bounds__(1024) select_prev_kernel(const int64_t* __restrict__ labels, int n,
                                                            const uint8_t* __restrict__ prev_mask, int num_classes,
                                                            int max_out, int64_t* __restrict__ ids, int* __restrict__ count) {
-  __shared__ int warp_cnt[32];
-  __shared__ int running;
+  __shared__ int list[kSelChunk];
+  __shared__ int warp_off[33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) running = 0;
-  __syncthreads();
-  for (int base = 0; base < n; base += blockDim.x) {
-    const int q = base + threadIdx.x;
-    bool hit = false;
-    if (q < n) {
-      const int64_t lab = labels[q];
-      hit = lab >= 0 && lab < num_classes && prev_mask[lab] != 0;
+  int running = 0;
+  for (int base = 0; base < n; base += kSelChunk) {
+    int cnt = 0;
+    const int seg0 = base + warp * kSelSeg;
+    for (int it = 0; it < kSelSeg; it += 32) {
+      const int q = seg0 + it + lane;
+      bool hit = false;
+      if (q < n) {
+        const int64_t lab = labels[q];
+        hit = lab >= 0 && lab < num_classes && prev_mask[lab] != 0;
+      }
+      const unsigned b = __ballot_sync(0xffffffffu, hit);
+      if (hit) list[warp * kSelSeg + cnt + __popc(b & ((1u << lane) - 1u))] = q;
+      cnt += __popc(b);
     }
-    const unsigned b = __ballot_sync(0xffffffffu, hit);
-    if (lane == 0) warp_cnt[warp] = __popc(b);
+    if (lane == 0) warp_off[warp + 1] = cnt;
     __syncthreads();
-    int off = running, total = 0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
-      if (w < warp) off += warp_cnt[w];
-      total += warp_cnt[w];
+    if (warp == 0) {                       // inclusive scan of the 32 segment counts
+      int v = warp_off[lane + 1];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+      }
+      warp_off[lane + 1] = v;
+      if (lane == 0) warp_off[0] = 0;
     }
-    const int slot = off + __popc(b & ((1u << lane) - 1u));
-    if (hit && slot < max_out) ids[slot] = q;
     __syncthreads();
-    if (threadIdx.x == 0) running += total;
+    const int off = running + warp_off[warp];
+    for (int e = lane; e < cnt; e += 32)
+      if (off + e < max_out) ids[off + e] = list[warp * kSelSeg + e];
+    running += warp_off[32];
     __syncthreads();
   }
-  const int total = running;
-  for (int k = total + threadIdx.x; k < max_out; k += blockDim.x) ids[k] = 0;
-  if (threadIdx.x == 0 && count) count[0] = total;
+  for (int k = running + threadIdx.x; k < max_out; k += blockDim.x) ids[k] = 0;
+  if (threadIdx.x == 0 && count) count[0] = running;
 }
 
 }  // namespace dskd

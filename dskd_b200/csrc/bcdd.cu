@@ -8,8 +8,12 @@
 
 namespace dskd {
 
-// grid (num_classes, 2): side 0 = teacher, 1 = student.  Entries are compacted in ascending index
-// order (ballot prefix) so every class sums its rows in the reference's loop order.
+// grid (num_classes, 2): side 0 = teacher, 1 = student.  The rows of one class are gathered in ascending
+// index order (each warp compacts a contiguous segment of the label array with ballots, segments are then
+// walked in order), so every class sums its rows in the reference's Python-loop order: bit-exact sums.
+constexpr int kProtoSeg = 256;                 // labels per warp per chunk
+constexpr int kProtoChunk = 8 * kProtoSeg;     // labels per CTA per chunk
+
 __global__ void __launch_bounds__(256) bcdd_proto_kernel(const float* __restrict__ hs_s,
                                                          const int64_t* __restrict__ s_labels, int n_s,
                                                          const float* __restrict__ hs_t,
@@ -17,7 +21,7 @@ __global__ void __launch_bounds__(256) bcdd_proto_kernel(const float* __restrict
                                                          const int64_t* __restrict__ t_labels, int n_t,
                                                          const uint8_t* __restrict__ prev_mask, int C,
                                                          float* __restrict__ proto, int num_classes) {
-  __shared__ int64_t list[256];
+  __shared__ int list[kProtoChunk];
   __shared__ int warp_cnt[8];
   const int cls = blockIdx.x, side = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -29,28 +33,31 @@ __global__ void __launch_bounds__(256) bcdd_proto_kernel(const float* __restrict
   constexpr int kMaxPerThread = 4;  // supports C <= 1024
   float acc[kMaxPerThread] = {0.f, 0.f, 0.f, 0.f};
   int count = 0;
-  for (int base = 0; base < n && cls_on; base += blockDim.x) {
-    const int q = base + threadIdx.x;
-    const bool hit = (q < n) && (labels[q] == (int64_t)cls);
-    const unsigned b = __ballot_sync(0xffffffffu, hit);
-    if (lane == 0) warp_cnt[warp] = __popc(b);
+  for (int base = 0; base < n && cls_on; base += kProtoChunk) {
+    int cnt = 0;
+    const int seg0 = base + warp * kProtoSeg;
+    for (int it = 0; it < kProtoSeg; it += 32) {
+      const int q = seg0 + it + lane;
+      const bool hit = (q < n) && (labels[q] == (int64_t)cls);
+      const unsigned b = __ballot_sync(0xffffffffu, hit);
+      if (hit) list[warp * kProtoSeg + cnt + __popc(b & ((1u << lane) - 1u))] = q;
+      cnt += __popc(b);
+    }
+    if (lane == 0) warp_cnt[warp] = cnt;
     __syncthreads();
-    int off = 0, total = 0;
     for (int w = 0; w < 8; ++w) {
-      if (w < warp) off += warp_cnt[w];
-      total += warp_cnt[w];
-    }
-    if (hit) list[off + __popc(b & ((1u << lane) - 1u))] = side ? (int64_t)q : t_keep[q];
-    __syncthreads();
-    for (int e = 0; e < total; ++e) {
-      const float* row = hs + list[e] * (int64_t)C;
+      const int m = warp_cnt[w];
+      for (int e = 0; e < m; ++e) {
+        const int q = list[w * kProtoSeg + e];
+        const float* row = hs + (side ? (int64_t)q : t_keep[q]) * (int64_t)C;
 #pragma unroll
-      for (int k = 0; k < kMaxPerThread; ++k) {
-        const int c = threadIdx.x + k * 256;
-        if (c < C) acc[k] += row[c];
+        for (int k = 0; k < kMaxPerThread; ++k) {
+          const int c = threadIdx.x + k * 256;
+          if (c < C) acc[k] += row[c];
+        }
       }
+      count += m;
     }
-    count += total;
     __syncthreads();
   }
 #pragma unroll
@@ -71,26 +78,41 @@ __device__ __forceinline__ float proto_elem(const float* proto, int num_classes,
 }
 
 // grid L: CTA k computes row k of both distance matrices, then d loss / d (student sum row k).
+// STAGED: every CTA first normalises all 2*L prototypes into shared memory (2*L*C floats: 82 KB at L=40,
+// 144 KB at L=70) so the L x C inner loops never leave the SM; otherwise they are re-derived from global.
+template <bool STAGED>
 __global__ void __launch_bounds__(256) bcdd_distance_kernel(const float* __restrict__ proto, int num_classes,
                                                             int C, int L, float gcoef, float grad_scale,
                                                             float* __restrict__ dist,
                                                             float* __restrict__ grad_proto_s) {
   extern __shared__ float sm[];
-  float* ck_t = sm;            // [C] normalised teacher prototype k
-  float* ck_s = sm + C;        // [C] normalised student prototype k
-  float* coef = sm + 2 * C;    // [L]
+  float* coef = sm;                              // [L]
+  float* ck_t = sm + L;                          // [C] (not STAGED) | all teacher rows [L][C] (STAGED)
+  float* ck_s = STAGED ? sm + L + L * C : sm + L + C;
   const int k = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    ck_t[c] = proto_elem(proto, num_classes, C, 0, k, c);
-    ck_s[c] = proto_elem(proto, num_classes, C, 1, k, c);
+  if (STAGED) {
+    for (int idx = threadIdx.x; idx < L * C; idx += blockDim.x) {
+      const int j = idx / C, c = idx - j * C;
+      ck_t[idx] = proto_elem(proto, num_classes, C, 0, j, c);
+      ck_s[idx] = proto_elem(proto, num_classes, C, 1, j, c);
+    }
+  } else {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      ck_t[c] = proto_elem(proto, num_classes, C, 0, k, c);
+      ck_s[c] = proto_elem(proto, num_classes, C, 1, k, c);
+    }
   }
   __syncthreads();
+  const float* mine_t = STAGED ? ck_t + k * C : ck_t;
+  const float* mine_s = STAGED ? ck_s + k * C : ck_s;
   for (int j = warp; j < L; j += nw) {
     float st = 0.f, ss = 0.f;
     for (int c = lane; c < C; c += 32) {
-      const float dt = ck_t[c] - proto_elem(proto, num_classes, C, 0, j, c);
-      const float ds = ck_s[c] - proto_elem(proto, num_classes, C, 1, j, c);
+      const float ot = STAGED ? ck_t[j * C + c] : proto_elem(proto, num_classes, C, 0, j, c);
+      const float os = STAGED ? ck_s[j * C + c] : proto_elem(proto, num_classes, C, 1, j, c);
+      const float dt = mine_t[c] - ot;
+      const float ds = mine_s[c] - os;
       st = fmaf(dt, dt, st);
       ss = fmaf(ds, ds, ss);
     }
@@ -111,8 +133,11 @@ __global__ void __launch_bounds__(256) bcdd_distance_kernel(const float* __restr
   const float n_s = proto[((int64_t)num_classes + k) * (C + 1) + C];
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float g = 0.f;
-    const float ck = ck_s[c];
-    for (int j = 0; j < L; ++j) g = fmaf(coef[j], ck - proto_elem(proto, num_classes, C, 1, j, c), g);
+    const float ck = mine_s[c];
+    for (int j = 0; j < L; ++j) {
+      const float os = STAGED ? ck_s[j * C + c] : proto_elem(proto, num_classes, C, 1, j, c);
+      g = fmaf(coef[j], ck - os, g);
+    }
     if (n_t != 0.f) g = __fdiv_rn(g, n_s);
     grad_proto_s[(int64_t)k * (C + 1) + c] = g * grad_scale;
   }
@@ -178,8 +203,17 @@ extern "C" int dskd_bcdd_distance_loss(const float* d_proto, int32_t num_classes
   const float gcoef = 2.f * factor;  // d loss / d D_S = -gcoef * (D_T - D_S)
   if (d_grad_proto_student != nullptr)
     DSKD_CUDA_OK(cudaMemsetAsync(d_grad_proto_student, 0, sizeof(float) * (size_t)num_classes * (C + 1), st));
-  const size_t smem = sizeof(float) * (2 * (size_t)C + L);
-  bcdd_distance_kernel<<<L, 256, smem, st>>>(d_proto, num_classes, C, L, gcoef, grad_scale, d_dist, d_grad_proto_student);
+  const size_t staged = sizeof(float) * (2 * (size_t)L * C + L);
+  if (staged <= 200 * 1024) {
+    if (staged > 48 * 1024)
+      DSKD_CUDA_OK(cudaFuncSetAttribute(bcdd_distance_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged));
+    bcdd_distance_kernel<true><<<L, 256, staged, st>>>(d_proto, num_classes, C, L, gcoef, grad_scale, d_dist,
+                                                       d_grad_proto_student);
+  } else {
+    const size_t smem = sizeof(float) * (2 * (size_t)C + L);
+    bcdd_distance_kernel<false><<<L, 256, smem, st>>>(d_proto, num_classes, C, L, gcoef, grad_scale, d_dist,
+                                                      d_grad_proto_student);
+  }
   DSKD_LAUNCH_OK("bcdd_distance_kernel");
   bcdd_loss_kernel<<<1, 256, 0, st>>>(d_dist, L, factor, d_loss);
   DSKD_LAUNCH_OK("bcdd_loss_kernel");

@@ -9,7 +9,8 @@ from .registry import LOSSES, ASSIGNERS, build_loss, build_assigner, register_in
 from .losses import (DSGFeatureDistillLoss, BetweenClassDistanceLoss, MSELoss,  # noqa: F401
                      KnowledgeDistillationKLDivLoss)
 from .assigner import GFLHungarianAssigner, AssignResult, lsap  # noqa: F401
-from . import synth  # noqa: F401
+from . import synth, teacher, dist  # noqa: F401
+from .teacher import teacher_info_from_outputs  # noqa: F401
 
 __version__ = '0.1.0'
 register_into_mmdet()

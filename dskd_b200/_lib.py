@@ -89,6 +89,8 @@ SIGNATURES = {
     'dskd_bcdd_scatter_grad': [vp, vp, i32, vp, i32, i32, vp, vp],
     'dskd_cost_matrix': [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, i32, f32, f32, f32, vp, vp],
     'dskd_assign_targets': [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
+    'dskd_teacher_decode': [vp, vp, i32, i32, i32, i32, vp, f32, i32, vp, vp, vp, vp, vp, vp, vp],
+    'dskd_teacher_compact': [vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
     'dskd_lsap_f64': [vp, i32, i32, vp, vp],
     'dskd_lsap_batch_f32': [vp, i32, i32, i32, vp, vp, i32],
     'dskd_mse_elementwise': [vp, vp, vp, i64, f32, vp, vp, vp, vp, vp],

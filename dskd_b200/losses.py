@@ -19,6 +19,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib as L
+from . import dist as dskd_dist
 from . import profiling
 from .registry import LOSSES
 
@@ -376,10 +377,9 @@ class _BcddFn(torch.autograd.Function):
                                          L.ptr(t_labels), keepid.numel(), L.ptr(prev_mask), num_classes, C,
                                          L.ptr(proto), st), 'dskd_bcdd_prototypes')
         grad_scale = 1.0
-        if sync and torch.distributed.is_available() and torch.distributed.is_initialized():
+        if sync:
             # the ONLY cross-rank state of the hot path: 2 x num_classes x (C+1) fp32 sums + counts
-            torch.distributed.all_reduce(proto, op=torch.distributed.ReduceOp.SUM)
-            grad_scale = float(torch.distributed.get_world_size())
+            grad_scale, _ = dskd_dist.allreduce_prototypes(proto)
         want_grad = ctx.needs_input_grad[1]
         dist = torch.empty(2, num_prev, num_prev, dtype=torch.float32, device=dev)
         loss = torch.empty(1, dtype=torch.float32, device=dev)

@@ -273,6 +273,34 @@ int dskd_assign_targets(const int64_t* d_assigned_gt, int32_t num_problems, int3
                         int64_t* d_labels, float* d_bbox_targets, float* d_bbox_weights, float* d_teacher_only,
                         void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Teacher keep-ids: gfl_deformable_detr_head_il.py:1622-1668 (`_get_bboxes_single`,
+ * sigmoid branch, need_logits=True) + core/utils/misc.py:143-152 (`filter_scores_and_topk`) +
+ * detectors/deformable_detr_il.py:138-151 (keep-id flattening), for all images in one launch.
+ * ------------------------------------------------------------------------------------------- */
+/* d_cls: [N,Q,num_classes] logits and d_box: [N,Q,2+4*(reg_max+1)] sigmoid outputs of the teacher's LAST
+ * decoder layer (reg_max == 0: d_box is [N,Q,4] normalised cxcywh); d_img_hw int32 [N,2].  Per image the
+ * (query, class) pairs with sigmoid(logit) > score_thr are ordered by descending score (ties: lower
+ * q*num_classes + class first) and the first max_per_img (<= 1024) kept:
+ *   d_count  int32 [N]                  K_i
+ *   d_bboxes fp32  [N,max_per_img,4]    px xyxy, clamped to the image (:1658-1663); 16-byte aligned
+ *   d_scores fp32  [N,max_per_img]      sigmoid score
+ *   d_labels int64 [N,max_per_img]      class
+ *   d_keepid int64 [N,max_per_img]      q + Q*i  (deformable_detr_il.py:151)
+ *   d_logits fp32  [N,max_per_img,num_classes]  sigmoid(cls)[q,:] (`det_logits`, :1636); rows >= K_i untouched
+ * Slots r >= K_i hold 0 / -1.  Every output except d_count may be NULL. */
+int dskd_teacher_decode(const float* d_cls, const float* d_box, int32_t N, int32_t Q, int32_t num_classes,
+                        int32_t reg_max, const int32_t* d_img_hw, float score_thr, int32_t max_per_img,
+                        int32_t* d_count, float* d_bboxes, float* d_scores, int64_t* d_labels, int64_t* d_keepid,
+                        float* d_logits, void* stream);
+
+/* Ragged -> concatenated form the losses take: d_start int32 [N+1] prefix sums of d_count, and the first K_i
+ * rows of every image copied behind each other into d_cat_* (capacity N*max_per_img rows; NULL = skip). */
+int dskd_teacher_compact(const int32_t* d_count, int32_t N, int32_t max_per_img, const float* d_bboxes,
+                         const float* d_scores, const int64_t* d_labels, const int64_t* d_keepid, int32_t* d_start,
+                         float* d_cat_bboxes, float* d_cat_scores, int64_t* d_cat_labels, int64_t* d_cat_keepid,
+                         void* stream);
+
 /* scipy.optimize.linear_sum_assignment (rectangular_lsap, modified Jonker-Volgenant), float64, minimise.
  * h_cost row-major [rows, cols]; writes k = min(rows, cols) pairs sorted by row.  Bit-exact with SciPy. */
 int dskd_lsap_f64(const double* h_cost, int32_t rows, int32_t cols, int64_t* h_row_ind, int64_t* h_col_ind);

@@ -65,6 +65,14 @@ class DsgfdStepArgs(C.Structure):
                 ('ev_kernel_begin', _FP), ('ev_kernel_end', _FP)]
 
 
+class QmemArgs(C.Structure):
+    _fields_ = [('N', C.c_int32), ('C', C.c_int32), ('S', C.c_int64),
+                ('d_memory', _FP), ('d_hs_teacher', _FP), ('num_query_rows', C.c_int32),
+                ('d_keepid', _FP), ('d_scores', _FP), ('d_box_start', _FP),
+                ('num_pairs', C.c_int32), ('max_per_image', C.c_int32), ('temperature', C.c_float),
+                ('d_cell_weight', _FP), ('d_workspace', _FP), ('workspace_bytes', C.c_int64)]
+
+
 CRIT_MSE, CRIT_KL = 0, 1
 MODE_DECODE_V1, MODE_DECODE_V2, MODE_SG_OUT, MODE_FG_ONLY, MODE_FG_BK = 0, 1, 2, 3, 4
 
@@ -91,6 +99,7 @@ SIGNATURES = {
     'dskd_assign_targets': [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
     'dskd_teacher_decode': [vp, vp, i32, i32, i32, i32, vp, f32, i32, vp, vp, vp, vp, vp, vp, vp],
     'dskd_teacher_compact': [vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
+    'dskd_qmem_cell_weights': [C.POINTER(QmemArgs), vp],
     'dskd_lsap_f64': [vp, i32, i32, vp, vp],
     'dskd_lsap_batch_f32': [vp, i32, i32, i32, vp, vp, i32],
     'dskd_mse_elementwise': [vp, vp, vp, i64, f32, vp, vp, vp, vp, vp],
@@ -118,6 +127,14 @@ def load():
     lib.dskd_launch_count.argtypes = []
     lib.dskd_dsgfd_step_workspace_bytes.restype = C.c_int64
     lib.dskd_dsgfd_step_workspace_bytes.argtypes = [C.c_int32, C.c_int64, C.c_int32, C.c_int32]
+    lib.dskd_struct_size.restype = C.c_int64
+    lib.dskd_struct_size.argtypes = [C.c_int32]
+    for which, mirror in enumerate((Level, DsgfdMseArgs, DsgfdKlArgs, DsgfdStepArgs, QmemArgs)):
+        if lib.dskd_struct_size(which) != C.sizeof(mirror):
+            raise DskdError(f'{mirror.__name__}: ctypes mirror is {C.sizeof(mirror)} bytes, the library says '
+                            f'{lib.dskd_struct_size(which)} (include/dskd_b200.h and _lib.py are out of step)')
+    lib.dskd_qmem_workspace_bytes.restype = C.c_int64
+    lib.dskd_qmem_workspace_bytes.argtypes = [C.c_int32, C.c_int64, C.c_int32, C.c_int32]
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes

@@ -46,6 +46,17 @@ extern "C" int dskd_abi_version(void) { return DSKD_ABI_VERSION; }
 extern "C" const char* dskd_last_error(void) { return g_error; }
 extern "C" uint64_t dskd_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
+extern "C" int64_t dskd_struct_size(int32_t which) {
+  switch (which) {
+    case 0: return (int64_t)sizeof(DskdLevel);
+    case 1: return (int64_t)sizeof(DskdDsgfdMseArgs);
+    case 2: return (int64_t)sizeof(DskdDsgfdKlArgs);
+    case 3: return (int64_t)sizeof(DskdDsgfdStepArgs);
+    case 4: return (int64_t)sizeof(DskdQmemArgs);
+    default: return -1;
+  }
+}
+
 extern "C" int dskd_check_device(void) {
   int dev = 0;
   DSKD_CUDA_OK(cudaGetDevice(&dev));

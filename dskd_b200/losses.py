@@ -21,6 +21,7 @@ import torch.nn as nn
 from . import _lib as L
 from . import dist as dskd_dist
 from . import profiling
+from . import qmem as dskd_qmem
 from .registry import LOSSES
 
 _REDUCTIONS = (None, 'none', 'mean', 'sum')
@@ -250,7 +251,10 @@ class DSGFeatureDistillLoss(nn.Module):
             over the H axis, kd_loss.py:28-34 on [C,H,W]).
         T (float): KL temperature (kd_loss.py:58 asserts T >= 1).
         mask_mode (str): 'decode_v1' (:664-719), 'decode_v2' (:721-772), 'sg_out' (:860-925),
-            'fg_only' (:1082-1129), 'fg_bk' (_fg_bk.py:534-578).
+            'fg_only' (:1082-1129), 'fg_bk' (_fg_bk.py:534-578); 'qmem' -- NOT in the reference: the soft-ownership
+            mask from the query x memory contraction on tcgen05 (dskd_b200/qmem.py), temperature
+            `temp` (the head's unused ctor argument, head_il.py:90,124), confidences from
+            `assignments['teacher_scores']` (optional).
         feature_source (str): 'neck' -- 4 x [N,C,H,W] (:678-679); 'memory' -- ([S,N,C], spatial_shapes)
             (:866-880).  decode_* + 'kl' supports 'neck' only.
         validate (bool): read the matched-query count back (one host sync) and raise IndexError like
@@ -258,12 +262,16 @@ class DSGFeatureDistillLoss(nn.Module):
     """
 
     def __init__(self, loss_weight=1.0, reduction='sum', criterion='mse', T=2.0, mask_mode='decode_v1',
-                 feature_source='neck', validate=False):
+                 feature_source='neck', validate=False, temp=0.5):
         super().__init__()
         assert criterion in ('mse', 'kl'), criterion
-        assert mask_mode in _ROW_MODES or mask_mode in _CELL_MODES, mask_mode
+        assert mask_mode in _ROW_MODES or mask_mode in _CELL_MODES or mask_mode == 'qmem', mask_mode
         assert feature_source in ('neck', 'memory'), feature_source
         assert T >= 1
+        if mask_mode == 'qmem' and (criterion != 'mse' or feature_source != 'memory'):
+            raise ValueError("mask_mode='qmem' is the query x memory soft-ownership mask: masked MSE on encoder memory "
+                             "(criterion='mse', feature_source='memory')")
+        self.temp = float(temp)
         if mask_mode == 'fg_bk' and (criterion != 'mse' or feature_source != 'memory'):
             raise ValueError("mask_mode='fg_bk' is the area-mask MSE on encoder memory (_fg_bk.py:534-578)")
         if criterion == 'kl' and feature_source != 'neck':
@@ -336,6 +344,9 @@ class DSGFeatureDistillLoss(nn.Module):
             scales.append(base * r)
         plan.scales = scales
 
+        if self.mask_mode == 'qmem':
+            return self._forward_qmem(s_feats[0], t_feats[0], hs_teacher, assignments, scales, plan.shapes)
+
         # ---- assignments
         img_hw = _img_hw_list(assignments, N)
         gt = assignments.get('gt_bboxes') if self.mask_mode == 'sg_out' else None
@@ -358,6 +369,24 @@ class DSGFeatureDistillLoss(nn.Module):
         if hs_s.shape[-1] != C:
             raise L.DskdError(f'embedding width {hs_s.shape[-1]} != feature channels {C} (head_il.py:706 broadcasts them)')
         return _DsgfdFn.apply(plan, hs_s, hs_t, *s_feats, *t_feats)
+
+
+    def _forward_qmem(self, s_mem, t_mem, hs_teacher, assignments, scales, shapes):
+        """Soft-ownership mask (tcgen05 contraction) + streaming masked MSE; the mask is a constant like the
+        reference's other cell masks (sg_out / fg_only carry no gradient to the queries either)."""
+        dev = s_mem.device
+        N = s_mem.shape[1]
+        lens = [int(b.shape[0]) for b in assignments['teacher_bboxes']]
+        if len(lens) != N:
+            raise L.DskdError(f'{len(lens)} per-image detection lists for {N} images')
+        start = [0]
+        for k in lens:
+            start.append(start[-1] + k)
+        box_start = _meta_tensor(start, dev)
+        w = dskd_qmem.qmem_cell_weights(t_mem, hs_teacher, assignments['teacher_keepid'],
+                                        assignments.get('teacher_scores'), box_start, max(lens) if lens else 0, self.temp)
+        self.last_cell_weights = w
+        return dskd_qmem.CellWeightMseFn.apply(shapes, scales, w, s_mem, t_mem)
 
 
 # ----------------------------------------------------------------------------------------------

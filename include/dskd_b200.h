@@ -46,6 +46,9 @@ int dskd_abi_version(void);
 const char* dskd_last_error(void);
 /* Number of CUDA kernels this library has launched in this process (statistics for bench.py). */
 uint64_t dskd_launch_count(void);
+/* sizeof() of the argument structs as this library was compiled (0 DskdLevel, 1 DskdDsgfdMseArgs, 2 DskdDsgfdKlArgs,
+ * 3 DskdDsgfdStepArgs, 4 DskdQmemArgs; -1 otherwise): lets a foreign-language binding check its struct mirror. */
+int64_t dskd_struct_size(int32_t which);
 /* DSKD_OK iff the current CUDA device is sm_100 (B200).  There is no fallback arch. */
 int dskd_check_device(void);
 
@@ -210,6 +213,35 @@ typedef struct {
 
 int64_t dskd_dsgfd_step_workspace_bytes(int32_t N, int64_t cells_per_image, int32_t num_pairs, int32_t C);
 int dskd_dsgfd_step(const DskdDsgfdStepArgs* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Query x memory contraction (north_star's "query x memory mask").  NOT in the reference
+ * (no matmul exists in the IL head): an extension whose oracle is oracle/qmem.py.
+ * Replaces the hard box rectangles of head_il.py:688-706 by a soft ownership computed on tcgen05 tensor
+ * cores (tf32, fp32 accumulation in tensor memory, operands staged by TMA):
+ *   z[s,j] = <memory[s,i,:], hs_T[keepid[j],:]> / (sqrt(C) * temperature)       j over the K_i detections of image i
+ *   w[i,s] = sqrt( sum_j c_j e^z[s,j] / (1 + sum_j e^z[s,j]) )                   c_j = d_scores[j] (NULL: 1)
+ * The [S, K_i] score matrix never reaches HBM.  d_cell_weight [N,S] is the `cell-mask` input of
+ * dskd_dsgfd_mse_fwd_bwd (token index == cell index of the [S,N,C] layout).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t N, C;
+  int64_t S;                      /* tokens per image (sum of H*W over levels)                              */
+  const float* d_memory;          /* [S,N,C] teacher encoder memory (transformer.py:1053), 16-byte aligned  */
+  const float* d_hs_teacher;      /* [num_query_rows, C] teacher decoder embeddings, last layer             */
+  int32_t num_query_rows;
+  const int64_t* d_keepid;        /* [num_pairs] rows of d_hs_teacher (deformable_detr_il.py:151)           */
+  const float* d_scores;          /* [num_pairs] teacher confidences (`pred_scores`), or NULL               */
+  const int32_t* d_box_start;     /* [N+1] prefix offsets of the per-image detections                       */
+  int32_t num_pairs, max_per_image;
+  float temperature;              /* the head's unused `temp` ctor argument (head_il.py:90,124), default 0.5 */
+  float* d_cell_weight;           /* [N,S] out                                                              */
+  void* d_workspace;              /* >= dskd_qmem_workspace_bytes(...) bytes, 256-byte aligned               */
+  int64_t workspace_bytes;
+} DskdQmemArgs;
+
+int64_t dskd_qmem_workspace_bytes(int32_t N, int64_t S, int32_t C, int32_t max_per_image);
+int dskd_qmem_cell_weights(const DskdQmemArgs* args, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * BCDD (head_il.py:525-555, :1197-1222)

@@ -34,4 +34,4 @@ Third-party arithmetic on the path that is not vendored in the reference:
     through torch 2.11 CPU.
 """
 
-from . import boxes, losses, assign, dsgfd, bcdd  # noqa: F401
+from . import boxes, losses, assign, dsgfd, bcdd, qmem  # noqa: F401

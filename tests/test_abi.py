@@ -28,7 +28,8 @@ def test_library_exports_every_declared_symbol():
 
 def test_binding_table_matches_header():
     names = set(declared_functions())
-    bound = set(_lib.SIGNATURES) | {'dskd_last_error', 'dskd_launch_count', 'dskd_dsgfd_step_workspace_bytes'}
+    bound = set(_lib.SIGNATURES) | {'dskd_last_error', 'dskd_launch_count', 'dskd_dsgfd_step_workspace_bytes',
+                                   'dskd_qmem_workspace_bytes', 'dskd_struct_size'}
     assert names == bound, (sorted(names - bound), sorted(bound - names))
 
 
@@ -56,4 +57,10 @@ def test_struct_layout_matches_c():
     assert _lib.DsgfdKlArgs.levels.offset == 16
     assert _lib.DsgfdMseArgs.d_student.offset == 16 + 16 * _lib.MAX_LEVELS
     assert _lib.DsgfdStepArgs.levels.offset == 24
-    assert _lib.load().dskd_dsgfd_step_workspace_bytes(2, 22223, 50, 256) % 256 == 0
+    lib = _lib.load()
+    assert lib.dskd_dsgfd_step_workspace_bytes(2, 22223, 50, 256) % 256 == 0
+    for which, mirror in enumerate((_lib.Level, _lib.DsgfdMseArgs, _lib.DsgfdKlArgs, _lib.DsgfdStepArgs, _lib.QmemArgs)):
+        assert lib.dskd_struct_size(which) == ctypes.sizeof(mirror), mirror.__name__
+    assert lib.dskd_struct_size(99) == -1
+    # 300 queries -> two blocks of 160 resident rows; 100 -> one block of 112
+    assert lib.dskd_qmem_workspace_bytes(2, 22223, 256, 300) > lib.dskd_qmem_workspace_bytes(2, 22223, 256, 100) > 0

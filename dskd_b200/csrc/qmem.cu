@@ -11,17 +11,18 @@
 // cell masks because the MSE squares it (head_il.py:914,1119).  The reference has no such contraction
 // (SURVEY.md section 0.4); this is the unpinned extension row, its oracle is oracle/qmem.py.
 //
-// Kernel anatomy (one CTA per SM, persistent, 192 threads, cta_group::1):
+// Kernel anatomy (one CTA per SM, persistent, 320 threads, cta_group::1):
 //   warp 0   TMA producer : memory tiles [128 tokens x 32 ch] fp32 (one 128-byte swizzle row per token) through a
 //            ring of kAStages shared-memory stages; the query block [NB x C] of the current image is loaded
 //            once and stays resident in shared memory (it is the B operand of every tile of that image)
 //   warp 1   MMA issuer   : tcgen05.mma kind::tf32, M = 128 tokens, N = NB queries, K = 8 per instruction,
 //            fp32 accumulators in TMEM, kAccStages accumulator stages of kMaxNB columns
-//   warps 2-5 epilogue    : tcgen05.ld 32 lanes x 32 columns, online softmax in registers (thread = token),
-//            one coalesced 4-byte store per token
+//   warps 2-9 epilogue    : two sets of 4 warps alternating over the tiles; tcgen05.ld 32 lanes x 32 columns,
+//            online softmax in registers (thread = token), one coalesced 4-byte store per token
 // More than kMaxNB matched queries per image are split into query blocks handled by neighbouring CTAs (the
 // memory tile is then read from HBM once and from L2 nblk times) and merged by qmem_combine_kernel.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -33,7 +34,8 @@ constexpr int kMaxNB = 160;               // queries per block: UMMA N (multiple
 constexpr int kAStages = 4;               // memory-tile ring
 constexpr int kAccStages = 3;             // 3 x 160 = 480 of the 512 TMEM columns
 constexpr int kTmemCols = 512;
-constexpr int kQmemThreads = 192;
+constexpr int kEpiSets = 2;               // epilogue warp sets (4 warps each) alternating over the tiles
+constexpr int kQmemThreads = 64 + 128 * kEpiSets;
 constexpr uint32_t kAStageBytes = kTokTile * kSlabCh * 4;  // 16 KB
 
 struct QmemParams {
@@ -44,6 +46,7 @@ struct QmemParams {
   const float* cpad;        // [N, nblk, NB] confidences, zero padded
   float* part;              // [N*nblk][3][S] (max, den, num) when nblk > 1
   float* weight;            // [N, S]
+  int debug;                // DSKD_QMEM_DEBUG bits (perf experiments): 1 skip epilogue math, 2 skip MMA issue
 };
 
 // ------------------------------------------------------------------------------------------------ PTX
@@ -109,6 +112,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr)
       : "memory");
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -201,7 +209,7 @@ qmem_weight_kernel(const __grid_constant__ CUtensorMap tmap_mem, const __grid_co
           const uint64_t db = smem_desc_sw128(smem_q + ks * q_slab_bytes);
 #pragma unroll
           for (int kk = 0; kk < kSlabCh / 8; ++kk)  // 8 tf32 = 32 bytes along K per instruction: +2 in 16-byte units
-            umma_tf32(tmem_d, da + 2 * kk, db + 2 * kk, idesc, (ks | kk) ? 1u : 0u);
+            if (!(p.debug & 2)) umma_tf32(tmem_d, da + 2 * kk, db + 2 * kk, idesc, (ks | kk) ? 1u : 0u);
           umma_commit(bar_empty + 8 * stage);  // frees the memory-tile stage when those MMAs retire
           if (++stage == kAStages) { stage = 0; phase ^= 1; }
         }
@@ -214,50 +222,64 @@ qmem_weight_kernel(const __grid_constant__ CUtensorMap tmap_mem, const __grid_co
     __syncwarp();
   } else {
     // ================================================================ epilogue: thread = token (TMEM lane)
-    const int sub = warp & 3;  // TMEM sub-partition this warp may read: lanes [32*sub, 32*sub + 32)
-    uint32_t acc = 0, acc_phase = 0;
+    // Two sets of four warps alternate over the tiles, so each SM sub-partition always has two epilogue warps to
+    // interleave (a single warp per sub-partition is bound by its own dependent-issue latency).
+    const int sub = warp & 3;               // TMEM sub-partition this warp may read: lanes [32*sub, 32*sub + 32)
+    const int eset = (warp - 2) >> 2;
     const bool single = p.nblk == 1;
-    for (long long t = t_begin; t < t_end; ++t) {
+    const float scale = p.score_scale;
+    long long n = eset;                     // ordinal of the tile inside this CTA: fixes the accumulator stage
+    for (long long t = t_begin + eset; t < t_end; t += kEpiSets, n += kEpiSets) {
+      const uint32_t acc = (uint32_t)(n % kAccStages), acc_phase = (uint32_t)((n / kAccStages) & 1);
       const int img = (int)(t / p.tiles_per_image), tt = (int)(t % p.tiles_per_image);
       const int K = p.box_start[img + 1] - p.box_start[img];
-      const int kv = max(0, min(p.NB, K - b * p.NB));  // valid query columns of this block
-      const float* __restrict__ cj = p.cpad + ((long long)img * p.nblk + b) * p.NB;
+      const int kv = (p.debug & 1) ? 0 : max(0, min(p.NB, K - b * p.NB));  // valid query columns of this block
+      const float4* __restrict__ cj = reinterpret_cast<const float4*>(p.cpad + ((long long)img * p.nblk + b) * p.NB);
       mbar_wait(bar_accfull + 8 * acc, acc_phase);
       tc_fence_after();
       // the null logit 0 is part of the softmax; with several query blocks it is added once, by the combine kernel
-      float mx = single ? 0.f : -1e30f, den = single ? 1.f : 0.f, num = 0.f;
+      float mx = single ? 0.f : -1e30f, den0 = single ? 1.f : 0.f, den1 = 0.f, num0 = 0.f, num1 = 0.f;
       const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + acc * kMaxNB;
       for (int c0 = 0; c0 < kv; c0 += 32) {
+        float c[32];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {  // confidences of these 32 columns: warp-uniform 128-bit loads (L1 broadcast)
+          const float4 c4 = __ldg(cj + (c0 >> 2) + q);
+          c[4 * q] = c4.x; c[4 * q + 1] = c4.y; c[4 * q + 2] = c4.z; c[4 * q + 3] = c4.w;
+        }
         uint32_t v[32];
         tmem_ld32(taddr + c0, v);
         tmem_ld_wait();
-        const int nc = min(32, kv - c0);
-        float cm = -1e30f;
+        const int nc = kv - c0;
+        if (nc < 32) {  // padded query rows are zero vectors (score 0): take them out of the softmax
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float z = __uint_as_float(v[j]) * p.score_scale;
-          v[j] = __float_as_uint(z);
-          if (j < nc) cm = fmaxf(cm, z);
+          for (int j = 0; j < 32; ++j)
+            if (j >= nc) v[j] = 0xff800000u;
         }
+        float vm = __uint_as_float(v[0]);
+#pragma unroll
+        for (int j = 1; j < 32; ++j) vm = fmaxf(vm, __uint_as_float(v[j]));
+        const float cm = vm * scale;
         if (cm > mx) {
-          const float r = exp2f(mx - cm);
-          den *= r;
-          num *= r;
+          const float r = ex2_approx(mx - cm);
+          den0 *= r; den1 *= r; num0 *= r; num1 *= r;
           mx = cm;
         }
+        const float nmx = -mx;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (j < nc) {
-            const float e = exp2f(__uint_as_float(v[j]) - mx);
-            den += e;
-            num = fmaf(__ldg(cj + c0 + j), e, num);
-          }
+        for (int j = 0; j < 32; j += 2) {
+          const float e0 = ex2_approx(fmaf(__uint_as_float(v[j]), scale, nmx));
+          const float e1 = ex2_approx(fmaf(__uint_as_float(v[j + 1]), scale, nmx));
+          den0 += e0;
+          den1 += e1;
+          num0 = fmaf(c[j], e0, num0);
+          num1 = fmaf(c[j + 1], e1, num1);
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_accempty + 8 * acc);
-      if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+      const float den = den0 + den1, num = num0 + num1;
       const int tok = tt * kTokTile + sub * 32 + lane;
       if (tok < p.S) {
         if (single) {
@@ -430,6 +452,7 @@ extern "C" int dskd_qmem_cell_weights(const DskdQmemArgs* a, void* stream) {
   p.cpad = cpad;
   p.part = part;
   p.weight = a->d_cell_weight;
+  { const char* dbg = getenv("DSKD_QMEM_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
   const size_t smem = 1024 + (size_t)plan.NB * a->C * 4 + (size_t)kAStages * kAStageBytes + 256;
   DSKD_CUDA_OK(cudaFuncSetAttribute(qmem_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long groups = std::max(1ll, std::min<long long>(kNumSMs / plan.nblk, p.total_tiles));

@@ -65,7 +65,8 @@ def test_temperature_and_large_scores_do_not_overflow():
     ref = oq.qmem_cell_weights(t_mem, big.hs_teacher, cpu.assignments['teacher_keepid'], sc, counts, 1.0, tf32='trunc',
                                dtype=torch.float64)
     assert torch.isfinite(w).all()
-    torch.testing.assert_close(w.double(), ref, rtol=0, atol=TIGHT)
+    # |z| in the hundreds: fp32 rounding of z itself (1e-7 * 300) shows up in e^z
+    torch.testing.assert_close(w.double(), ref, rtol=0, atol=1e-4)
 
 
 def test_images_without_detections_get_zero_weight():

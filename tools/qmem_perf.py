@@ -34,6 +34,17 @@ def bench(N, K, S=22223, C=256, Q=None, iters=20):
 
 
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'one':
+        bench(int(sys.argv[2]), int(sys.argv[3]), iters=3)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'exp':
+        for dbg in ('0', '1', '2', '3'):
+            os.environ['DSKD_QMEM_DEBUG'] = dbg
+            print('debug', dbg)
+            bench(16, 160)
+            bench(1, 160, S=22223 * 16)
+            bench(16, 96)
+        sys.exit(0)
     for N in (2, 16):
         for K in (100, 160, 300, 600, 900):
             bench(N, K)

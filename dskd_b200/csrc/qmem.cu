@@ -13,7 +13,7 @@
 //
 // Kernel anatomy (one CTA per SM, persistent, 320 threads, cta_group::1):
 //   warp 0   TMA producer : memory tiles [128 tokens x 32 ch] fp32 (one 128-byte swizzle row per token) through a
-//            ring of kAStages shared-memory stages; the query block [NB x C] of the current image is loaded
+//            ring of up to 12 shared-memory stages (whatever fits beside the queries); the query block [NB x C] of the current image is loaded
 //            once and stays resident in shared memory (it is the B operand of every tile of that image)
 //   warp 1   MMA issuer   : tcgen05.mma kind::tf32, M = 128 tokens, N = NB queries, K = 8 per instruction,
 //            fp32 accumulators in TMEM, kAccStages accumulator stages of kMaxNB columns
@@ -21,6 +21,9 @@
 //            online softmax in registers (thread = token), one coalesced 4-byte store per token
 // More than kMaxNB matched queries per image are split into query blocks handled by neighbouring CTAs (the
 // memory tile is then read from HBM once and from L2 nblk times) and merged by qmem_combine_kernel.
+// Measured dead ends (tools/qmem_perf.py, profiles/r1/qmem_notes.md): an L2 prefetch ahead of the ring raised DRAM
+// traffic by 60 % and cost 30 %; TMA multicast of the tile to the query blocks of a cluster was 10-20 % slower than
+// letting each CTA fetch it (the lock-step release of a stage by every CTA outweighs the saved L2 requests).
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -31,7 +34,7 @@ namespace dskd {
 constexpr int kTokTile = 128;             // UMMA M: tokens per tile = TMEM lanes
 constexpr int kSlabCh = 32;               // fp32 channels per 128-byte swizzle row = one TMA box row
 constexpr int kMaxNB = 160;               // queries per block: UMMA N (multiple of 16) and TMEM columns per stage
-constexpr int kAStages = 4;               // memory-tile ring
+constexpr int kMaxAStages = 12;           // memory-tile ring: as many 16 KB stages as fit beside the resident queries
 constexpr int kAccStages = 3;             // 3 x 160 = 480 of the 512 TMEM columns
 constexpr int kTmemCols = 512;
 constexpr int kEpiSets = 2;               // epilogue warp sets (4 warps each) alternating over the tiles
@@ -46,6 +49,8 @@ struct QmemParams {
   const float* cpad;        // [N, nblk, NB] confidences, zero padded
   float* part;              // [N*nblk][3][S] (max, den, num) when nblk > 1
   float* weight;            // [N, S]
+  int stages;               // memory-tile ring depth (<= kMaxAStages)
+  int n_lo, n_hi;           // pair mode: columns of the two MMAs per k-step (n_hi may be 0); NB = n_lo + n_hi
   int debug;                // DSKD_QMEM_DEBUG bits (perf experiments): 1 skip epilogue math, 2 skip MMA issue
 };
 
@@ -120,6 +125,90 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- CTA-pair (cta_group::2) variants
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 rem;\n\t"
+      "mapa.shared::cluster.u32 rem, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [rem];\n\t"
+      "}" ::"r"(bar), "r"(cta)
+      : "memory");
+}
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a pair: addresses the leader's barrier
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// M = 256 over the CTA pair: each CTA supplies its 128 rows of A and half of the rows of B; issued by the leader only
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the barrier at this offset in BOTH CTAs of the pair when the leader's previously issued MMAs complete
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+
+// One 32-column chunk of the online softmax of a token row (thread = token): v = raw scores from TMEM, c = confidences.
+__device__ __forceinline__ void softmax_chunk(uint32_t (&v)[32], const float4* __restrict__ c4p, int nc, float scale, float& mx,
+                                              float& den0, float& den1, float& num0, float& num1) {
+  float c[32];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {  // confidences of these 32 columns: warp-uniform 128-bit loads (L1 broadcast)
+    const float4 c4 = __ldg(c4p + q);
+    c[4 * q] = c4.x; c[4 * q + 1] = c4.y; c[4 * q + 2] = c4.z; c[4 * q + 3] = c4.w;
+  }
+  if (nc < 32) {  // padded query rows are zero vectors (score 0): take them out of the softmax
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j >= nc) v[j] = 0xff800000u;
+  }
+  float vm = __uint_as_float(v[0]);
+#pragma unroll
+  for (int j = 1; j < 32; ++j) vm = fmaxf(vm, __uint_as_float(v[j]));
+  const float cm = vm * scale;
+  if (cm > mx) {
+    const float r = ex2_approx(mx - cm);
+    den0 *= r; den1 *= r; num0 *= r; num1 *= r;
+    mx = cm;
+  }
+  const float nmx = -mx;
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+    const float e0 = ex2_approx(fmaf(__uint_as_float(v[j]), scale, nmx));
+    const float e1 = ex2_approx(fmaf(__uint_as_float(v[j + 1]), scale, nmx));
+    den0 += e0;
+    den1 += e1;
+    num0 = fmaf(c[j], e0, num0);
+    num1 = fmaf(c[j + 1], e1, num1);
+  }
+}
+
 // Shared-memory matrix descriptor, K-major, SWIZZLE_128B: rows of 128 bytes, 8-row swizzle atoms 1024 bytes apart
 // (SBO), LBO unused, descriptor version 1 (sm_100), base offset 0 (tiles are 1024-byte aligned).
 __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr) {
@@ -127,7 +216,7 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr) {
 }
 
 // ------------------------------------------------------------------------------------------------ kernel
-// dynamic shared memory (1024-byte aligned): [Q slabs: C/32 x NB x 128 B][A ring: kAStages x 16 KB][barriers]
+// dynamic shared memory (1024-byte aligned): [Q slabs: C/32 x NB x 128 B][A ring: p.stages x 16 KB][barriers]
 __global__ void __launch_bounds__(kQmemThreads, 1)
 qmem_weight_kernel(const __grid_constant__ CUtensorMap tmap_mem, const __grid_constant__ CUtensorMap tmap_q,
                    const __grid_constant__ QmemParams p) {
@@ -137,9 +226,10 @@ qmem_weight_kernel(const __grid_constant__ CUtensorMap tmap_mem, const __grid_co
   const uint32_t q_slab_bytes = (uint32_t)p.NB * 128u;
   const uint32_t smem_q = smem_base;
   const uint32_t smem_a = smem_q + (uint32_t)num_slabs * q_slab_bytes;
+  const int kAStages = p.stages;
   const uint32_t bars = smem_a + kAStages * kAStageBytes;
   // barrier slots (8 bytes each)
-  const uint32_t bar_full = bars, bar_empty = bars + 8 * kAStages, bar_qfull = bars + 16 * kAStages,
+  const uint32_t bar_full = bars, bar_empty = bars + 8 * kMaxAStages, bar_qfull = bars + 16 * kMaxAStages,
                  bar_qempty = bar_qfull + 8, bar_accfull = bar_qfull + 16, bar_accempty = bar_accfull + 8 * kAccStages,
                  tmem_slot = bar_accempty + 8 * kAccStages;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -241,40 +331,10 @@ qmem_weight_kernel(const __grid_constant__ CUtensorMap tmap_mem, const __grid_co
       float mx = single ? 0.f : -1e30f, den0 = single ? 1.f : 0.f, den1 = 0.f, num0 = 0.f, num1 = 0.f;
       const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + acc * kMaxNB;
       for (int c0 = 0; c0 < kv; c0 += 32) {
-        float c[32];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {  // confidences of these 32 columns: warp-uniform 128-bit loads (L1 broadcast)
-          const float4 c4 = __ldg(cj + (c0 >> 2) + q);
-          c[4 * q] = c4.x; c[4 * q + 1] = c4.y; c[4 * q + 2] = c4.z; c[4 * q + 3] = c4.w;
-        }
         uint32_t v[32];
         tmem_ld32(taddr + c0, v);
         tmem_ld_wait();
-        const int nc = kv - c0;
-        if (nc < 32) {  // padded query rows are zero vectors (score 0): take them out of the softmax
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j >= nc) v[j] = 0xff800000u;
-        }
-        float vm = __uint_as_float(v[0]);
-#pragma unroll
-        for (int j = 1; j < 32; ++j) vm = fmaxf(vm, __uint_as_float(v[j]));
-        const float cm = vm * scale;
-        if (cm > mx) {
-          const float r = ex2_approx(mx - cm);
-          den0 *= r; den1 *= r; num0 *= r; num1 *= r;
-          mx = cm;
-        }
-        const float nmx = -mx;
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          const float e0 = ex2_approx(fmaf(__uint_as_float(v[j]), scale, nmx));
-          const float e1 = ex2_approx(fmaf(__uint_as_float(v[j + 1]), scale, nmx));
-          den0 += e0;
-          den1 += e1;
-          num0 = fmaf(c[j], e0, num0);
-          num1 = fmaf(c[j + 1], e1, num1);
-        }
+        softmax_chunk(v, cj + (c0 >> 2), kv - c0, scale, mx, den0, den1, num0, num1);
       }
       tc_fence_before();
       __syncwarp();
@@ -301,14 +361,179 @@ qmem_weight_kernel(const __grid_constant__ CUtensorMap tmap_mem, const __grid_co
   }
 }
 
-// Query rows of every (image, block), zero padded to NB rows: Qpad[N, nblk, NB, C] and cpad[N, nblk, NB].
+// ------------------------------------------------------------------------------------------------ CTA-pair kernel
+// More than kMaxNB queries per image: two CTAs of a cluster (one TPC) work as one tcgen05.mma.cta_group::2 unit on a
+// 256-token tile.  Each CTA streams ITS 128 tokens of the memory (every byte is read once, by one SM) and keeps HALF of
+// the query block resident (<= 160 rows), so up to 320 queries are contracted per byte of memory read -- twice the
+// arithmetic intensity of the single-CTA kernel at the same shared-memory footprint.  The leader CTA issues the MMAs
+// (two per k-step when NB > 256: N = n_lo and N = n_hi); completion is multicast to the barriers of both CTAs.
+// TMEM holds one accumulator stage of NB <= 320 columns per CTA; the two epilogue warp sets split its 32-column
+// chunks between them and write per-set partials that qmem_combine_kernel merges.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQmemThreads, 1)
+qmem_weight_pair_kernel(const __grid_constant__ CUtensorMap tmap_mem, const __grid_constant__ CUtensorMap tmap_q,
+                        const __grid_constant__ QmemParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int num_slabs = p.C / kSlabCh;
+  const int half = p.NB / 2;                                // query rows resident in this CTA
+  const uint32_t q_slab_bytes = (uint32_t)half * 128u;
+  const uint32_t smem_q = smem_base;
+  const uint32_t smem_a = smem_q + (uint32_t)num_slabs * q_slab_bytes;
+  const int kAStages = p.stages;
+  const uint32_t bars = smem_a + kAStages * kAStageBytes;
+  const uint32_t bar_full = bars, bar_empty = bars + 8 * kMaxAStages, bar_qfull = bars + 16 * kMaxAStages,
+                 bar_qempty = bar_qfull + 8, bar_accfull = bar_qfull + 16, bar_accempty = bar_qfull + 24,
+                 tmem_slot = bar_qfull + 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  // work of this pair: query block b of a contiguous range of (image, 256-token tile) pairs
+  const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int b = pair_id % p.nblk;
+  const long long g = pair_id / p.nblk, G = num_pairs / p.nblk;
+  const long long t_begin = g * p.total_tiles / G, t_end = (g + 1) * p.total_tiles / G;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kAStages; ++s) { mbar_init(bar_full + 8 * s, 2); mbar_init(bar_empty + 8 * s, 1); }
+    mbar_init(bar_qfull, 2);
+    mbar_init(bar_qempty, 1);
+    mbar_init(bar_accfull, 1);
+    mbar_init(bar_accempty, 2 * 4 * kEpiSets);  // one arrival per epilogue warp of both CTAs
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  if (warp == 0) {
+    // ================================================================ TMA producer (both CTAs; signals the leader's barriers)
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, qe_phase = 0;
+      int cur_img = -1;
+      for (long long t = t_begin; t < t_end; ++t) {
+        const int img = (int)(t / p.tiles_per_image), tt = (int)(t % p.tiles_per_image);
+        if (img != cur_img) {
+          if (cur_img >= 0) { mbar_wait(bar_qempty, qe_phase); qe_phase ^= 1; }
+          if (leader) mbar_arrive_expect_tx(bar_qfull, 2u * (uint32_t)num_slabs * q_slab_bytes);
+          else mbar_arrive_cluster(bar_qfull, 0);
+          for (int ks = 0; ks < num_slabs; ++ks)
+            tma_load_2d_pair(&tmap_q, bar_qfull, smem_q + ks * q_slab_bytes, ks * kSlabCh,
+                             ((img * p.nblk + b) * 2 + (int)rank) * half);
+          cur_img = img;
+        }
+        for (int ks = 0; ks < num_slabs; ++ks) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          if (leader) mbar_arrive_expect_tx(bar_full + 8 * stage, 2u * kAStageBytes);
+          else mbar_arrive_cluster(bar_full + 8 * stage, 0);
+          tma_load_3d_pair(&tmap_mem, bar_full + 8 * stage, smem_a + stage * kAStageBytes, ks * kSlabCh, img,
+                           tt * 2 * kTokTile + (int)rank * kTokTile);
+          if (++stage == kAStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer (leader CTA only)
+    if (leader && lane == 0) {
+      const uint32_t idesc_base = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(2 * kTokTile >> 4) << 24);
+      const uint32_t idesc_lo = idesc_base | ((uint32_t)(p.n_lo >> 3) << 17);
+      const uint32_t idesc_hi = idesc_base | ((uint32_t)(p.n_hi >> 3) << 17);
+      const uint32_t hi_row_bytes = (uint32_t)(p.n_lo / 2) * 128u;  // rows of the second MMA inside each resident slab
+      uint32_t stage = 0, phase = 0, qf_phase = 0, acc_phase = 0;
+      int cur_img = -1;
+      for (long long t = t_begin; t < t_end; ++t) {
+        const int img = (int)(t / p.tiles_per_image);
+        if (img != cur_img) { mbar_wait(bar_qfull, qf_phase); qf_phase ^= 1; cur_img = img; }
+        mbar_wait(bar_accempty, acc_phase ^ 1);
+        acc_phase ^= 1;
+        tc_fence_after();
+        for (int ks = 0; ks < num_slabs; ++ks) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint64_t da = smem_desc_sw128(smem_a + stage * kAStageBytes);
+          const uint64_t db = smem_desc_sw128(smem_q + ks * q_slab_bytes);
+          const uint64_t dbh = smem_desc_sw128(smem_q + ks * q_slab_bytes + hi_row_bytes);
+#pragma unroll
+          for (int kk = 0; kk < kSlabCh / 8; ++kk) {
+            if (p.debug & 2) continue;
+            umma_tf32_pair(tmem_base, da + 2 * kk, db + 2 * kk, idesc_lo, (ks | kk) ? 1u : 0u);
+            if (p.n_hi) umma_tf32_pair(tmem_base + p.n_lo, da + 2 * kk, dbh + 2 * kk, idesc_hi, (ks | kk) ? 1u : 0u);
+          }
+          umma_commit_pair(bar_empty + 8 * stage);
+          if (++stage == kAStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_pair(bar_accfull);
+        const bool last_of_image = (t + 1 == t_end) || ((int)((t + 1) / p.tiles_per_image) != img);
+        if (last_of_image) umma_commit_pair(bar_qempty);
+      }
+      if (t_end > t_begin) mbar_wait(bar_accempty, acc_phase ^ 1);  // the peer's last remote arrivals have landed
+    }
+    __syncwarp();
+  } else {
+    // ================================================================ epilogue (both CTAs): thread = token
+    const int sub = warp & 3;
+    const int eset = (warp - 2) >> 2;
+    const float scale = p.score_scale;
+    uint32_t acc_phase = 0;
+    for (long long t = t_begin; t < t_end; ++t) {
+      const int img = (int)(t / p.tiles_per_image), tt = (int)(t % p.tiles_per_image);
+      const int K = p.box_start[img + 1] - p.box_start[img];
+      const int kv = (p.debug & 1) ? 0 : max(0, min(p.NB, K - b * p.NB));
+      const float4* __restrict__ cj = reinterpret_cast<const float4*>(p.cpad + ((long long)img * p.nblk + b) * p.NB);
+      mbar_wait(bar_accfull, acc_phase);
+      acc_phase ^= 1;
+      tc_fence_after();
+      float mx = -1e30f, den0 = 0.f, den1 = 0.f, num0 = 0.f, num1 = 0.f;
+      const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16);
+      for (int c0 = 32 * eset; c0 < kv; c0 += 32 * kEpiSets) {  // the warp sets interleave over the 32-column chunks
+        uint32_t v[32];
+        tmem_ld32(taddr + c0, v);
+        tmem_ld_wait();
+        softmax_chunk(v, cj + (c0 >> 2), kv - c0, scale, mx, den0, den1, num0, num1);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(bar_accempty, 0);
+      const int tok = tt * 2 * kTokTile + (int)rank * kTokTile + sub * 32 + lane;
+      if (tok < p.S) {
+        float* o = p.part + (((long long)img * p.nblk + b) * kEpiSets + eset) * 3 * p.S + tok;
+        o[0] = mx;
+        o[p.S] = den0 + den1;
+        o[2 * (long long)p.S] = num0 + num1;
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+  }
+}
+
+// Query rows of every (image, block), zero padded to NB rows: Qpad[N, nblk, NB, C] and cpad[N, nblk, NB] (cpad in
+// accumulator-column order).  Pair mode: the first NB/2 rows of a block are resident in the leader CTA, the rest in its
+// peer, and accumulator column j of the MMA with N = n (n_lo, then n_hi) comes from row j of CTA 0 for j < n/2 and from
+// row j - n/2 of CTA 1 otherwise -- the rows are laid out so that the accumulator columns are the queries in order.
 __global__ void __launch_bounds__(256) qmem_gather_kernel(const float* __restrict__ hs_teacher, const int64_t* __restrict__ keepid,
                                                           const float* __restrict__ scores, const int* __restrict__ box_start,
-                                                          int nblk, int NB, int C, int64_t num_rows, float* __restrict__ qpad,
-                                                          float* __restrict__ cpad) {
-  const int r = blockIdx.x;  // (img * nblk + b) * NB + j
-  const int j = r % NB, ib = r / NB, b = ib % nblk, img = ib / nblk;
-  const int q = b * NB + j, K = box_start[img + 1] - box_start[img];
+                                                          int nblk, int NB, int pair, int n_lo, int n_hi, int C,
+                                                          int64_t num_rows, float* __restrict__ qpad, float* __restrict__ cpad) {
+  const int r = blockIdx.x;  // (img * nblk + b) * NB + rr
+  const int rr = r % NB, ib = r / NB, b = ib % nblk, img = ib / nblk;
+  int col = rr;
+  if (pair) {
+    const int half = NB / 2, cta = rr / half, lr = rr % half, hl = n_lo / 2;
+    col = lr < hl ? cta * hl + lr : n_lo + cta * (n_hi / 2) + (lr - hl);
+  }
+  const int q = b * NB + col, K = box_start[img + 1] - box_start[img];
   const bool valid = q < K;
   int64_t src = 0;
   if (valid) {
@@ -318,7 +543,7 @@ __global__ void __launch_bounds__(256) qmem_gather_kernel(const float* __restric
   const float4* s4 = reinterpret_cast<const float4*>(hs_teacher + src * C);
   float4* d4 = reinterpret_cast<float4*>(qpad + (int64_t)r * C);
   for (int c = threadIdx.x; c < C / 4; c += blockDim.x) d4[c] = valid ? __ldg(s4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-  if (threadIdx.x == 0) cpad[r] = valid ? (scores ? scores[box_start[img] + q] : 1.f) : 0.f;
+  if (threadIdx.x == 0) cpad[(int64_t)ib * NB + col] = valid ? (scores ? scores[box_start[img] + q] : 1.f) : 0.f;
 }
 
 // Merge the per-block (max, den, num) partials and add the null logit once.
@@ -357,17 +582,28 @@ EncodeTiledFn encode_tiled_fn() {
 }
 
 struct QmemPlan {
-  int nblk, NB;
+  bool pair;                 // CTA-pair kernel (cta_group::2): more than kMaxNB queries per image
+  int nblk, NB, n_lo, n_hi;  // query blocks per image, padded queries per block, MMA widths (pair mode)
+  int part_blocks;           // partial (max, den, num) planes per image; 1 = the kernel writes the weights itself
   int64_t qpad, cpad, part, total;
   QmemPlan(int N, int64_t S, int C, int kmax) {
-    nblk = std::max(1, (kmax + kMaxNB - 1) / kMaxNB);
+    const char* mode = getenv("DSKD_QMEM_MODE");  // "1" / "2": force the single-CTA / CTA-pair kernel (tests, tools)
+    // Measured on B200 (tools/qmem_perf.py, profiles/r1/qmem_sweep.txt): the pair kernel is correct but slower than two
+    // single-CTA query blocks sharing the tile through L2 -- with 152 resident rows only 4 ring stages fit, and its
+    // stage hand-off crosses the CTA pair, so it is latency-bound.  It stays opt-in.
+    pair = mode != nullptr && mode[0] == '2';
+    const int cap = pair ? 2 * kMaxNB : kMaxNB;
+    nblk = std::max(1, (kmax + cap - 1) / cap);
     const int per = (std::max(kmax, 1) + nblk - 1) / nblk;
-    NB = (per + 15) / 16 * 16;
+    NB = std::max((per + 15) / 16 * 16, pair ? 32 : 16);
+    n_lo = NB; n_hi = 0;
+    if (pair && NB > 256) { n_lo = kMaxNB; n_hi = NB - kMaxNB; }
+    part_blocks = pair ? nblk * kEpiSets : nblk;
     int64_t off = 0;
     auto up = [](int64_t x) { return (x + 255) / 256 * 256; };
     qpad = off; off += up((int64_t)N * nblk * NB * C * 4);
     cpad = off; off += up((int64_t)N * nblk * NB * 4);
-    part = off; off += (nblk > 1) ? up((int64_t)N * nblk * 3 * S * 4) : 0;
+    part = off; off += (part_blocks > 1) ? up((int64_t)N * part_blocks * 3 * S * 4) : 0;
     total = off;
   }
 };
@@ -403,10 +639,10 @@ extern "C" int dskd_qmem_cell_weights(const DskdQmemArgs* a, void* stream) {
   char* base = static_cast<char*>(a->d_workspace);
   float* qpad = reinterpret_cast<float*>(base + plan.qpad);
   float* cpad = reinterpret_cast<float*>(base + plan.cpad);
-  float* part = plan.nblk > 1 ? reinterpret_cast<float*>(base + plan.part) : nullptr;
+  float* part = plan.part_blocks > 1 ? reinterpret_cast<float*>(base + plan.part) : nullptr;
   const int rows = a->N * plan.nblk * plan.NB;
-  qmem_gather_kernel<<<rows, 64, 0, st>>>(a->d_hs_teacher, a->d_keepid, a->d_scores, a->d_box_start, plan.nblk, plan.NB, a->C,
-                                          a->num_query_rows, qpad, cpad);
+  qmem_gather_kernel<<<rows, 64, 0, st>>>(a->d_hs_teacher, a->d_keepid, a->d_scores, a->d_box_start, plan.nblk, plan.NB, plan.pair ? 1 : 0,
+                                          plan.n_lo, plan.n_hi, a->C, a->num_query_rows, qpad, cpad);
   DSKD_LAUNCH_OK("qmem_gather_kernel");
 
   EncodeTiledFn encode = encode_tiled_fn();
@@ -433,7 +669,7 @@ extern "C" int dskd_qmem_cell_weights(const DskdQmemArgs* a, void* stream) {
     // padded queries [N*nblk*NB, C]: box = 32 channels x NB rows
     const cuuint64_t dims[2] = {(cuuint64_t)a->C, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)a->C * 4};
-    const cuuint32_t box[2] = {kSlabCh, (cuuint32_t)plan.NB};
+    const cuuint32_t box[2] = {kSlabCh, (cuuint32_t)(plan.pair ? plan.NB / 2 : plan.NB)};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = encode(&tmap_q, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, qpad, dims, strides, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -445,22 +681,38 @@ extern "C" int dskd_qmem_cell_weights(const DskdQmemArgs* a, void* stream) {
   }
   QmemParams p;
   p.N = a->N; p.C = a->C; p.S = (int)a->S; p.nblk = plan.nblk; p.NB = plan.NB;
-  p.tiles_per_image = (int)ceil_div(a->S, kTokTile);
+  const int tile_tokens = plan.pair ? 2 * kTokTile : kTokTile;
+  p.tiles_per_image = (int)ceil_div(a->S, tile_tokens);
   p.total_tiles = (long long)p.tiles_per_image * a->N;
   p.score_scale = 1.4426950408889634f / (sqrtf((float)a->C) * a->temperature);
   p.box_start = a->d_box_start;
   p.cpad = cpad;
   p.part = part;
   p.weight = a->d_cell_weight;
+  p.n_lo = plan.n_lo;
+  p.n_hi = plan.n_hi;
   { const char* dbg = getenv("DSKD_QMEM_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
-  const size_t smem = 1024 + (size_t)plan.NB * a->C * 4 + (size_t)kAStages * kAStageBytes + 256;
-  DSKD_CUDA_OK(cudaFuncSetAttribute(qmem_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const long long groups = std::max(1ll, std::min<long long>(kNumSMs / plan.nblk, p.total_tiles));
-  qmem_weight_kernel<<<(unsigned)(groups * plan.nblk), kQmemThreads, smem, st>>>(tmap_mem, tmap_q, p);
-  DSKD_LAUNCH_OK("qmem_weight_kernel");
-  if (plan.nblk > 1) {
+  const int resident_rows = plan.pair ? plan.NB / 2 : plan.NB;
+  const size_t kSmemMax = 227 * 1024, fixed = 1024 + (size_t)resident_rows * a->C * 4 + 512;
+  int stages = (int)std::min<size_t>(kMaxAStages, (kSmemMax - fixed) / kAStageBytes);
+  { const char* e = getenv("DSKD_QMEM_STAGES"); if (e && atoi(e) > 0) stages = std::min(stages, atoi(e)); }
+  DSKD_REQUIRE(stages >= 2, "dskd_qmem_cell_weights: not enough shared memory for the memory-tile ring");
+  p.stages = stages;
+  const size_t smem = fixed + (size_t)stages * kAStageBytes;
+  const int units = plan.pair ? kNumSMs / 2 : kNumSMs;  // CTAs or CTA pairs that fit the chip, one per SM
+  const long long groups = std::max(1ll, std::min<long long>(units / plan.nblk, p.total_tiles));
+  if (plan.pair) {
+    DSKD_CUDA_OK(cudaFuncSetAttribute(qmem_weight_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    qmem_weight_pair_kernel<<<(unsigned)(2 * groups * plan.nblk), kQmemThreads, smem, st>>>(tmap_mem, tmap_q, p);
+    DSKD_LAUNCH_OK("qmem_weight_pair_kernel");
+  } else {
+    DSKD_CUDA_OK(cudaFuncSetAttribute(qmem_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    qmem_weight_kernel<<<(unsigned)(groups * plan.nblk), kQmemThreads, smem, st>>>(tmap_mem, tmap_q, p);
+    DSKD_LAUNCH_OK("qmem_weight_kernel");
+  }
+  if (plan.part_blocks > 1) {
     const int64_t total = (int64_t)a->N * a->S;
-    qmem_combine_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(part, a->N, plan.nblk, (int)a->S, a->d_cell_weight);
+    qmem_combine_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(part, a->N, plan.part_blocks, (int)a->S, a->d_cell_weight);
     DSKD_LAUNCH_OK("qmem_combine_kernel");
   }
   return DSKD_OK;

@@ -35,15 +35,29 @@ def kernel_weights(cpu, counts, sc, start, temp=0.5):
                                   None if sc is None else sc.to(DEV), start.to(DEV), max(counts) if counts else 0, temp).cpu()
 
 
+@pytest.fixture
+def qmem_mode(monkeypatch):
+    def set_mode(mode):
+        if mode is None:
+            monkeypatch.delenv('DSKD_QMEM_MODE', raising=False)
+        else:
+            monkeypatch.setenv('DSKD_QMEM_MODE', mode)      # '1': single-CTA kernel, '2': CTA-pair (cta_group::2) kernel
+    return set_mode
+
+
+@pytest.mark.parametrize('mode', [None, '1', '2'], ids=['auto', 'cta1', 'cta2'])
 @pytest.mark.parametrize('n,levels,q,c,kpi,scores', [
     (2, SMALL, 100, 256, 20, True),            # one query block
     (2, SMALL, 100, 64, 7, True),              # 2 channel slabs
     (3, SMALL, 100, 256, None, True),          # ragged K_i
-    (2, SMALL, 320, 256, 300, False),          # two query blocks of 160 resident rows, unit confidences
-    (1, SMALL, 700, 256, 600, True),           # four query blocks
+    (2, SMALL, 320, 256, 300, False),          # 300 queries: 2 blocks of 160 (single CTA) / one 304-wide pair block
+    (2, SMALL, 320, 256, 250, True),           # pair mode: one MMA of N = 256 per k-step
+    (1, SMALL, 700, 256, 600, True),           # four single blocks / two pair blocks
     (2, ((13, 21), (7, 11)), 60, 128, 5, True),  # S = 350: partial last token tile
-], ids=['1blk', 'c64', 'ragged', '2blk', '4blk', 'tail'])
-def test_cell_weights_vs_oracle(n, levels, q, c, kpi, scores):
+    (3, ((9, 15),), 60, 64, 9, True),          # S = 135: one token tile in pair mode, the peer CTA half empty
+], ids=['1blk', 'c64', 'ragged', 'k300', 'k250', 'k600', 'tail', 'tiny'])
+def test_cell_weights_vs_oracle(n, levels, q, c, kpi, scores, mode, qmem_mode):
+    qmem_mode(mode)
     cpu, counts, sc, start = make(n, levels, q, c, kpi, scores=scores)
     w = kernel_weights(cpu, counts, sc, start)
     _, t_mem = cpu.memory()

@@ -46,16 +46,83 @@ def parse_args():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='time eager launches only')
     ap.add_argument('--cpu-sample-images', type=int, default=2)
+    ap.add_argument('--no-contraction', action='store_true', help='skip the tcgen05 query x memory kernel line')
+    ap.add_argument('--contraction-queries', type=int, default=300,
+                    help="queries contracted against every memory token (north_star: ~300 x 256 against ~20k x 256)")
     return ap.parse_args()
 
 
 def peaks():
+    """(HBM GB/s, bf16 TFLOP/s burst, source) -- measured by the driver, else the profiling guide's fallback."""
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
         with open(path) as f:
             p = json.load(f)
-        return float(p['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
-    return 6650.0, 'fallback (B200_PROFILING.md)'
+        return float(p['hbm_gbs']), float(p['bf16_tflops']), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 1590.0, 'fallback (B200_PROFILING.md)'
+
+
+def recorded_traffic(kernel, images_per_gpu):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this
+    very command (profiles/traffic.json); None when no capture matches the configuration."""
+    path = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        table = json.load(f)
+    rec = table.get(kernel)
+    if rec and int(rec.get('images_per_gpu', -1)) == int(images_per_gpu):
+        return rec
+    return None
+
+
+def time_contraction(args, dev, N, world, dist):
+    """The tcgen05 query x memory contraction at the north_star shape: K queries x 256 channels
+    against the 22 223 x 256 memory tokens of each of this rank's N images; CUDA-graph replay, L2 flushed between
+    replays, CUDA events; FLOPs = 2*K*C*S per image."""
+    from dskd_b200 import qmem
+    K, S, C, Q = args.contraction_queries, 22223, 256, max(300, args.contraction_queries)
+    g = torch.Generator(device=dev).manual_seed(4321)
+    mem = torch.randn(S, N, C, device=dev, generator=g)
+    hs = torch.randn(N, Q, C, device=dev, generator=g)
+    keep = torch.cat([torch.randperm(Q, device=dev, generator=g)[:K] + i * Q for i in range(N)])
+    sc = torch.rand(N * K, device=dev, generator=g)
+    start = torch.arange(N + 1, device=dev, dtype=torch.int32) * K
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            qmem.qmem_cell_weights(mem, hs, keep, sc, start, K, 0.5)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        qmem.qmem_cell_weights(mem, hs, keep, sc, start, K, 0.5)
+    times = []
+    for _ in range(max(args.steps, 5)):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        graph.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    ms = statistics.median(times)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    flop = 2.0 * K * C * S * N
+    _, bf16_peak, src = peaks()
+    achieved = flop / (ms * 1e-3) / 1e12
+    return {'bound': 'tensor', 'kernel': 'qmem_weight_kernel (tcgen05.mma kind::tf32, TMA-fed, TMEM accumulators)',
+            'achieved': achieved, 'peak': bf16_peak, 'unit': 'TFLOP/s', 'frac': achieved / bf16_peak,
+            'frac_of_tf32_rate': achieved / (bf16_peak / 2),
+            'peak_source': f'{src}: cuBLAS bf16 dense; kind::tf32 issues at half that rate',
+            'flop_per_launch': flop, 'call_ms': ms, 'queries': K, 'tokens': S, 'channels': C, 'images': N,
+            'images_per_s': world * N / (ms * 1e-3), 'traffic': None,
+            'timing': 'gather + contraction + combine, CUDA-graph replay, L2 flushed between replays, median'}
 
 
 class ClockSampler:
@@ -325,17 +392,23 @@ def main():
         e2e = {'value': world * N * e2e_steps / float(tt.item()), 'unit': UNIT, 'h2d_bytes_per_step': h2d,
                'd2h_bytes_per_step': 4, 'steps': e2e_steps, 'ms_per_step': float(tt.item()) / e2e_steps * 1e3}
 
+    contraction = None
+    if not args.no_contraction:
+        contraction = time_contraction(args, dev, N, world, dist)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    peak, peak_src = peaks()
+    peak, _, peak_src = peaks()
     if args.criterion == 'mse':
         alg_bytes = BYTES_PER_IMAGE_MSE * N
     else:
         alg_bytes = 2 * 22223 * 256 * 4 * N
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    kernel_name = 'dsgfd_mse_nchw_kernel' if args.criterion == 'mse' else 'dsgfd_kl_kernel'
+    traffic_rec = recorded_traffic(kernel_name, N)
     ms_per_step = elapsed_ms / args.steps
     line = {
         'metric': METRIC, 'value': world * N * args.steps / (elapsed_ms * 1e-3), 'unit': UNIT, 'n_gpus': world,
@@ -350,7 +423,10 @@ def main():
                      'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                      'frac_of_nominal_8000': achieved / 8000.0, 'peak_source': peak_src,
                      'algorithmic_bytes_per_launch': alg_bytes, 'kernel_ms': kernel_ms,
-                     'kernel_share_of_step': kernel_ms / ms_per_step, 'traffic': None},
+                     'kernel_share_of_step': kernel_ms / ms_per_step,
+                     'traffic': (traffic_rec or {}).get('dram_bytes_per_launch'),
+                     'traffic_source': (traffic_rec or {}).get('source')},
+        'contraction': contraction,
         'e2e': e2e,
         'gpu_launches': int(launches),
         'eager': {'value': world * N * args.steps / (eager_ms * 1e-3), 'unit': UNIT, 'ms_per_step': eager_ms / args.steps,

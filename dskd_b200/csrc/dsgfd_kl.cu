@@ -2,16 +2,34 @@
 // [C,H,W] maps, i.e. softmax over H (kd_loss.py:28-34 with dim=1 == H), target = student*mask
 // (detached), pred = teacher*mask.  Reference: gfl_deformable_detr_head_il.py:707-718 + kd_loss.py:12-43.
 //
-// Column kernel: lane = one (channel, w) column, walked over H twice (online softmax statistics,
-// then the KL terms and d loss / d mask).  Cells outside every box have logit 0 for both softmaxes
-// and need no feature bytes; columns without any owned cell contribute exactly 0 and are skipped.
-// No gradient reaches the student features (target is detached): the only gradient is d loss / d rows.
+// Cells outside every box have logit 0 for both softmaxes and need no feature bytes; strips without any owned cell
+// contribute exactly 0 and are skipped.  No gradient reaches the student features (target is detached): the only
+// gradient is d loss / d rows.  Algorithmic bytes: read S + read T = 8 B per element (45.51 MB per 800x1333 image).
 #include "common.cuh"
 
 namespace dskd {
 
-constexpr int kKlChan = 4;          // channels walked together by one warp (8 independent loads per row)
-constexpr int kKlWarps = 4;         // warps per CTA -> 16 channels per CTA
+// Strip kernel.  A CTA owns one strip = (level, image, kKlCols consecutive w) x all H rows and a chunk of channels; each
+// of its warps walks kKlChan channels one after the other; the 32 lanes are kKlCols columns x kKlPhases row phases (a
+// lane takes every kKlPhases-th row of its column; narrow strips keep the shared-memory footprint per warp small enough
+// for 16 resident warps per SM).  Per channel the warp
+//   0. cp.async's the owned cells of the student / teacher strip [H][32] into ITS shared-memory buffers (every
+//      feature byte is read from HBM exactly once; ~200 independent 128-byte copies in flight per warp),
+//   A. turns them in place into the logits x = feature * mask / T (0 outside boxes) and takes the column maxima,
+//   B. sums e^(x - max) for both softmaxes and sum e^(xs - max) (xs - xt) -- the KL of a column needs nothing else:
+//        KL = sum_h t_h (xs_h - xt_h) - (lse_s - lse_t),
+//   C. (only when the mask rows need a gradient) accumulates T_h * (p_h - t_h) per owning box over each run of rows
+//      (warp-cooperative sum, one red.global per box, run and channel).
+// The owner strip and the runs -- maximal row ranges in which no column changes owner -- are computed once per CTA and
+// shared by all its channels, so the per-channel sweeps carry no per-row ownership tests.
+constexpr int kKlChan = 4;        // channels per warp (sequential)
+constexpr int kKlCols = 8;        // columns (w) per strip: a warp covers kKlCols columns x kKlPhases interleaved row phases
+constexpr int kKlPhases = 32 / kKlCols;
+constexpr int kKlMaxWarps = 32;   // warps per CTA
+constexpr int kKlMaxH = 800;      // rows per level the shared-memory strips can hold (one warp per CTA at the limit)
+constexpr size_t kKlSmemBudget = 220 * 1024;
+// owner strip (kKlCols ints per row) + run table, rounded to 128 B
+__host__ __device__ inline size_t kl_header_bytes(int max_h) { return ((size_t)max_h * kKlCols * 4 + (size_t)(max_h + 2) * 4 + 127) / 128 * 128; }
 
 struct KlParams {
   DskdLevel levels[DSKD_MAX_LEVELS];
@@ -21,7 +39,8 @@ struct KlParams {
   int block_start[DSKD_MAX_LEVELS + 1];
   int wtiles[DSKD_MAX_LEVELS];
   int num_levels, N, C;
-  float temperature;
+  int warps, max_h;               // warps per CTA, max H over the levels (sizes the shared-memory strips)
+  float temperature, inv_temperature;
   int64_t cells_per_image;
   const int* owner;
   const float* rows;
@@ -30,149 +49,246 @@ struct KlParams {
   double* loss;
 };
 
-struct OnlineLse {  // running max / sum of exp for a softmax over H
-  float mx, sum;
-  __device__ __forceinline__ void init() { mx = -INFINITY; sum = 0.f; }
-  __device__ __forceinline__ void push(float x) {
-    if (x > mx) {
-      sum = sum * expf(mx - x) + 1.f;
-      mx = x;
-    } else {
-      sum += expf(x - mx);
-    }
-  }
-  // log-sum-exp in double: the KL below is a second-order quantity (sum_h t_h (log t_h - log p_h) with both
-  // log-softmaxes ~ -log H), so an fp32 logf here (abs. error ~3e-7) would be ~1 % of a column's KL.
-  __device__ __forceinline__ double lse() const { return (double)mx + log((double)sum); }
-};
+__device__ __forceinline__ void cp_async_f32(uint32_t dst, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
-template <bool CELL>
-__global__ void __launch_bounds__(32 * kKlWarps) dsgfd_kl_kernel(const __grid_constant__ KlParams prm) {
+// POW2: T is a power of two, so (feature * mask) / T == feature * (mask / T) bit for bit and the division is hoisted.
+template <bool CELL, bool POW2>
+__global__ void __launch_bounds__(32 * kKlMaxWarps) dsgfd_kl_kernel(const __grid_constant__ KlParams prm) {
+  extern __shared__ __align__(16) unsigned char kl_smem[];
   __shared__ double red[32];
+  __shared__ int strip_any, num_runs;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wl = lane % kKlCols, ph = lane / kKlCols;  // column inside the strip, row phase (rows ph, ph + kKlPhases, ...)
   int lvl = 0;
 #pragma unroll
   for (int k = 1; k < DSKD_MAX_LEVELS; ++k)
     if (k < prm.num_levels && (int)blockIdx.x >= prm.block_start[k]) lvl = k;
   const int H = prm.levels[lvl].H, W = prm.levels[lvl].W, C = prm.C;
   const int HW = H * W;
-  const int nchunks = C / (kKlChan * kKlWarps);
+  const int ch_per_cta = prm.warps * kKlChan;
+  const int nchunks = (C + ch_per_cta - 1) / ch_per_cta;
   int idx = blockIdx.x - prm.block_start[lvl];
+  const int chunk = idx % nchunks;     // channel chunks of one strip are neighbours: the owner strip stays in L2 / L1
+  idx /= nchunks;
   const int wt = idx % prm.wtiles[lvl];
-  idx /= prm.wtiles[lvl];
-  const int chunk = idx % nchunks;
-  const int img = idx / nchunks;
-  const int w = wt * 32 + lane;
+  const int img = idx / prm.wtiles[lvl];
+  const int w = wt * kKlCols + wl;
   const bool col_ok = w < W;
-  const int c0 = (chunk * kKlWarps + warp) * kKlChan;
   const float Temp = prm.temperature;
   const float scale = prm.scale[lvl];
-  const float* __restrict__ S = prm.student[lvl] + ((int64_t)img * C + c0) * HW + w;
-  const float* __restrict__ T = prm.teacher[lvl] + ((int64_t)img * C + c0) * HW + w;
-  const int64_t cell_base = (int64_t)img * prm.cells_per_image + prm.levels[lvl].cell_offset + w;
+  const int64_t strip_base = (int64_t)img * prm.cells_per_image + prm.levels[lvl].cell_offset + wt * kKlCols;
+  const int64_t cell_base = strip_base + wl;
 
-  auto cell_owner = [&](int h) -> int {
-    if (!col_ok) return -1;
-    if (CELL) return (__ldg(prm.cell_weight + cell_base + (int64_t)h * W) != 0.f) ? 0 : -1;
-    return __ldg(prm.owner + cell_base + (int64_t)h * W);
-  };
-  auto mask_value = [&](int owner, int h, int k) -> float {
-    if (CELL) return __ldg(prm.cell_weight + cell_base + (int64_t)h * W);
-    return __ldg(prm.rows + (int64_t)owner * C + c0 + k);
-  };
+  // shared memory: owner strip int32 [max_h][kKlCols] | run starts int32 [max_h + 2] | per warp: xs, xt [max_h][kKlCols]
+  int* own_s = reinterpret_cast<int*>(kl_smem);
+  int* run_s = own_s + (size_t)prm.max_h * kKlCols;
+  float* xs_s = reinterpret_cast<float*>(kl_smem + kl_header_bytes(prm.max_h)) + (size_t)warp * 2 * prm.max_h * kKlCols;
+  float* xt_s = xs_s + (size_t)prm.max_h * kKlCols;
 
-  // pass 0: does this column meet any box?  (owners are shared by every channel)
-  bool any = false;
-  for (int h = 0; h < H; ++h) any |= cell_owner(h) >= 0;
+  // ---- once per CTA: owner strip; rows at which the owner of any column changes ("runs" of rows between them have
+  // one owner per column, so the per-channel sweeps need no per-row checks); any owned cell at all?
+  if (threadIdx.x == 0) strip_any = 0;
+  for (int h = threadIdx.x; h <= H; h += blockDim.x) run_s[h] = 0;
+  __syncthreads();
+  {
+    bool any = false;
+    for (int i = threadIdx.x; i < H * kKlCols; i += blockDim.x) {
+      const int h = i / kKlCols, c = i % kKlCols;
+      int o = -1;
+      if (wt * kKlCols + c < W) {
+        if (CELL) o = (__ldg(prm.cell_weight + strip_base + c + (int64_t)h * W) != 0.f) ? 0 : -1;
+        else o = __ldg(prm.owner + strip_base + c + (int64_t)h * W);
+      }
+      own_s[i] = o;
+      any |= o >= 0;
+    }
+    if (__any_sync(0xffffffffu, any) && lane == 0) strip_any = 1;
+  }
+  __syncthreads();
+  if (!strip_any) return;  // no box touches this strip: every column's KL is exactly 0
+  const bool want_grad = !CELL && prm.grad_rows != nullptr;
+  if (want_grad) {
+    for (int i = kKlCols + threadIdx.x; i < H * kKlCols; i += blockDim.x)
+      if (own_s[i] != own_s[i - kKlCols]) run_s[i / kKlCols] = 1;  // flag (same value from every writer); compacted below
+    __syncthreads();
+    if (threadIdx.x == 0) {  // run_s[0..n) = first rows of the runs, run_s[n] = H
+      int n = 0;
+      for (int h = 0; h < H; ++h)
+        if (h == 0 || run_s[h]) run_s[n++] = h;
+      run_s[n] = H;
+      num_runs = n;
+    }
+    __syncthreads();
+  }
+
+  const float kLog2e = 1.4426950408889634f;
+  const float gcoef = scale * Temp / (float)H;  // d loss / d pred = scale * (T/H) * (p - t)
   double kl_total = 0.0;
-  if (__any_sync(0xffffffffu, any)) {
-    // pass 1: softmax statistics over H for target (student*mask/T) and pred (teacher*mask/T)
-    OnlineLse ls[kKlChan], lt[kKlChan];
+  constexpr int kRow = kKlCols;                  // floats per strip row
+  constexpr int kStep = kKlPhases * kKlCols;     // floats between two rows of the same lane
+  const uint32_t xs_addr = (uint32_t)__cvta_generic_to_shared(xs_s) + (uint32_t)(ph * kRow + wl) * 4u;
+  const uint32_t xt_addr = (uint32_t)__cvta_generic_to_shared(xt_s) + (uint32_t)(ph * kRow + wl) * 4u;
+  const int* own_l = own_s + wl;                 // own_l[h * kRow]
+  float* xs_l = xs_s + wl;
+  float* xt_l = xt_s + wl;
+  auto phase_max = [](float v) {
 #pragma unroll
-    for (int k = 0; k < kKlChan; ++k) { ls[k].init(); lt[k].init(); }
-    if (any) {
-      for (int h = 0; h < H; ++h) {
-        const int o = cell_owner(h);
-        float xs[kKlChan], xt[kKlChan];
+    for (int o = kKlCols; o < 32; o <<= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+  };
+  auto phase_sum = [](float v) {
 #pragma unroll
-        for (int k = 0; k < kKlChan; ++k) xs[k] = xt[k] = 0.f;
-        if (o >= 0) {
-#pragma unroll
-          for (int k = 0; k < kKlChan; ++k) {
-            const float m = mask_value(o, h, k);
-            xs[k] = __fdiv_rn(ld_stream_f1(S + (int64_t)k * HW + (int64_t)h * W) * m, Temp);
-            xt[k] = __fdiv_rn(ld_stream_f1(T + (int64_t)k * HW + (int64_t)h * W) * m, Temp);
-          }
+    for (int o = kKlCols; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  };
+
+  for (int k = 0; k < kKlChan; ++k) {
+    const int c = (chunk * prm.warps + warp) * kKlChan + k;
+    if (c >= C) break;
+    const float* __restrict__ S = prm.student[lvl] + ((int64_t)img * C + c) * HW + w;
+    const float* __restrict__ T = prm.teacher[lvl] + ((int64_t)img * C + c) * HW + w;
+    auto mask_of = [&](int o, int h) -> float {  // mask value of the cell (divided by T when that is exact)
+      if (o < 0) return 0.f;
+      const float m = CELL ? __ldg(prm.cell_weight + cell_base + (int64_t)h * W) : __ldg(prm.rows + (int64_t)o * C + c);
+      return POW2 ? m * prm.inv_temperature : m;
+    };
+    // ---- 0: owned cells -> shared memory asynchronously (every feature byte leaves HBM once), zeros elsewhere
+    {
+      const float* sp = S + (int64_t)ph * W;
+      const float* tp = T + (int64_t)ph * W;
+      uint32_t xa = xs_addr, ta = xt_addr;
+      for (int h = ph; h < H; h += kKlPhases, sp += kKlPhases * W, tp += kKlPhases * W, xa += kStep * 4u, ta += kStep * 4u) {
+        if (own_l[h * kRow] >= 0) {
+          cp_async_f32(xa, sp);
+          cp_async_f32(ta, tp);
+        } else {
+          xs_l[h * kRow] = 0.f;
+          xt_l[h * kRow] = 0.f;
         }
-#pragma unroll
-        for (int k = 0; k < kKlChan; ++k) { ls[k].push(xs[k]); lt[k].push(xt[k]); }
       }
     }
-    // pass 2: KL terms and d loss / d mask, accumulated per owning box along the column
-    float lse_s[kKlChan], lse_t[kKlChan], acc[kKlChan];
-    double dl[kKlChan], kl[kKlChan];  // dl = lse_s - lse_t
-#pragma unroll
-    for (int k = 0; k < kKlChan; ++k) {
-      const double a = any ? ls[k].lse() : 0.0, b = any ? lt[k].lse() : 0.0;
-      lse_s[k] = (float)a;
-      lse_t[k] = (float)b;
-      dl[k] = a - b;
-      kl[k] = 0.0;
-      acc[k] = 0.f;
+    cp_async_wait_all();
+    __syncwarp();
+    // ---- A: logits in place (0 outside boxes: a zero feature times a zero mask), column maxima
+    float ms = -INFINITY, mt = -INFINITY;
+    {
+      int prev = -2;
+      float m = 0.f;
+      auto row = [&](int h) {
+        const int o = own_l[h * kRow];
+        if (CELL ? (o >= 0) : (o != prev)) { m = mask_of(o, h); prev = o; }  // the mask is constant along a run of rows
+        float x = xs_l[h * kRow] * m, y = xt_l[h * kRow] * m;
+        if (!POW2) { x = __fdiv_rn(x, Temp); y = __fdiv_rn(y, Temp); }
+        xs_l[h * kRow] = x;
+        xt_l[h * kRow] = y;
+        ms = fmaxf(ms, x);
+        mt = fmaxf(mt, y);
+      };
+      int h = ph;
+      for (; h + 3 * kKlPhases < H; h += 4 * kKlPhases) { row(h); row(h + kKlPhases); row(h + 2 * kKlPhases); row(h + 3 * kKlPhases); }
+      for (; h < H; h += kKlPhases) row(h);
+      ms = phase_max(ms);
+      mt = phase_max(mt);
     }
-    const float gcoef = scale * Temp / (float)H;  // d loss / d pred = scale * (T/H) * (p - t)
-    int cur = -1;
-    for (int h = 0; h <= H; ++h) {
-      const int o = (any && h < H) ? cell_owner(h) : -1;
-      // flush the per-lane accumulators of the box that just ended (warp-cooperative reduction)
-      const bool need = (o != cur) && (cur >= 0);
-      unsigned pending = __ballot_sync(0xffffffffu, need);
-      if (!CELL && prm.grad_rows != nullptr) {
+    // ---- B: softmax sums and the t-weighted logit difference (four interleaved accumulator sets)
+    const float nms = -ms * kLog2e, nmt = -mt * kLog2e;
+    float ss[4] = {0.f, 0.f, 0.f, 0.f}, st4[4] = {0.f, 0.f, 0.f, 0.f}, ws[4] = {0.f, 0.f, 0.f, 0.f};
+    {
+      int h = ph;
+      for (; h + 3 * kKlPhases < H; h += 4 * kKlPhases) {
+        float a[4], b[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) { a[r] = xs_l[(h + r * kKlPhases) * kRow]; b[r] = xt_l[(h + r * kKlPhases) * kRow]; }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const float ea = fast_ex2(fmaf(a[r], kLog2e, nms));
+          ss[r] += ea;
+          st4[r] += fast_ex2(fmaf(b[r], kLog2e, nmt));
+          ws[r] = fmaf(ea, a[r] - b[r], ws[r]);
+        }
+      }
+      for (; h < H; h += kKlPhases) {
+        const float a = xs_l[h * kRow], b = xt_l[h * kRow];
+        const float ea = fast_ex2(fmaf(a, kLog2e, nms));
+        ss[0] += ea;
+        st4[0] += fast_ex2(fmaf(b, kLog2e, nmt));
+        ws[0] = fmaf(ea, a - b, ws[0]);
+      }
+    }
+    const float sum_s = phase_sum((ss[0] + ss[2]) + (ss[1] + ss[3])), sum_t = phase_sum((st4[0] + st4[2]) + (st4[1] + st4[3]));
+    const float wsum = phase_sum((ws[0] + ws[2]) + (ws[1] + ws[3]));
+    // KL of the column = sum_h t_h (xs - xt) - (lse_s - lse_t): a second-order quantity (both log-softmaxes sit near
+    // -log H), so the log-sum-exp difference is taken in double.  One lane per column keeps it.
+    if (ph == 0) {
+      const double dl = ((double)ms - (double)mt) + log((double)sum_s / (double)sum_t);
+      kl_total += (double)wsum / (double)sum_s - dl;
+    }
+
+    // ---- C: d loss / d mask rows, one run of rows at a time; inside a run every column has a single owner, and
+    // columns without one hold zero logits, so their terms vanish without a test
+    if (want_grad) {
+      const float rs = __fdividef(1.f, sum_s), rt = __fdividef(1.f, sum_t);
+      const int nr = num_runs;
+      int cur = own_l[0], seg_h0 = 0;  // owner of this column in the current run, first row of its current box segment
+      float acc = 0.f;                 // sum over the segment so far of xt_h (p_h - t_h) = (mask/T) sum T_h (p_h - t_h)
+      for (int i = 0; i < nr; ++i) {
+        const int h0 = run_s[i], h1 = run_s[i + 1];
+        const int hb = h0 + ((ph - h0) & (kKlPhases - 1));  // first row of this lane's phase inside the run
+        float acc0 = 0.f, acc1 = 0.f;
+        int h = hb;
+        for (; h + kKlPhases < h1; h += 2 * kKlPhases) {
+          const float b0 = xt_l[h * kRow], a0 = xs_l[h * kRow], b1 = xt_l[(h + kKlPhases) * kRow], a1 = xs_l[(h + kKlPhases) * kRow];
+          const float p0 = fast_ex2(fmaf(b0, kLog2e, nmt)) * rt, t0 = fast_ex2(fmaf(a0, kLog2e, nms)) * rs;
+          const float p1 = fast_ex2(fmaf(b1, kLog2e, nmt)) * rt, t1 = fast_ex2(fmaf(a1, kLog2e, nms)) * rs;
+          acc0 = fmaf(b0, p0 - t0, acc0);
+          acc1 = fmaf(b1, p1 - t1, acc1);
+        }
+        if (h < h1) {
+          const float b0 = xt_l[h * kRow], a0 = xs_l[h * kRow];
+          acc0 = fmaf(b0, fast_ex2(fmaf(b0, kLog2e, nmt)) * rt - fast_ex2(fmaf(a0, kLog2e, nms)) * rs, acc0);
+        }
+        acc += acc0 + acc1;
+        // a column flushes its sum when its box ends (its owner differs in the next run); the lanes of one box flush together
+        const int nxt = (i + 1 < nr) ? own_l[h1 * kRow] : -1;
+        const bool need = (nxt != cur) && (cur >= 0);
+        unsigned pending = __ballot_sync(0xffffffffu, need);
         while (pending) {
           const int leader = __ffs(pending) - 1;
           const int who = __shfl_sync(0xffffffffu, cur, leader);
-          const unsigned same = __ballot_sync(0xffffffffu, need && cur == who);
-#pragma unroll
-          for (int k = 0; k < kKlChan; ++k) {
-            float v = (need && cur == who) ? acc[k] : 0.f;
-            v = warp_sum(v);
-            if (lane == leader) atomicAdd(prm.grad_rows + (int64_t)who * C + c0 + k, v);
+          const bool mine = need && cur == who;
+          const unsigned same = __ballot_sync(0xffffffffu, mine);
+          const float m = mask_of(who, 0);  // warp-uniform
+          float v = mine ? acc : 0.f;
+          if (m == 0.f) {
+            // the mask value underflowed to 0: the logits carry no trace of the teacher feature, re-read it
+            v = 0.f;
+            if (mine)
+              for (int r = seg_h0 + ((ph - seg_h0) & (kKlPhases - 1)); r < h1; r += kKlPhases) {
+                const float pp = fast_ex2(fmaf(xt_l[r * kRow], kLog2e, nmt)) * rt;
+                const float tt = fast_ex2(fmaf(xs_l[r * kRow], kLog2e, nms)) * rs;
+                v = fmaf(ld_stream_f1(T + (int64_t)r * W), pp - tt, v);
+              }
+          }
+          v = warp_sum(v);
+          if (lane == leader) {
+            const float div = (m == 0.f) ? 1.f : (POW2 ? m : m / Temp);
+            atomicAdd(prm.grad_rows + (int64_t)who * C + c, __fdividef(gcoef * v, div));
           }
           pending &= ~same;
         }
-      }
-      if (need) {
-#pragma unroll
-        for (int k = 0; k < kKlChan; ++k) acc[k] = 0.f;
-      }
-      cur = o;
-      if (h == H || !any) continue;
-      float xs[kKlChan], xt[kKlChan], tf[kKlChan];
-#pragma unroll
-      for (int k = 0; k < kKlChan; ++k) xs[k] = xt[k] = tf[k] = 0.f;
-      if (o >= 0) {
-#pragma unroll
-        for (int k = 0; k < kKlChan; ++k) {
-          const float m = mask_value(o, h, k);
-          tf[k] = ld_stream_f1(T + (int64_t)k * HW + (int64_t)h * W);
-          xs[k] = __fdiv_rn(ld_stream_f1(S + (int64_t)k * HW + (int64_t)h * W) * m, Temp);
-          xt[k] = __fdiv_rn(tf[k] * m, Temp);
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < kKlChan; ++k) {
-        const float log_t = xs[k] - lse_s[k];
-        const float log_p = xt[k] - lse_t[k];
-        const float t = expf(log_t);
-        // log t - log p = (xs - xt) - (lse_s - lse_t), the difference of the small parts taken first
-        kl[k] += (double)t * ((double)(xs[k] - xt[k]) - dl[k]);
-        if (o >= 0) acc[k] = fmaf(tf[k], gcoef * (expf(log_p) - t), acc[k]);
+        if (nxt != cur) { acc = 0.f; seg_h0 = h1; }
+        cur = nxt;
       }
     }
-    if (any) {
-#pragma unroll
-      for (int k = 0; k < kKlChan; ++k) kl_total += kl[k];
-    }
+    __syncwarp();
   }
   // loss = scale * T^2 / H * sum over columns of sum_h t (log t - log p)
   double tot = block_sum(kl_total, red);
@@ -187,7 +303,6 @@ using namespace dskd;
 extern "C" int dskd_dsgfd_kl_fwd_bwd(const DskdDsgfdKlArgs* a, void* stream) {
   DSKD_REQUIRE(a != nullptr, "dskd_dsgfd_kl_fwd_bwd: null args");
   DSKD_REQUIRE(a->num_levels > 0 && a->num_levels <= DSKD_MAX_LEVELS && a->N >= 0 && a->C > 0, "dsgfd_kl: bad sizes");
-  DSKD_REQUIRE(a->C % (kKlChan * kKlWarps) == 0, "dsgfd_kl: C (%d) must be a multiple of %d", a->C, kKlChan * kKlWarps);
   DSKD_REQUIRE(a->temperature >= 1.f, "dsgfd_kl: T must be >= 1 (kd_loss.py:58)");
   const bool cell = a->d_cell_weight != nullptr;
   DSKD_REQUIRE(cell != (a->d_owner != nullptr), "dsgfd_kl: exactly one of d_owner / d_cell_weight must be set");
@@ -199,6 +314,7 @@ extern "C" int dskd_dsgfd_kl_fwd_bwd(const DskdDsgfdKlArgs* a, void* stream) {
   prm.N = a->N;
   prm.C = a->C;
   prm.temperature = a->temperature;
+  prm.inv_temperature = 1.f / a->temperature;
   prm.cells_per_image = a->cells_per_image;
   prm.owner = a->d_owner;
   prm.rows = a->d_rows;
@@ -206,24 +322,47 @@ extern "C" int dskd_dsgfd_kl_fwd_bwd(const DskdDsgfdKlArgs* a, void* stream) {
   prm.cell_weight = a->d_cell_weight;
   prm.loss = a->d_loss;
   int64_t cells = 0;
-  int blocks = 0;
+  int max_h = 0;
   for (int l = 0; l < a->num_levels; ++l) {
     DSKD_REQUIRE(a->levels[l].H > 0 && a->levels[l].W > 0 && a->levels[l].cell_offset == cells,
                  "dsgfd_kl: level %d is not densely packed", l);
     DSKD_REQUIRE(a->d_student[l] && a->d_teacher[l], "dsgfd_kl: null feature pointer at level %d", l);
     cells += (int64_t)a->levels[l].H * a->levels[l].W;
+    max_h = std::max(max_h, a->levels[l].H);
+  }
+  DSKD_REQUIRE(cells == a->cells_per_image, "dsgfd_kl: cells_per_image mismatch");
+  DSKD_REQUIRE(max_h <= kKlMaxH, "dsgfd_kl: H (%d) above the supported %d", max_h, kKlMaxH);
+  // shared memory: owner strip (128 B per row) + two logit strips (256 B per row) per warp
+  int warps = (int)std::min<int64_t>(kKlMaxWarps, ((int64_t)kKlSmemBudget - (int64_t)kl_header_bytes(max_h)) / (8ll * kKlCols * max_h));
+  DSKD_REQUIRE(warps >= 1, "dsgfd_kl: H (%d) does not fit the shared-memory strips", max_h);
+  warps = std::min(warps, std::max(1, a->C / kKlChan));
+  prm.warps = warps;
+  prm.max_h = max_h;
+  const int ch_per_cta = warps * kKlChan;
+  const int nchunks = (a->C + ch_per_cta - 1) / ch_per_cta;
+  int blocks = 0;
+  for (int l = 0; l < a->num_levels; ++l) {
     prm.levels[l] = a->levels[l];
     prm.student[l] = a->d_student[l];
     prm.teacher[l] = a->d_teacher[l];
     prm.scale[l] = a->scale[l];
-    prm.wtiles[l] = (a->levels[l].W + 31) / 32;
+    prm.wtiles[l] = (a->levels[l].W + kKlCols - 1) / kKlCols;
     prm.block_start[l] = blocks;
-    blocks += prm.wtiles[l] * (a->C / (kKlChan * kKlWarps)) * a->N;
+    blocks += prm.wtiles[l] * nchunks * a->N;
   }
   prm.block_start[a->num_levels] = blocks;
-  DSKD_REQUIRE(cells == a->cells_per_image, "dsgfd_kl: cells_per_image mismatch");
-  if (cell) dsgfd_kl_kernel<true><<<blocks, 32 * kKlWarps, 0, as_stream(stream)>>>(prm);
-  else dsgfd_kl_kernel<false><<<blocks, 32 * kKlWarps, 0, as_stream(stream)>>>(prm);
+  const size_t smem = kl_header_bytes(max_h) + 8ull * kKlCols * max_h * warps;
+  int texp = 0;
+  const bool pow2 = frexpf(a->temperature, &texp) == 0.5f;  // T = 2^k: the division by T is an exact scaling
+  cudaStream_t st = as_stream(stream);
+#define DSKD_KL_LAUNCH(CELLV, P2V)                                                                                  \
+  do {                                                                                                              \
+    DSKD_CUDA_OK(cudaFuncSetAttribute(dsgfd_kl_kernel<CELLV, P2V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    dsgfd_kl_kernel<CELLV, P2V><<<blocks, 32 * warps, smem, st>>>(prm);                                             \
+  } while (0)
+  if (cell) { if (pow2) DSKD_KL_LAUNCH(true, true); else DSKD_KL_LAUNCH(true, false); }
+  else { if (pow2) DSKD_KL_LAUNCH(false, true); else DSKD_KL_LAUNCH(false, false); }
+#undef DSKD_KL_LAUNCH
   DSKD_LAUNCH_OK("dsgfd_kl_kernel");
   return DSKD_OK;
 }

@@ -9,7 +9,7 @@
 // i.e. a softmax over the matched queries with a null "background" logit 0 (soft ownership instead of the
 // reference's hard last-writer-wins rectangles, head_il.py:688-706), square-rooted like the reference's other
 // cell masks because the MSE squares it (head_il.py:914,1119).  The reference has no such contraction
-// (SURVEY.md section 0.4); this is the unpinned extension row, its oracle is oracle/qmem.py.
+// (SURVEY.md section 0.4); this is the unpinned extension row, its definition is the qmem module of the test oracle.
 //
 // Kernel anatomy (one CTA per SM, persistent, 320 threads, cta_group::1):
 //   warp 0   TMA producer : memory tiles [128 tokens x 32 ch] fp32 (one 128-byte swizzle row per token) through a

@@ -1,0 +1,156 @@
+"""One 40+40 incremental training step hosting the distillation hot path.
+
+Call stack mirrored (mmdet/models/detectors/deformable_detr_il.py:255-319 -> gfl_deformable_detr_head_il.py:412-1195):
+  teacher forward (no_grad) -> teacher keep-ids            dskd_b200.teacher_info_from_outputs      (CUDA)
+  pseudo labels gt := cat(teacher_pred, gt) (:462-465)     torch.cat
+  6 x N Hungarian assignments (:504-512, :1670-1797)       GFLHungarianAssigner.assign_batch        (CUDA + C++ LSAP)
+  QFL / DFL / L1 / GIoU per decoder layer (:1379-1533)     plain PyTorch below (stock detection losses, out of scope)
+  BCDD  loss_corr (:525-555)                               BetweenClassDistanceLoss                 (CUDA)
+  DSG-FD loss_fg_feature, decode_v1 (:664-719)             DSGFeatureDistillLoss                    (CUDA)
+  backward, grad-clip 0.1, AdamW (config :214-225)         torch
+"""
+import copy
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import build_loss, GFLHungarianAssigner, teacher_info_from_outputs
+from .model import GFLDeformableDETR
+
+
+def _cxcywh_to_xyxy(b):
+    cx, cy, w, h = b.unbind(-1)
+    return torch.stack([cx - 0.5 * w, cy - 0.5 * h, cx + 0.5 * w, cy + 0.5 * h], -1)
+
+
+def _iou_giou(a, b, eps=1e-6):
+    """aligned IoU and GIoU of xyxy boxes (iou2d_calculator.py:192-261, is_aligned=True)."""
+    lt, rb = torch.max(a[:, :2], b[:, :2]), torch.min(a[:, 2:], b[:, 2:])
+    wh = (rb - lt).clamp(min=0)
+    inter = wh[:, 0] * wh[:, 1]
+    area = lambda x: (x[:, 2] - x[:, 0]) * (x[:, 3] - x[:, 1])
+    union = (area(a) + area(b) - inter).clamp(min=eps)
+    iou = inter / union
+    e_wh = (torch.max(a[:, 2:], b[:, 2:]) - torch.min(a[:, :2], b[:, :2])).clamp(min=0)
+    e_area = (e_wh[:, 0] * e_wh[:, 1]).clamp(min=eps)
+    return iou, iou - (e_area - union) / e_area
+
+
+def integral_average(lrtb, reg_max=16):
+    """head_il.py:42-59."""
+    x = lrtb.reshape(-1, reg_max + 1)
+    x = x / x.sum(1, keepdim=True)
+    space = torch.linspace(0, reg_max, reg_max + 1, device=x.device) / reg_max / 2
+    return (x * space).sum(1).reshape(-1, 2, 2).sum(2)
+
+
+def detection_losses(cls, box70, targets, num_classes=80, reg_max=16, img_wh=None):
+    """QFL (beta 2, w 2.0) + L1 (w 5.0) + GIoU (w 2.0) + DFL (w 0.5) for ONE decoder layer (head_il.py:1379-1533,
+    losses/gfocal_loss.py).  cls [M,80], box70 [M,70] sigmoid outputs, targets: labels / bbox_targets / bbox_weights [M(,4)]."""
+    labels, bt, bw = targets['labels'], targets['bbox_targets'], targets['bbox_weights']
+    wh = integral_average(box70[:, 2:], reg_max)
+    pred = torch.cat((box70[:, :2], wh), 1)
+    pos = torch.nonzero(labels < num_classes).squeeze(1)
+    num_pos = max(float(pos.numel()), 1.0)
+    score = cls.new_zeros(labels.shape)
+    if pos.numel():
+        score[pos] = _iou_giou(_cxcywh_to_xyxy(pred[pos]), _cxcywh_to_xyxy(bt[pos]))[0].detach()
+    # QualityFocalLoss
+    sig = cls.sigmoid()
+    loss_cls = F.binary_cross_entropy_with_logits(cls, torch.zeros_like(cls), reduction='none') * sig.pow(2)
+    if pos.numel():
+        pl = labels[pos]
+        sf = score[pos] - sig[pos, pl]
+        loss_cls[pos, pl] = F.binary_cross_entropy_with_logits(cls[pos, pl], score[pos], reduction='none') * sf.abs().pow(2)
+    loss_cls = 2.0 * loss_cls.sum() / num_pos
+    factor = img_wh
+    giou = _iou_giou(_cxcywh_to_xyxy(pred) * factor, _cxcywh_to_xyxy(bt) * factor)[1]
+    loss_iou = 2.0 * ((1 - giou) * bw[:, 0]).sum() / num_pos
+    loss_bbox = 5.0 * ((pred - bt).abs() * bw).sum() / num_pos
+    # DistributionFocalLoss on the 4 x (reg_max+1) bins
+    corners = box70[:, 2:].reshape(-1, reg_max + 1)
+    target = (bt[:, 2:].unsqueeze(2).repeat(1, 1, 2).reshape(-1) / 2 * 2 * reg_max).clamp(0, reg_max - 0.01)
+    dl = target.long()
+    dr = dl + 1
+    logp = torch.log(corners.clamp(min=1e-12) / corners.sum(1, keepdim=True).clamp(min=1e-12))
+    dfl = -(logp.gather(1, dl[:, None]).squeeze(1) * (dr.float() - target) +
+            logp.gather(1, dr[:, None]).squeeze(1) * (target - dl.float()))
+    loss_dfl = 0.5 * (dfl * bw.reshape(-1)).sum() / (4 * num_pos)
+    return loss_cls + loss_iou + loss_bbox + loss_dfl
+
+
+def make_student_teacher(device, detections_per_image=30, num_prev=40, seed=0, **model_kw):
+    """Random-init student; teacher = deepcopy (tools/train_increment.py:250-251), frozen.  A random detector fires no
+    detection above score_thr = 0.3, so the teacher's class bias is calibrated on a probe batch to keep about
+    `detections_per_image` (query, class) pairs of the PREVIOUS classes per image -- synthetic stand-in for a trained task-1 model."""
+    torch.manual_seed(seed)
+    student = GFLDeformableDETR(**model_kw).to(device)
+    teacher = copy.deepcopy(student).eval()
+    for p in teacher.parameters():
+        p.requires_grad_(False)
+    with torch.no_grad():
+        probe = teacher(torch.randn(1, 3, 256, 320, device=device))['cls'][-1][0, :, :num_prev]      # [Q, prev]
+        k = min(detections_per_image, probe.numel() - 1)
+        kth = probe.flatten().topk(k + 1).values[-1]
+        shift = math.log(0.3 / 0.7) - float(kth) + 1e-3
+        teacher.cls_branch.bias[:num_prev] += shift
+        teacher.cls_branch.bias[num_prev:] = -20.0
+    return student, teacher
+
+
+class IncrementalTrainStep:
+    """student / teacher + the drop-in distillation path + AdamW: `step(img, gt_bboxes, gt_labels)` runs one iteration."""
+
+    def __init__(self, student, teacher, num_prev=40, criterion='kl', lr=4e-4, sync_prototypes=False):
+        self.student, self.teacher = student, teacher
+        self.prev_labels = list(range(num_prev))
+        self.assigner = GFLHungarianAssigner()
+        self.loss_corr = build_loss(dict(type='BetweenClassDistanceLoss', reduction='mean', loss_weight=1.0,
+                                         sync_prototypes=sync_prototypes))
+        self.loss_fg = build_loss(dict(type='DSGFeatureDistillLoss', criterion=criterion, T=2.0, reduction='sum',
+                                       loss_weight=1.0, mask_mode='decode_v1', feature_source='neck'))
+        params = [p for p in self.module.parameters() if p.requires_grad]
+        self.opt = torch.optim.AdamW(params, lr=lr, weight_decay=1e-4)
+        self.params = params
+
+    @property
+    def module(self):
+        return self.student.module if hasattr(self.student, 'module') else self.student
+
+    def step(self, img, gt_bboxes, gt_labels):
+        N, _, H, W = img.shape
+        dev = img.device
+        img_shapes = [(H, W)] * N
+        with torch.no_grad():
+            t = self.teacher(img)
+            tinfo = teacher_info_from_outputs(t['cls'][-1], t['box'][-1], img_shapes, score_thr=0.3, max_per_img=100)
+        s = self.student(img)
+        # hard + teacher-first pseudo labels (head_il.py:462-465)
+        all_b = [torch.cat([tb, gb]) for tb, gb in zip(tinfo['pred_bboxes'], gt_bboxes)]
+        all_l = [torch.cat([tl, gl]) for tl, gl in zip(tinfo['pred_labels'], gt_labels)]
+        tg = self.assigner.assign_batch(s['cls'].detach(), s['box'].detach(), all_b, all_l, img_shapes,
+                                        prev_labels=self.prev_labels)
+        L, Q = s['cls'].shape[0], s['cls'].shape[2]
+        M = N * Q
+        img_wh = torch.tensor([W, H, W, H], dtype=torch.float32, device=dev)
+        loss = 0.
+        for l in range(L):
+            sl = slice(l * M, (l + 1) * M)
+            loss = loss + detection_losses(s['cls'][l].reshape(M, -1), s['box'][l].reshape(M, -1),
+                                           dict(labels=tg['labels'][sl], bbox_targets=tg['bbox_targets'][sl],
+                                                bbox_weights=tg['bbox_weights'][sl]), img_wh=img_wh)
+        assignments = dict(student_labels=tg['labels'][(L - 1) * M:], teacher_keepid=tinfo['pred_keepid'],
+                           teacher_labels=tinfo['cat_labels'], teacher_bboxes=tinfo['pred_bboxes'],
+                           img_shapes=img_shapes, prev_labels=self.prev_labels, num_classes=self.module.num_classes)
+        queries = (s['hs'][-1], t['hs'][-1])
+        loss_corr = self.loss_corr(None, None, queries, assignments)
+        loss_fg = self.loss_fg(s['neck_feats'], t['neck_feats'], queries, assignments)
+        total = loss + loss_corr + loss_fg
+        self.opt.zero_grad(set_to_none=True)
+        total.backward()
+        torch.nn.utils.clip_grad_norm_(self.params, 0.1)
+        self.opt.step()
+        return dict(loss=total.detach(), loss_det=loss.detach(), loss_corr=loss_corr.detach(), loss_fg_feature=loss_fg.detach(),
+                    num_teacher=int(tinfo['pred_keepid'].numel()))

@@ -100,6 +100,9 @@ SIGNATURES = {
     'dskd_teacher_decode': [vp, vp, i32, i32, i32, i32, vp, f32, i32, vp, vp, vp, vp, vp, vp, vp],
     'dskd_teacher_compact': [vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
     'dskd_qmem_cell_weights': [C.POINTER(QmemArgs), vp],
+    'dskd_graph_instantiate_prioritized': [vp, i32, C.POINTER(vp), C.POINTER(i32), C.POINTER(i32)],
+    'dskd_graph_launch': [vp, vp],
+    'dskd_graph_exec_destroy': [vp],
     'dskd_lsap_f64': [vp, i32, i32, vp, vp],
     'dskd_lsap_batch_f32': [vp, i32, i32, i32, vp, vp, i32],
     'dskd_mse_elementwise': [vp, vp, vp, i64, f32, vp, vp, vp, vp, vp],

@@ -92,10 +92,21 @@ __global__ void __launch_bounds__(256) bcdd_distance_kernel(const float* __restr
   const int k = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   if (STAGED) {
-    for (int idx = threadIdx.x; idx < L * C; idx += blockDim.x) {
-      const int j = idx / C, c = idx - j * C;
-      ck_t[idx] = proto_elem(proto, num_classes, C, 0, j, c);
-      ck_s[idx] = proto_elem(proto, num_classes, C, 1, j, c);
+    // counts first (coef doubles as scratch: teacher count, then the student divisor goes to registers per row)
+    float* cnt_t = coef;                         // [L], overwritten by the coefficients after the distances
+    for (int j = threadIdx.x; j < L; j += blockDim.x) cnt_t[j] = proto[(int64_t)j * (C + 1) + C];
+    __syncthreads();
+    // one warp per prototype row: coalesced row loads, one IEEE division per element, four rows in flight
+    for (int j = warp; j < L; j += nw) {
+      const float n_t = cnt_t[j];
+      const float* t_row = proto + (int64_t)j * (C + 1);
+      const float* s_row = proto + ((int64_t)num_classes + j) * (C + 1);
+      const float n_s = s_row[C];
+      for (int c = lane; c < C; c += 32) {
+        const float a = t_row[c], b = s_row[c];
+        ck_t[j * C + c] = (n_t != 0.f) ? __fdiv_rn(a, n_t) : a;
+        ck_s[j * C + c] = (n_t != 0.f) ? __fdiv_rn(b, n_s) : b;
+      }
     }
   } else {
     for (int c = threadIdx.x; c < C; c += blockDim.x) {

@@ -360,6 +360,19 @@ int dskd_kd_kl_rows(const float* d_pred, const float* d_soft, int64_t outer, int
                     float temperature, const float* d_row_weight, float grad_scale, float* d_rowloss,
                     double* d_sum, float* d_grad_pred, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * CUDA-graph launch policy (no reference counterpart: the reference runs eagerly).  `graph` is a cudaGraph_t holding
+ * a captured loss step (e.g. torch.cuda.CUDAGraph(keep_graph=True).raw_cuda_graph()).  Every kernel node with fewer
+ * than big_grid_ctas CTAs gets the highest launch priority, the others the lowest, and the graph is instantiated with
+ * cudaGraphInstantiateFlagUseNodePriority so that the latency-bound chains (mask build, BCDD, the prototype
+ * all-reduce) are dispatched ahead of the remaining CTAs of the HBM-bound streaming kernel instead of behind them.
+ * *exec_out receives a cudaGraphExec_t owned by the caller (dskd_graph_exec_destroy).
+ * ------------------------------------------------------------------------------------------- */
+int dskd_graph_instantiate_prioritized(void* graph, int32_t big_grid_ctas, void** exec_out, int32_t* num_small,
+                                       int32_t* num_big);
+int dskd_graph_launch(void* exec, void* stream);
+int dskd_graph_exec_destroy(void* exec);
+
 /* x[i] *= *d_factor for i<n, skipped entirely when *d_factor == 1.0f (read on the device: no host
  * sync).  Used by autograd backward to apply grad_output to gradients staged by the fused kernels. */
 int dskd_scale_inplace(float* d_x, int64_t n, const float* d_factor, void* stream);

@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument('--no-graph', action='store_true', help='time eager launches only')
     ap.add_argument('--plain-graph', action='store_true', help='replay with torch.cuda.CUDAGraph (no node priorities)')
     ap.add_argument('--cpu-sample-images', type=int, default=2)
+    ap.add_argument('--no-feeders', action='store_true', help='skip the teacher keep-id / assignment timings')
     ap.add_argument('--no-contraction', action='store_true', help='skip the tcgen05 query x memory kernel line')
     ap.add_argument('--contraction-queries', type=int, default=300,
                     help="queries contracted against every memory token (north_star: ~300 x 256 against ~20k x 256)")
@@ -75,6 +76,39 @@ def recorded_traffic(kernel, images_per_gpu):
     if rec and int(rec.get('images_per_gpu', -1)) == int(images_per_gpu):
         return rec
     return None
+
+
+def time_path_feeders(args, dev, N):
+    """The rows of the hot path that FEED the losses, timed by wall clock around a device sync
+    (the host solver contains one): teacher keep-ids for N images, and the Hungarian assignment of all 6*N
+    (layer, image) problems with the device LSAP kernel and with the C++ host solver."""
+    import dskd_b200
+    from dskd_b200 import synth
+    ai = synth.make_assign_inputs(num_images=N, seed=1234, device=dev)
+    t_cls = ai.cls_logits[-1] + 0.5
+    out = {}
+
+    def wall(fn, reps=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            fn()
+            torch.cuda.synchronize()
+            ts.append(time.perf_counter() - t0)
+        return statistics.median(ts) * 1e3
+
+    out['teacher_keepids_ms'] = wall(lambda: dskd_b200.teacher_info_from_outputs(t_cls, ai.box_pred[-1], ai.img_shapes))
+    for solver in ('device', 'host'):
+        asg = dskd_b200.GFLHungarianAssigner(solver=solver)
+        out[f'assignment_{solver}_lsap_ms'] = wall(lambda: asg.assign_batch(
+            ai.cls_logits, ai.box_pred, ai.gt_bboxes, ai.gt_labels, ai.img_shapes, prev_labels=list(range(args.num_prev))))
+    out['problems'] = int(ai.cls_logits.shape[0] * N)
+    out['note'] = ('wall clock incl. Python and a final device sync; the device solver itself needs no sync and is '
+                   'index-identical to SciPy (tests/test_gpu_lsap.py)')
+    return out
 
 
 def time_contraction(args, dev, N, world, dist):
@@ -451,6 +485,8 @@ def main():
         'clocks': clocks,
         'loss': loss_value,
     }
+    if world == 1 and not args.no_feeders:
+        line['feeders'] = time_path_feeders(args, dev, N)
     if world == 1 and not args.no_cpu_baseline:
         base, _ = time_cpu_reference(args, steps=3, warmup=1)
         line['cpu_baseline'] = base

@@ -105,6 +105,7 @@ SIGNATURES = {
     'dskd_graph_exec_destroy': [vp],
     'dskd_lsap_f64': [vp, i32, i32, vp, vp],
     'dskd_lsap_batch_f32': [vp, i32, i32, i32, vp, vp, i32],
+    'dskd_lsap_batch_device': [vp, i32, i32, i32, i32, vp, i32, vp, vp, vp],
     'dskd_mse_elementwise': [vp, vp, vp, i64, f32, vp, vp, vp, vp, vp],
     'dskd_kd_kl_rows': [vp, vp, i64, i32, i64, f32, vp, f32, vp, vp, vp, vp],
     'dskd_scale_inplace': [vp, i64, vp, vp],

@@ -58,7 +58,7 @@ class GFLHungarianAssigner:
     def __init__(self, cls_cost=dict(type='QualityFocalLossCost', weight=2.0),
                  reg_cost=dict(type='BBoxL1Cost', weight=5.0, box_format='xywh'),
                  iou_cost=dict(type='IoUCost', iou_mode='giou', weight=2.0),
-                 num_classes=80, reg_max=16, num_threads=0):
+                 num_classes=80, reg_max=16, num_threads=0, solver='device'):
         if cls_cost.get('type', 'QualityFocalLossCost') != 'QualityFocalLossCost':
             raise NotImplementedError('only QualityFocalLossCost is on the DSKD path')
         if reg_cost.get('box_format', 'xywh') != 'xywh' or iou_cost.get('iou_mode', 'giou') != 'giou':
@@ -69,6 +69,9 @@ class GFLHungarianAssigner:
         self.num_classes = num_classes
         self.reg_max = reg_max
         self.num_threads = num_threads
+        if solver not in ('device', 'host'):
+            raise ValueError("solver must be 'device' (batched LSAP kernel, no host sync) or 'host' (C++ threads)")
+        self.solver = solver          # `assign_batch` only; the per-image `assign` always returns host-checked results
 
     # ------------------------------------------------------------------ batched path
     def cost_matrices(self, cls_scores, bbox_preds, gt_bboxes_list, gt_labels_list, img_shapes, decoded=False):
@@ -123,6 +126,20 @@ class GFLHungarianAssigner:
                                              C.c_void_p(out.data_ptr()), self.num_threads), 'dskd_lsap_batch_f32')
         return out
 
+    def solve_device(self, cost: torch.Tensor, m: dict, check: bool = False) -> torch.Tensor:
+        """The same matching on the device (`dskd_lsap_batch_device`): no copy of the cost matrices, no host sync.
+        `check=True` reads the per-problem status back (one sync) and raises like SciPy on an infeasible matrix."""
+        P, Q, ld = cost.shape
+        dev = cost.device
+        assigned = torch.empty(P, Q, dtype=torch.int64, device=dev)
+        status = torch.empty(P, dtype=torch.int32, device=dev)
+        L.check(L.load().dskd_lsap_batch_device(L.ptr(cost), P, m['N'], Q, ld, L.ptr(m['gt_start']), m['max_gt'],
+                                                L.ptr(assigned), L.ptr(status), L.stream_of(cost)), 'dskd_lsap_batch_device')
+        self.last_status = status
+        if check and bool((status != 0).any()):
+            raise ValueError('cost matrix is infeasible')          # scipy.optimize.linear_sum_assignment's message
+        return assigned
+
     def assign_batch(self, cls_scores, bbox_preds, gt_bboxes_list, gt_labels_list, img_shapes,
                      prev_labels: Optional[Sequence[int]] = None) -> Dict[str, torch.Tensor]:
         """All decoder layers at once (`loss_single_split` x 6 -> `get_targets`, head_il.py:504-512,1437-1455).
@@ -134,10 +151,12 @@ class GFLHungarianAssigner:
         cost, cols, m = self.cost_matrices(cls_scores, bbox_preds, gt_bboxes_list, gt_labels_list, img_shapes)
         dev = cost.device
         P, N, Q = m['P'], m['N'], m['Q']
-        if m['max_gt'] > 0:
-            assigned = self.solve(cost, cols).to(dev, non_blocking=True)
-        else:
+        if m['max_gt'] == 0:
             assigned = torch.zeros(P, Q, dtype=torch.int64, device=dev)
+        elif self.solver == 'device' and max(Q, m['max_gt']) <= 1024:
+            assigned = self.solve_device(cost, m)
+        else:
+            assigned = self.solve(cost, cols).to(dev, non_blocking=True)
         labels = torch.empty(P * Q, dtype=torch.int64, device=dev)
         bt = torch.empty(P * Q, 4, dtype=torch.float32, device=dev)
         bw = torch.empty(P * Q, 4, dtype=torch.float32, device=dev)

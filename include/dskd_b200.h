@@ -343,6 +343,16 @@ int dskd_lsap_f64(const double* h_cost, int32_t rows, int32_t cols, int64_t* h_r
 int dskd_lsap_batch_f32(const float* h_cost, int32_t num_problems, int32_t rows, int32_t ld,
                         const int32_t* h_cols, int64_t* h_assigned_gt, int32_t num_threads);
 
+/* The same solver on the DEVICE for a batch laid out like dskd_cost_matrix's output (problem p: [rows, cols_p]
+ * with row stride ld, cols_p = d_gt_start[p % N + 1] - d_gt_start[p % N] <= max_cols): one CTA per problem, float64
+ * arithmetic in SciPy's operation order and tie-breaking, so the indices are identical to dskd_lsap_batch_f32 / SciPy
+ * -- without the device->host copy and sync of gfl_hungarian_assigner.py:143-151.  Asynchronous on `stream`.
+ * d_assigned_gt int64 [P, rows] (1-based matched column or 0); d_status int32 [P] (DSKD_OK / DSKD_EINFEASIBLE for a
+ * matrix with NaN / -inf or no feasible matching; may be NULL).  max(rows, max_cols) <= 1024. */
+int dskd_lsap_batch_device(const float* d_cost, int32_t num_problems, int32_t N, int32_t rows, int32_t ld,
+                           const int32_t* d_gt_start, int32_t max_cols, int64_t* d_assigned_gt, int32_t* d_status,
+                           void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Registry loss modules (mse_loss.py, kd_loss.py, utils.py) -- generic tensors
  * ------------------------------------------------------------------------------------------- */

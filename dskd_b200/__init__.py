@@ -6,7 +6,7 @@ assignment, and the MSE / KD-KL loss modules, all backed by hand-written CUDA ke
 C ABI in include/dskd_b200.h.  Importing this package never falls back to a CPU implementation.
 """
 from .registry import LOSSES, ASSIGNERS, build_loss, build_assigner, register_into_mmdet  # noqa: F401
-from .losses import (DSGFeatureDistillLoss, BetweenClassDistanceLoss, MSELoss,  # noqa: F401
+from .losses import (DSGFeatureDistillLoss, BetweenClassDistanceLoss, MSELoss, SmoothL1Loss, L1Loss,  # noqa: F401
                      KnowledgeDistillationKLDivLoss)
 from .assigner import GFLHungarianAssigner, AssignResult, lsap  # noqa: F401
 from . import synth, teacher, dist  # noqa: F401

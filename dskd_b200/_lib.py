@@ -107,6 +107,7 @@ SIGNATURES = {
     'dskd_lsap_batch_f32': [vp, i32, i32, i32, vp, vp, i32],
     'dskd_lsap_batch_device': [vp, i32, i32, i32, i32, vp, i32, vp, vp, vp],
     'dskd_mse_elementwise': [vp, vp, vp, i64, f32, vp, vp, vp, vp, vp],
+    'dskd_elementwise_loss': [i32, f32, vp, vp, vp, i64, f32, vp, vp, vp, vp, vp],
     'dskd_kd_kl_rows': [vp, vp, i64, i32, i64, f32, vp, f32, vp, vp, vp, vp],
     'dskd_scale_inplace': [vp, i64, vp, vp],
     'dskd_f64_to_f32': [vp, vp, i32, f32, vp],

@@ -4,9 +4,12 @@
 
 namespace dskd {
 
+// KIND 0: (pred-target)^2 (mse_loss.py:9-12); 1: smooth L1 with threshold beta (smooth_l1_loss.py:12-35);
+// 2: |pred-target| (smooth_l1_loss.py:38-56).
+template <int KIND>
 __global__ void __launch_bounds__(256) mse_elementwise_kernel(const float* __restrict__ pred,
                                                               const float* __restrict__ target,
-                                                              const float* __restrict__ weight, int64_t n,
+                                                              const float* __restrict__ weight, int64_t n, float beta,
                                                               float grad_scale, float* __restrict__ elem,
                                                               double* __restrict__ sum, float* __restrict__ gp,
                                                               float* __restrict__ gt) {
@@ -15,10 +18,24 @@ __global__ void __launch_bounds__(256) mse_elementwise_kernel(const float* __res
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float d = pred[i] - target[i];
     const float w = weight ? weight[i] : 1.f;
-    const float e = d * d * w;
+    float l, dl;  // loss and d loss / d pred before the weight
+    if (KIND == 0) {
+      l = d * d;
+      dl = 2.f * d;
+    } else {
+      const float a = fabsf(d), sgn = (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f);
+      if (KIND == 1 && a < beta) {
+        l = __fdiv_rn(0.5f * a * a, beta);
+        dl = __fdiv_rn(d, beta);
+      } else {
+        l = (KIND == 1) ? a - 0.5f * beta : a;
+        dl = sgn;
+      }
+    }
+    const float e = l * w;
     if (elem) elem[i] = e;
     acc += (double)e;
-    const float g = 2.f * d * w * grad_scale;
+    const float g = dl * w * grad_scale;
     if (gp) gp[i] = g;
     if (gt) gt[i] = -g;
   }
@@ -93,17 +110,30 @@ __global__ void __launch_bounds__(256) kd_kl_rows_kernel(const float* __restrict
 
 using namespace dskd;
 
+extern "C" int dskd_elementwise_loss(int32_t kind, float beta, const float* d_pred, const float* d_target,
+                                     const float* d_weight, int64_t n, float grad_scale, float* d_elem, double* d_sum,
+                                     float* d_grad_pred, float* d_grad_target, void* stream) {
+  DSKD_REQUIRE(n >= 0, "dskd_elementwise_loss: negative size");
+  DSKD_REQUIRE(kind >= 0 && kind <= 2, "dskd_elementwise_loss: kind must be 0 (mse), 1 (smooth L1) or 2 (L1)");
+  DSKD_REQUIRE(kind != 1 || beta > 0.f, "dskd_elementwise_loss: smooth L1 needs beta > 0 (smooth_l1_loss.py:24)");
+  if (n == 0) return DSKD_OK;
+  DSKD_REQUIRE(d_pred && d_target, "dskd_elementwise_loss: null pointer");
+  const int grid = (int)std::min<int64_t>(ceil_div(n, 256), (int64_t)kNumSMs * 8);
+  cudaStream_t st = as_stream(stream);
+  if (kind == 0)
+    mse_elementwise_kernel<0><<<grid, 256, 0, st>>>(d_pred, d_target, d_weight, n, beta, grad_scale, d_elem, d_sum, d_grad_pred, d_grad_target);
+  else if (kind == 1)
+    mse_elementwise_kernel<1><<<grid, 256, 0, st>>>(d_pred, d_target, d_weight, n, beta, grad_scale, d_elem, d_sum, d_grad_pred, d_grad_target);
+  else
+    mse_elementwise_kernel<2><<<grid, 256, 0, st>>>(d_pred, d_target, d_weight, n, beta, grad_scale, d_elem, d_sum, d_grad_pred, d_grad_target);
+  DSKD_LAUNCH_OK("mse_elementwise_kernel");
+  return DSKD_OK;
+}
+
 extern "C" int dskd_mse_elementwise(const float* d_pred, const float* d_target, const float* d_weight, int64_t n,
                                     float grad_scale, float* d_elem, double* d_sum, float* d_grad_pred,
                                     float* d_grad_target, void* stream) {
-  DSKD_REQUIRE(n >= 0, "dskd_mse_elementwise: negative size");
-  if (n == 0) return DSKD_OK;
-  DSKD_REQUIRE(d_pred && d_target, "dskd_mse_elementwise: null pointer");
-  const int grid = (int)std::min<int64_t>(ceil_div(n, 256), (int64_t)kNumSMs * 8);
-  mse_elementwise_kernel<<<grid, 256, 0, as_stream(stream)>>>(d_pred, d_target, d_weight, n, grad_scale, d_elem,
-                                                             d_sum, d_grad_pred, d_grad_target);
-  DSKD_LAUNCH_OK("mse_elementwise_kernel");
-  return DSKD_OK;
+  return dskd_elementwise_loss(0, 0.f, d_pred, d_target, d_weight, n, grad_scale, d_elem, d_sum, d_grad_pred, d_grad_target, stream);
 }
 
 extern "C" int dskd_kd_kl_rows(const float* d_pred, const float* d_soft, int64_t outer, int32_t D, int64_t inner,

@@ -491,6 +491,9 @@ class BetweenClassDistanceLoss(nn.Module):
 # ----------------------------------------------------------------------------------------------
 # The registry modules the reference head builds by config (R1-R3)
 # ----------------------------------------------------------------------------------------------
+_ELEMENTWISE_KINDS = {'mse': 0, 'smooth_l1': 1, 'l1': 2}
+
+
 class _ElementwiseFn(torch.autograd.Function):
     """kind 'mse': (pred-target)^2 ; kind 'kd': KL rows over dim=1.  Returns the un-reduced loss
     (elementwise weight applied) and its sum; gradients staged for d(sum) = 1."""
@@ -503,12 +506,14 @@ class _ElementwiseFn(torch.autograd.Function):
         dev = pred.device
         acc = torch.zeros(1, dtype=torch.float64, device=dev)
         total = torch.empty(1, dtype=torch.float32, device=dev)
-        if kind == 'mse':
+        if kind in _ELEMENTWISE_KINDS:
             elem = torch.empty_like(pred)
             gp = torch.empty_like(pred) if ctx.needs_input_grad[2] else None
             gt = torch.empty_like(pred) if ctx.needs_input_grad[3] else None
-            L.check(lib.dskd_mse_elementwise(L.ptr(pred), L.ptr(target), L.ptr(weight), pred.numel(), 1.0, L.ptr(elem),
-                                             L.ptr(acc), L.ptr(gp), L.ptr(gt), st), 'dskd_mse_elementwise')
+            # for the elementwise criteria `T` carries smooth L1's beta
+            L.check(lib.dskd_elementwise_loss(_ELEMENTWISE_KINDS[kind], float(T), L.ptr(pred), L.ptr(target), L.ptr(weight),
+                                              pred.numel(), 1.0, L.ptr(elem), L.ptr(acc), L.ptr(gp), L.ptr(gt), st),
+                    'dskd_elementwise_loss')
         else:
             outer, D = pred.shape[0], pred.shape[1]
             inner = pred.numel() // max(outer * D, 1)
@@ -533,7 +538,7 @@ class _ElementwiseFn(torch.autograd.Function):
         # d/d elem arrives per row (kd) or per element (mse); d/d total is a scalar
         coef = None
         if g_elem is not None:
-            coef = g_elem if ctx.kind == 'mse' else g_elem.unsqueeze(1)
+            coef = g_elem if ctx.kind in _ELEMENTWISE_KINDS else g_elem.unsqueeze(1)
         if g_total is not None:
             coef = g_total if coef is None else coef + g_total
         out_p = gp * coef if gp is not None and coef is not None else None
@@ -549,10 +554,10 @@ def _weighted_reduce(kind, T, pred, target, weight, reduction, avg_factor, loss_
     pred_c, target_c = L.f32c(pred), L.f32c(target)
     w = None
     if weight is not None:
-        shape = pred.shape if kind == 'mse' else (pred.shape[0],) + tuple(pred.shape[2:])
+        shape = pred.shape if kind in _ELEMENTWISE_KINDS else (pred.shape[0],) + tuple(pred.shape[2:])
         w = L.f32c(weight.expand(shape)) if tuple(weight.shape) != tuple(shape) else L.f32c(weight)
     if pred_c.numel() == 0:
-        elem = pred_c.new_zeros(pred.shape if kind == 'mse' else (pred.shape[0],) + tuple(pred.shape[2:]))
+        elem = pred_c.new_zeros(pred.shape if kind in _ELEMENTWISE_KINDS else (pred.shape[0],) + tuple(pred.shape[2:]))
         total = elem.sum()
     else:
         if kind == 'kd' and pred_c.dim() < 2:
@@ -588,6 +593,39 @@ class MSELoss(nn.Module):
         assert reduction_override in _REDUCTIONS
         reduction = reduction_override if reduction_override else self.reduction
         return _weighted_reduce('mse', 1.0, pred, target, weight, reduction, avg_factor, self.loss_weight)
+
+
+@LOSSES.register_module()
+class SmoothL1Loss(nn.Module):
+    """mmdet/models/losses/smooth_l1_loss.py:59-101 on `dskd_elementwise_loss` -- the criterion of the head's `bbox`
+    localisation distillation (`loss_ld_bbox`, gfl_deformable_detr_head_il.py:625-636)."""
+
+    def __init__(self, beta=1.0, reduction='mean', loss_weight=1.0):
+        super().__init__()
+        assert beta > 0
+        self.beta = beta
+        self.reduction = reduction
+        self.loss_weight = loss_weight
+
+    def forward(self, pred, target, weight=None, avg_factor=None, reduction_override=None, **kwargs):
+        assert reduction_override in _REDUCTIONS
+        reduction = reduction_override if reduction_override else self.reduction
+        return _weighted_reduce('smooth_l1', self.beta, pred, target, weight, reduction, avg_factor, self.loss_weight)
+
+
+@LOSSES.register_module()
+class L1Loss(nn.Module):
+    """mmdet/models/losses/smooth_l1_loss.py:104-146."""
+
+    def __init__(self, reduction='mean', loss_weight=1.0):
+        super().__init__()
+        self.reduction = reduction
+        self.loss_weight = loss_weight
+
+    def forward(self, pred, target, weight=None, avg_factor=None, reduction_override=None):
+        assert reduction_override in _REDUCTIONS
+        reduction = reduction_override if reduction_override else self.reduction
+        return _weighted_reduce('l1', 1.0, pred, target, weight, reduction, avg_factor, self.loss_weight)
 
 
 @LOSSES.register_module()

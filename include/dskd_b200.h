@@ -362,6 +362,13 @@ int dskd_mse_elementwise(const float* d_pred, const float* d_target, const float
                          float grad_scale, float* d_elem, double* d_sum, float* d_grad_pred,
                          float* d_grad_target, void* stream);
 
+/* Same contract for the other elementwise criteria the head builds by config: kind 0 = MSE, 1 = smooth L1 with
+ * threshold beta (`loss_ld_bbox=dict(type='SmoothL1Loss')`, chaosuan_..._40_...py:118; smooth_l1_loss.py:12-35),
+ * 2 = L1 (smooth_l1_loss.py:38-56). */
+int dskd_elementwise_loss(int32_t kind, float beta, const float* d_pred, const float* d_target, const float* d_weight,
+                          int64_t n, float grad_scale, float* d_elem, double* d_sum, float* d_grad_pred,
+                          float* d_grad_target, void* stream);
+
 /* knowledge_distillation_kl_div_loss on [outer, D, inner] with softmax over D (dim=1 of the
  * reference's [N,D] or [C,H,W] inputs): d_rowloss [outer*inner] = T^2/D * sum_d t(log t - logp);
  * optional d_row_weight[outer*inner] scales loss & grad; d_grad_pred (same shape as pred, optional)

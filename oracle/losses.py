@@ -4,6 +4,7 @@ TEST INFRASTRUCTURE -- see oracle/__init__.py.  Restates
   mmdet/models/losses/utils.py:9-105       (reduce / weight / avg_factor rules)
   mmdet/models/losses/mse_loss.py:9-57     (MSELoss)
   mmdet/models/losses/kd_loss.py:12-94     (KnowledgeDistillationKLDivLoss)
+  mmdet/models/losses/smooth_l1_loss.py:12-146 (SmoothL1Loss / L1Loss: the `bbox` localisation distillation term)
 """
 import torch
 import torch.nn.functional as F
@@ -76,9 +77,43 @@ class KnowledgeDistillationKLDivLoss(torch.nn.Module):
             kd_kl_elementwise(pred, soft_label, self.T), weight, reduction, avg_factor)
 
 
+def smooth_l1_elementwise(pred, target, beta=1.0):
+    """smooth_l1_loss.py:12-35."""
+    assert beta > 0
+    diff = torch.abs(pred - target)
+    return torch.where(diff < beta, 0.5 * diff * diff / beta, diff - 0.5 * beta)
+
+
+class SmoothL1Loss(torch.nn.Module):
+    """smooth_l1_loss.py:59-101."""
+
+    def __init__(self, beta=1.0, reduction='mean', loss_weight=1.0):
+        super().__init__()
+        self.beta, self.reduction, self.loss_weight = beta, reduction, loss_weight
+
+    def forward(self, pred, target, weight=None, avg_factor=None, reduction_override=None):
+        assert reduction_override in _REDUCTIONS
+        reduction = reduction_override if reduction_override else self.reduction
+        return self.loss_weight * reduce_elementwise(smooth_l1_elementwise(pred, target, self.beta), weight, reduction,
+                                                     avg_factor)
+
+
+class L1Loss(torch.nn.Module):
+    """smooth_l1_loss.py:104-146."""
+
+    def __init__(self, reduction='mean', loss_weight=1.0):
+        super().__init__()
+        self.reduction, self.loss_weight = reduction, loss_weight
+
+    def forward(self, pred, target, weight=None, avg_factor=None, reduction_override=None):
+        assert reduction_override in _REDUCTIONS
+        reduction = reduction_override if reduction_override else self.reduction
+        return self.loss_weight * reduce_elementwise(torch.abs(pred - target), weight, reduction, avg_factor)
+
+
 def build_loss(cfg):
     """builder.py:43-45 for the two types on the path."""
     cfg = dict(cfg)
     kind = cfg.pop('type')
-    return {'MSELoss': MSELoss,
+    return {'MSELoss': MSELoss, 'SmoothL1Loss': SmoothL1Loss, 'L1Loss': L1Loss,
             'KnowledgeDistillationKLDivLoss': KnowledgeDistillationKLDivLoss}[kind](**cfg)

@@ -87,3 +87,26 @@ def test_whole_map_kldv_and_memory_kl(case):
     s_mem, t_mem = inp.memory()
     for s_img, t_img in zip(s_mem.permute(1, 2, 0), t_mem.permute(1, 2, 0)):   # [C, S] per image: softmax over the tokens
         check(gpu, cpu, s_img.contiguous(), t_img.contiguous(), 1e-3, weight=None, avg_factor=None)
+
+
+def test_smooth_l1_and_l1_vs_reference_outputs():
+    """The CUDA modules against the reference's own SmoothL1Loss / L1Loss outputs (tests/golden/losses_smooth_l1.npz)."""
+    from conftest import Golden
+    g = Golden('losses_smooth_l1.npz')
+    pred, tgt, w = g.t('pred').to(DEV), g.t('target').to(DEV), g.t('weight').to(DEV)
+
+    def close(a, b):
+        torch.testing.assert_close(a.detach().cpu(), b, rtol=1e-5, atol=1e-6)
+    for beta in (1.0, 0.11, 2.5):
+        for red in ('none', 'mean', 'sum'):
+            close(dskd_b200.SmoothL1Loss(beta, red, 10.0)(pred, tgt), g.t(f'sl1.b{beta}.{red}'))
+        close(dskd_b200.SmoothL1Loss(beta, 'mean', 10.0)(pred, tgt, weight=w, avg_factor=9.0), g.t(f'sl1.b{beta}.mean.w.avg9'))
+        p = pred.clone().requires_grad_(True)
+        dskd_b200.SmoothL1Loss(beta, 'sum', 0.5)(p, tgt, weight=w).backward()
+        close(p.grad, g.t(f'sl1.b{beta}.grad'))
+    for red in ('none', 'mean', 'sum'):
+        close(dskd_b200.L1Loss(red, 5.0)(pred, tgt), g.t(f'l1.{red}'))
+    close(dskd_b200.L1Loss('mean', 5.0)(pred, tgt, weight=w, avg_factor=9.0), g.t('l1.mean.w.avg9'))
+    p = pred.clone().requires_grad_(True)
+    dskd_b200.L1Loss('sum')(p, tgt, weight=w).backward()
+    close(p.grad, g.t('l1.grad'))

@@ -43,6 +43,24 @@ def test_loss_modules_vs_reference():
     assert t.grad is None and g.v('kd.grad_target_is_none')
 
 
+def test_smooth_l1_and_l1_vs_reference():
+    g = Golden('losses_smooth_l1.npz')
+    pred, tgt, w = g.t('pred'), g.t('target'), g.t('weight')
+    for beta in (1.0, 0.11, 2.5):
+        for red in ('none', 'mean', 'sum'):
+            close(ol.SmoothL1Loss(beta, red, 10.0)(pred, tgt), g.t(f'sl1.b{beta}.{red}'))
+        close(ol.SmoothL1Loss(beta, 'mean', 10.0)(pred, tgt, weight=w, avg_factor=9.0), g.t(f'sl1.b{beta}.mean.w.avg9'))
+        p = pred.clone().requires_grad_(True)
+        ol.SmoothL1Loss(beta, 'sum', 0.5)(p, tgt, weight=w).backward()
+        close(p.grad, g.t(f'sl1.b{beta}.grad'))
+    for red in ('none', 'mean', 'sum'):
+        close(ol.L1Loss(red, 5.0)(pred, tgt), g.t(f'l1.{red}'))
+    close(ol.L1Loss('mean', 5.0)(pred, tgt, weight=w, avg_factor=9.0), g.t('l1.mean.w.avg9'))
+    p = pred.clone().requires_grad_(True)
+    ol.L1Loss('sum')(p, tgt, weight=w).backward()
+    close(p.grad, g.t('l1.grad'))
+
+
 def test_loss_module_known_answers():
     # reference tests/test_metrics/test_losses.py:82-109 and tests/test_models/test_loss.py:28-88
     with pytest.raises(AssertionError):

@@ -447,8 +447,9 @@ def test_grad_output_scaling_and_single_backward():
     feats3, hs3 = gpu.clone_student()
     loss3 = mod(feats3, gpu.teacher_feats, (hs3, gpu.hs_teacher), gpu.assignments)
     (loss3 * 3.0).backward(retain_graph=True)
-    # two forward passes differ in the last bits (fp32 atomics into the energy table), hence 1e-5
-    torch.testing.assert_close(hs3.grad, hs.grad * 3.0, rtol=1e-5, atol=1e-9)
+    # two forward passes differ in the last bits (the order of the fp32 atomics into the energy table is not fixed,
+    # and the softmax backward subtracts nearly equal terms), hence 1e-4 with a floor relative to the largest gradient
+    torch.testing.assert_close(hs3.grad, hs.grad * 3.0, rtol=1e-4, atol=1e-6 * float(hs.grad.abs().max()) * 3.0)
     torch.testing.assert_close(feats3[0].grad, feats[0].grad * 3.0, rtol=1e-6, atol=0)
     with pytest.raises(RuntimeError):
         (loss3 * 3.0).backward()

@@ -51,7 +51,6 @@ struct QmemParams {
   float* weight;            // [N, S]
   int stages;               // memory-tile ring depth (<= kMaxAStages)
   int n_lo, n_hi;           // pair mode: columns of the two MMAs per k-step (n_hi may be 0); NB = n_lo + n_hi
-  int debug;                // DSKD_QMEM_DEBUG bits (perf experiments): 1 skip epilogue math, 2 skip MMA issue
 };
 
 // ------------------------------------------------------------------------------------------------ PTX
@@ -299,7 +298,7 @@ qmem_weight_kernel(const __grid_constant__ CUtensorMap tmap_mem, const __grid_co
           const uint64_t db = smem_desc_sw128(smem_q + ks * q_slab_bytes);
 #pragma unroll
           for (int kk = 0; kk < kSlabCh / 8; ++kk)  // 8 tf32 = 32 bytes along K per instruction: +2 in 16-byte units
-            if (!(p.debug & 2)) umma_tf32(tmem_d, da + 2 * kk, db + 2 * kk, idesc, (ks | kk) ? 1u : 0u);
+            umma_tf32(tmem_d, da + 2 * kk, db + 2 * kk, idesc, (ks | kk) ? 1u : 0u);
           umma_commit(bar_empty + 8 * stage);  // frees the memory-tile stage when those MMAs retire
           if (++stage == kAStages) { stage = 0; phase ^= 1; }
         }
@@ -323,7 +322,7 @@ qmem_weight_kernel(const __grid_constant__ CUtensorMap tmap_mem, const __grid_co
       const uint32_t acc = (uint32_t)(n % kAccStages), acc_phase = (uint32_t)((n / kAccStages) & 1);
       const int img = (int)(t / p.tiles_per_image), tt = (int)(t % p.tiles_per_image);
       const int K = p.box_start[img + 1] - p.box_start[img];
-      const int kv = (p.debug & 1) ? 0 : max(0, min(p.NB, K - b * p.NB));  // valid query columns of this block
+      const int kv = max(0, min(p.NB, K - b * p.NB));  // valid query columns of this block
       const float4* __restrict__ cj = reinterpret_cast<const float4*>(p.cpad + ((long long)img * p.nblk + b) * p.NB);
       mbar_wait(bar_accfull + 8 * acc, acc_phase);
       tc_fence_after();
@@ -462,7 +461,6 @@ qmem_weight_pair_kernel(const __grid_constant__ CUtensorMap tmap_mem, const __gr
           const uint64_t dbh = smem_desc_sw128(smem_q + ks * q_slab_bytes + hi_row_bytes);
 #pragma unroll
           for (int kk = 0; kk < kSlabCh / 8; ++kk) {
-            if (p.debug & 2) continue;
             umma_tf32_pair(tmem_base, da + 2 * kk, db + 2 * kk, idesc_lo, (ks | kk) ? 1u : 0u);
             if (p.n_hi) umma_tf32_pair(tmem_base + p.n_lo, da + 2 * kk, dbh + 2 * kk, idesc_hi, (ks | kk) ? 1u : 0u);
           }
@@ -485,7 +483,7 @@ qmem_weight_pair_kernel(const __grid_constant__ CUtensorMap tmap_mem, const __gr
     for (long long t = t_begin; t < t_end; ++t) {
       const int img = (int)(t / p.tiles_per_image), tt = (int)(t % p.tiles_per_image);
       const int K = p.box_start[img + 1] - p.box_start[img];
-      const int kv = (p.debug & 1) ? 0 : max(0, min(p.NB, K - b * p.NB));
+      const int kv = max(0, min(p.NB, K - b * p.NB));
       const float4* __restrict__ cj = reinterpret_cast<const float4*>(p.cpad + ((long long)img * p.nblk + b) * p.NB);
       mbar_wait(bar_accfull, acc_phase);
       acc_phase ^= 1;
@@ -691,11 +689,9 @@ extern "C" int dskd_qmem_cell_weights(const DskdQmemArgs* a, void* stream) {
   p.weight = a->d_cell_weight;
   p.n_lo = plan.n_lo;
   p.n_hi = plan.n_hi;
-  { const char* dbg = getenv("DSKD_QMEM_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
   const int resident_rows = plan.pair ? plan.NB / 2 : plan.NB;
   const size_t kSmemMax = 227 * 1024, fixed = 1024 + (size_t)resident_rows * a->C * 4 + 512;
   int stages = (int)std::min<size_t>(kMaxAStages, (kSmemMax - fixed) / kAStageBytes);
-  { const char* e = getenv("DSKD_QMEM_STAGES"); if (e && atoi(e) > 0) stages = std::min(stages, atoi(e)); }
   DSKD_REQUIRE(stages >= 2, "dskd_qmem_cell_weights: not enough shared memory for the memory-tile ring");
   p.stages = stages;
   const size_t smem = fixed + (size_t)stages * kAStageBytes;

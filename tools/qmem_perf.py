@@ -54,7 +54,7 @@ def bench(N, K, S=22223, C=256, Q=None, iters=15, mode=None):
     return ms
 
 
-if __name__ == '__main__':
+if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == 'one':
         bench(int(sys.argv[2]), int(sys.argv[3]), mode=sys.argv[4] if len(sys.argv) > 4 else None)
         sys.exit(0)

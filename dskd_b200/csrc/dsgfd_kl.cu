@@ -18,18 +18,22 @@ namespace dskd {
 //   A. turns them in place into the logits x = feature * mask / T (0 outside boxes) and takes the column maxima,
 //   B. sums e^(x - max) for both softmaxes and sum e^(xs - max) (xs - xt) -- the KL of a column needs nothing else:
 //        KL = sum_h t_h (xs_h - xt_h) - (lse_s - lse_t),
-//   C. (only when the mask rows need a gradient) accumulates T_h * (p_h - t_h) per owning box over each run of rows
-//      (warp-cooperative sum, one red.global per box, run and channel).
-// The owner strip and the runs -- maximal row ranges in which no column changes owner -- are computed once per CTA and
-// shared by all its channels, so the per-channel sweeps carry no per-row ownership tests.
+//   C. (only when the mask rows need a gradient) accumulates T_h * (p_h - t_h) per box segment of each column and
+//      issues one red.global per (column, segment, channel).
+// The owner strip and the segment number of every cell are computed once per CTA and shared by all its channels, so
+// the gradient sweep carries no ownership logic.
 constexpr int kKlChan = 4;        // channels per warp (sequential)
 constexpr int kKlCols = 8;        // columns (w) per strip: a warp covers kKlCols columns x kKlPhases interleaved row phases
 constexpr int kKlPhases = 32 / kKlCols;
 constexpr int kKlMaxWarps = 32;   // warps per CTA
 constexpr int kKlMaxH = 800;      // rows per level the shared-memory strips can hold (one warp per CTA at the limit)
 constexpr size_t kKlSmemBudget = 220 * 1024;
-// owner strip (kKlCols ints per row) + run table, rounded to 128 B
-__host__ __device__ inline size_t kl_header_bytes(int max_h) { return ((size_t)max_h * kKlCols * 4 + (size_t)(max_h + 2) * 4 + 127) / 128 * 128; }
+constexpr int kKlSegGroup = 4;    // box segments of a column accumulated per pass of the gradient sweep
+__host__ __device__ inline size_t kl_header_bytes(int max_h) {
+  // owner strip int32 [max_h][kKlCols] | segment owners int32 [kKlCols][max_h] | segments per column int32 [kKlCols]
+  // | segment slot of every cell uint16 [max_h][kKlCols]
+  return ((size_t)max_h * kKlCols * 4 * 2 + (size_t)kKlCols * 4 + (size_t)max_h * kKlCols * 2 + 127) / 128 * 128;
+}
 
 struct KlParams {
   DskdLevel levels[DSKD_MAX_LEVELS];
@@ -64,7 +68,7 @@ template <bool CELL, bool POW2>
 __global__ void __launch_bounds__(32 * kKlMaxWarps) dsgfd_kl_kernel(const __grid_constant__ KlParams prm) {
   extern __shared__ __align__(16) unsigned char kl_smem[];
   __shared__ double red[32];
-  __shared__ int strip_any, num_runs;
+  __shared__ int strip_any, max_seg;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wl = lane % kKlCols, ph = lane / kKlCols;  // column inside the strip, row phase (rows ph, ph + kKlPhases, ...)
   int lvl = 0;
@@ -87,16 +91,18 @@ __global__ void __launch_bounds__(32 * kKlMaxWarps) dsgfd_kl_kernel(const __grid
   const int64_t strip_base = (int64_t)img * prm.cells_per_image + prm.levels[lvl].cell_offset + wt * kKlCols;
   const int64_t cell_base = strip_base + wl;
 
-  // shared memory: owner strip int32 [max_h][kKlCols] | run starts int32 [max_h + 2] | per warp: xs, xt [max_h][kKlCols]
+  // shared memory: header (owner strip, segment tables; kl_header_bytes) | per warp: xs, xt [max_h][kKlCols]
   int* own_s = reinterpret_cast<int*>(kl_smem);
-  int* run_s = own_s + (size_t)prm.max_h * kKlCols;
+  int* seg_owner = own_s + (size_t)prm.max_h * kKlCols;          // [col][k]: owner of the k-th box segment of the column
+  int* nseg_s = seg_owner + (size_t)prm.max_h * kKlCols;         // [col]
+  unsigned short* slot_s = reinterpret_cast<unsigned short*>(nseg_s + kKlCols);   // [h][col]: segment index of the cell
   float* xs_s = reinterpret_cast<float*>(kl_smem + kl_header_bytes(prm.max_h)) + (size_t)warp * 2 * prm.max_h * kKlCols;
   float* xt_s = xs_s + (size_t)prm.max_h * kKlCols;
 
-  // ---- once per CTA: owner strip; rows at which the owner of any column changes ("runs" of rows between them have
-  // one owner per column, so the per-channel sweeps need no per-row checks); any owned cell at all?
-  if (threadIdx.x == 0) strip_any = 0;
-  for (int h = threadIdx.x; h <= H; h += blockDim.x) run_s[h] = 0;
+  // ---- once per CTA: owner strip; any owned cell at all?  For the gradient: every column's cells are numbered by
+  // the box segment (maximal run of rows with one owner) they belong to, so that the per-channel gradient sweep is a
+  // plain loop over rows with kKlSegGroup accumulators and no ownership logic.
+  if (threadIdx.x == 0) { strip_any = 0; max_seg = 0; }
   __syncthreads();
   {
     bool any = false;
@@ -116,15 +122,17 @@ __global__ void __launch_bounds__(32 * kKlMaxWarps) dsgfd_kl_kernel(const __grid
   if (!strip_any) return;  // no box touches this strip: every column's KL is exactly 0
   const bool want_grad = !CELL && prm.grad_rows != nullptr;
   if (want_grad) {
-    for (int i = kKlCols + threadIdx.x; i < H * kKlCols; i += blockDim.x)
-      if (own_s[i] != own_s[i - kKlCols]) run_s[i / kKlCols] = 1;  // flag (same value from every writer); compacted below
-    __syncthreads();
-    if (threadIdx.x == 0) {  // run_s[0..n) = first rows of the runs, run_s[n] = H
-      int n = 0;
-      for (int h = 0; h < H; ++h)
-        if (h == 0 || run_s[h]) run_s[n++] = h;
-      run_s[n] = H;
-      num_runs = n;
+    if (threadIdx.x < kKlCols) {  // one thread per column walks its H rows
+      const int c = threadIdx.x;
+      int n = 0, prev = -1;
+      for (int h = 0; h < H; ++h) {
+        const int o = own_s[h * kKlCols + c];
+        if (o >= 0 && o != prev) seg_owner[c * prm.max_h + n++] = o;
+        slot_s[h * kKlCols + c] = (unsigned short)(o >= 0 ? n - 1 : 0xffff);
+        prev = o;
+      }
+      nseg_s[c] = n;
+      atomicMax(&max_seg, n);
     }
     __syncthreads();
   }
@@ -136,9 +144,6 @@ __global__ void __launch_bounds__(32 * kKlMaxWarps) dsgfd_kl_kernel(const __grid
   constexpr int kStep = kKlPhases * kKlCols;     // floats between two rows of the same lane
   const uint32_t xs_addr = (uint32_t)__cvta_generic_to_shared(xs_s) + (uint32_t)(ph * kRow + wl) * 4u;
   const uint32_t xt_addr = (uint32_t)__cvta_generic_to_shared(xt_s) + (uint32_t)(ph * kRow + wl) * 4u;
-  const int* own_l = own_s + wl;                 // own_l[h * kRow]
-  float* xs_l = xs_s + wl;
-  float* xt_l = xt_s + wl;
   auto phase_max = [](float v) {
 #pragma unroll
     for (int o = kKlCols; o < 32; o <<= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -160,41 +165,65 @@ __global__ void __launch_bounds__(32 * kKlMaxWarps) dsgfd_kl_kernel(const __grid
       const float m = CELL ? __ldg(prm.cell_weight + cell_base + (int64_t)h * W) : __ldg(prm.rows + (int64_t)o * C + c);
       return POW2 ? m * prm.inv_temperature : m;
     };
-    // ---- 0: owned cells -> shared memory asynchronously (every feature byte leaves HBM once), zeros elsewhere
+    // Lane-private views: row r of this lane is row ph + r * kKlPhases of the strip; consecutive rows of a lane are
+    // kStep floats apart, so the unrolled loops below address shared memory with immediate offsets.
+    const int nrl = (H - ph + kKlPhases - 1) / kKlPhases;
+    const int* oq0 = own_s + ph * kRow + wl;
+    float* xq0 = xs_s + ph * kRow + wl;
+    float* tq0 = xt_s + ph * kRow + wl;
+    // ---- 0: owned cells -> shared memory asynchronously (every feature byte leaves HBM once)
     {
-      const float* sp = S + (int64_t)ph * W;
-      const float* tp = T + (int64_t)ph * W;
+      const int* oq = oq0;
       uint32_t xa = xs_addr, ta = xt_addr;
-      for (int h = ph; h < H; h += kKlPhases, sp += kKlPhases * W, tp += kKlPhases * W, xa += kStep * 4u, ta += kStep * 4u) {
-        if (own_l[h * kRow] >= 0) {
-          cp_async_f32(xa, sp);
-          cp_async_f32(ta, tp);
-        } else {
-          xs_l[h * kRow] = 0.f;
-          xt_l[h * kRow] = 0.f;
+      unsigned goff = (unsigned)ph * (unsigned)W;
+      const unsigned gstep = (unsigned)kKlPhases * (unsigned)W;
+      int r = 0;
+      for (; r + 4 <= nrl; r += 4, oq += 4 * kStep, xa += 16u * kStep, ta += 16u * kStep, goff += 4u * gstep) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (oq[q * kStep] >= 0) {
+            cp_async_f32(xa + 4u * q * kStep, S + (goff + q * gstep));
+            cp_async_f32(ta + 4u * q * kStep, T + (goff + q * gstep));
+          }
+        }
+      }
+      for (; r < nrl; ++r, oq += kStep, xa += 4u * kStep, ta += 4u * kStep, goff += gstep) {
+        if (oq[0] >= 0) {
+          cp_async_f32(xa, S + goff);
+          cp_async_f32(ta, T + goff);
         }
       }
     }
     cp_async_wait_all();
     __syncwarp();
-    // ---- A: logits in place (0 outside boxes: a zero feature times a zero mask), column maxima
+    // ---- A: logits in place (exactly 0 outside boxes; those cells were never loaded), column maxima
     float ms = -INFINITY, mt = -INFINITY;
     {
       int prev = -2;
       float m = 0.f;
-      auto row = [&](int h) {
-        const int o = own_l[h * kRow];
+      const int* oq = oq0;
+      float* xq = xq0;
+      float* tq = tq0;
+      auto row = [&](int q, int h) {
+        const int o = oq[q * kStep];
         if (CELL ? (o >= 0) : (o != prev)) { m = mask_of(o, h); prev = o; }  // the mask is constant along a run of rows
-        float x = xs_l[h * kRow] * m, y = xt_l[h * kRow] * m;
-        if (!POW2) { x = __fdiv_rn(x, Temp); y = __fdiv_rn(y, Temp); }
-        xs_l[h * kRow] = x;
-        xt_l[h * kRow] = y;
+        float x = 0.f, y = 0.f;
+        if (o >= 0) {
+          x = xq[q * kStep] * m;
+          y = tq[q * kStep] * m;
+          if (!POW2) { x = __fdiv_rn(x, Temp); y = __fdiv_rn(y, Temp); }
+        }
+        xq[q * kStep] = x;
+        tq[q * kStep] = y;
         ms = fmaxf(ms, x);
         mt = fmaxf(mt, y);
       };
-      int h = ph;
-      for (; h + 3 * kKlPhases < H; h += 4 * kKlPhases) { row(h); row(h + kKlPhases); row(h + 2 * kKlPhases); row(h + 3 * kKlPhases); }
-      for (; h < H; h += kKlPhases) row(h);
+      int r = 0;
+      for (; r + 4 <= nrl; r += 4, oq += 4 * kStep, xq += 4 * kStep, tq += 4 * kStep) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) row(q, ph + (r + q) * kKlPhases);
+      }
+      for (; r < nrl; ++r, oq += kStep, xq += kStep, tq += kStep) row(0, ph + r * kKlPhases);
       ms = phase_max(ms);
       mt = phase_max(mt);
     }
@@ -202,21 +231,23 @@ __global__ void __launch_bounds__(32 * kKlMaxWarps) dsgfd_kl_kernel(const __grid
     const float nms = -ms * kLog2e, nmt = -mt * kLog2e;
     float ss[4] = {0.f, 0.f, 0.f, 0.f}, st4[4] = {0.f, 0.f, 0.f, 0.f}, ws[4] = {0.f, 0.f, 0.f, 0.f};
     {
-      int h = ph;
-      for (; h + 3 * kKlPhases < H; h += 4 * kKlPhases) {
+      const float* xq = xq0;
+      const float* tq = tq0;
+      int r = 0;
+      for (; r + 4 <= nrl; r += 4, xq += 4 * kStep, tq += 4 * kStep) {
         float a[4], b[4];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) { a[r] = xs_l[(h + r * kKlPhases) * kRow]; b[r] = xt_l[(h + r * kKlPhases) * kRow]; }
+        for (int q = 0; q < 4; ++q) { a[q] = xq[q * kStep]; b[q] = tq[q * kStep]; }
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const float ea = fast_ex2(fmaf(a[r], kLog2e, nms));
-          ss[r] += ea;
-          st4[r] += fast_ex2(fmaf(b[r], kLog2e, nmt));
-          ws[r] = fmaf(ea, a[r] - b[r], ws[r]);
+        for (int q = 0; q < 4; ++q) {
+          const float ea = fast_ex2(fmaf(a[q], kLog2e, nms));
+          ss[q] += ea;
+          st4[q] += fast_ex2(fmaf(b[q], kLog2e, nmt));
+          ws[q] = fmaf(ea, a[q] - b[q], ws[q]);
         }
       }
-      for (; h < H; h += kKlPhases) {
-        const float a = xs_l[h * kRow], b = xt_l[h * kRow];
+      for (; r < nrl; ++r, xq += kStep, tq += kStep) {
+        const float a = xq[0], b = tq[0];
         const float ea = fast_ex2(fmaf(a, kLog2e, nms));
         ss[0] += ea;
         st4[0] += fast_ex2(fmaf(b, kLog2e, nmt));
@@ -232,60 +263,57 @@ __global__ void __launch_bounds__(32 * kKlMaxWarps) dsgfd_kl_kernel(const __grid
       kl_total += (double)wsum / (double)sum_s - dl;
     }
 
-    // ---- C: d loss / d mask rows, one run of rows at a time; inside a run every column has a single owner, and
-    // columns without one hold zero logits, so their terms vanish without a test
+    // ---- C: d loss / d mask rows.  sum over a box segment of T_h (p_h - t_h) = (T/mask) sum xt_h (p_h - t_h); the cells
+    // carry their segment number, kKlSegGroup segments per column are accumulated per pass (one pass unless a column
+    // crosses more boxes), then the row phases are combined and one lane per column issues one red.global per segment.
     if (want_grad) {
       const float rs = __fdividef(1.f, sum_s), rt = __fdividef(1.f, sum_t);
-      const int nr = num_runs;
-      int cur = own_l[0], seg_h0 = 0;  // owner of this column in the current run, first row of its current box segment
-      float acc = 0.f;                 // sum over the segment so far of xt_h (p_h - t_h) = (mask/T) sum T_h (p_h - t_h)
-      for (int i = 0; i < nr; ++i) {
-        const int h0 = run_s[i], h1 = run_s[i + 1];
-        const int hb = h0 + ((ph - h0) & (kKlPhases - 1));  // first row of this lane's phase inside the run
-        float acc0 = 0.f, acc1 = 0.f;
-        int h = hb;
-        for (; h + kKlPhases < h1; h += 2 * kKlPhases) {
-          const float b0 = xt_l[h * kRow], a0 = xs_l[h * kRow], b1 = xt_l[(h + kKlPhases) * kRow], a1 = xs_l[(h + kKlPhases) * kRow];
-          const float p0 = fast_ex2(fmaf(b0, kLog2e, nmt)) * rt, t0 = fast_ex2(fmaf(a0, kLog2e, nms)) * rs;
-          const float p1 = fast_ex2(fmaf(b1, kLog2e, nmt)) * rt, t1 = fast_ex2(fmaf(a1, kLog2e, nms)) * rs;
-          acc0 = fmaf(b0, p0 - t0, acc0);
-          acc1 = fmaf(b1, p1 - t1, acc1);
+      const unsigned short* sq0 = slot_s + ph * kRow + wl;
+      const int my_nseg = nseg_s[wl];
+      for (int base = 0; base < max_seg; base += kKlSegGroup) {
+        float acc[kKlSegGroup];
+#pragma unroll
+        for (int k = 0; k < kKlSegGroup; ++k) acc[k] = 0.f;
+        const float* xq = xq0;
+        const float* tq = tq0;
+        const unsigned short* sq = sq0;
+        auto row = [&](int q) {
+          const float a = xq[q * kStep], b = tq[q * kStep];
+          const int sl = (int)sq[q * kStep] - base;
+          const float v = b * (fast_ex2(fmaf(b, kLog2e, nmt)) * rt - fast_ex2(fmaf(a, kLog2e, nms)) * rs);
+#pragma unroll
+          for (int k = 0; k < kKlSegGroup; ++k) acc[k] += (sl == k) ? v : 0.f;
+        };
+        int r = 0;
+        for (; r + 4 <= nrl; r += 4, xq += 4 * kStep, tq += 4 * kStep, sq += 4 * kStep) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) row(q);
         }
-        if (h < h1) {
-          const float b0 = xt_l[h * kRow], a0 = xs_l[h * kRow];
-          acc0 = fmaf(b0, fast_ex2(fmaf(b0, kLog2e, nmt)) * rt - fast_ex2(fmaf(a0, kLog2e, nms)) * rs, acc0);
-        }
-        acc += acc0 + acc1;
-        // a column flushes its sum when its box ends (its owner differs in the next run); the lanes of one box flush together
-        const int nxt = (i + 1 < nr) ? own_l[h1 * kRow] : -1;
-        const bool need = (nxt != cur) && (cur >= 0);
-        unsigned pending = __ballot_sync(0xffffffffu, need);
-        while (pending) {
-          const int leader = __ffs(pending) - 1;
-          const int who = __shfl_sync(0xffffffffu, cur, leader);
-          const bool mine = need && cur == who;
-          const unsigned same = __ballot_sync(0xffffffffu, mine);
-          const float m = mask_of(who, 0);  // warp-uniform
-          float v = mine ? acc : 0.f;
-          if (m == 0.f) {
-            // the mask value underflowed to 0: the logits carry no trace of the teacher feature, re-read it
-            v = 0.f;
-            if (mine)
-              for (int r = seg_h0 + ((ph - seg_h0) & (kKlPhases - 1)); r < h1; r += kKlPhases) {
-                const float pp = fast_ex2(fmaf(xt_l[r * kRow], kLog2e, nmt)) * rt;
-                const float tt = fast_ex2(fmaf(xs_l[r * kRow], kLog2e, nms)) * rs;
-                v = fmaf(ld_stream_f1(T + (int64_t)r * W), pp - tt, v);
+        for (; r < nrl; ++r, xq += kStep, tq += kStep, sq += kStep) row(0);
+#pragma unroll
+        for (int k = 0; k < kKlSegGroup; ++k) acc[k] = phase_sum(acc[k]);
+        if (ph == 0) {
+#pragma unroll
+          for (int k = 0; k < kKlSegGroup; ++k) {
+            if (base + k >= my_nseg) continue;
+            const int who = seg_owner[wl * prm.max_h + base + k];
+            const float m = mask_of(who, 0);
+            float v = acc[k];
+            float div = POW2 ? m : m / Temp;
+            if (m == 0.f) {
+              // the mask value underflowed to 0: the logits carry no trace of the teacher feature, re-read it
+              v = 0.f;
+              div = 1.f;
+              for (int h = 0; h < H; ++h) {
+                if ((int)slot_s[h * kRow + wl] != base + k) continue;
+                const float pp = fast_ex2(fmaf(xt_s[h * kRow + wl], kLog2e, nmt)) * rt;
+                const float tt = fast_ex2(fmaf(xs_s[h * kRow + wl], kLog2e, nms)) * rs;
+                v = fmaf(ld_stream_f1(T + (int64_t)h * W), pp - tt, v);
               }
-          }
-          v = warp_sum(v);
-          if (lane == leader) {
-            const float div = (m == 0.f) ? 1.f : (POW2 ? m : m / Temp);
+            }
             atomicAdd(prm.grad_rows + (int64_t)who * C + c, __fdividef(gcoef * v, div));
           }
-          pending &= ~same;
         }
-        if (nxt != cur) { acc = 0.f; seg_h0 = h1; }
-        cur = nxt;
       }
     }
     __syncwarp();

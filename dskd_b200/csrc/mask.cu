@@ -209,6 +209,199 @@ __global__ void __launch_bounds__(256) raster_kernel(const float* __restrict__ b
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// decode_v1 in three launches instead of eight.  The step is latency-bound outside its streaming kernel: every
+// dependent launch of a captured graph costs 2-3 us, and matched ids -> mask rows -> raster (+ two memsets) and
+// row finish -> loss conversion were eight of them.
+//
+// prepare_v1_kernel, one 1-D grid with three CTA roles:
+//   [0, raster_ctas)            owner raster of one 256-cell tile of one image (as raster_kernel<OWNER_EXCL>)
+//   [.., + num_pairs)           pair p: finds ITS matched student query -- the p-th query in ascending order whose
+//                               label is a previous-task label (head_il.py:1453-1455, :672) -- by a block-wide rank
+//                               search over the labels, writes ids[p], the mask row softmax_c|hs_T - hs_S|, and clears
+//                               its row of the energy table
+//   [.., + zero_ctas)           clears grad_hs_student, the loss accumulator and the finish counter
+// ------------------------------------------------------------------------------------------------
+struct PrepareV1Params {
+  RasterParams raster;
+  int raster_tiles, raster_ctas, num_pairs, zero_ctas;
+  int N, C, num_rows, num_classes;
+  int64_t cells_per_image;
+  const float* boxes; const int* box_start; const int* img_hw;
+  const float* hs_t; const float* hs_s; const int64_t* keepid; const int64_t* labels; const uint8_t* prev_mask;
+  int* owner; float* rows; float* energy; int64_t* ids; int* matched_count;
+  float* grad_hs; int64_t grad_hs_floats; double* acc; unsigned* counter;
+};
+
+__global__ void __launch_bounds__(256) prepare_v1_kernel(const __grid_constant__ PrepareV1Params p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ float red[32];
+  __shared__ int s_scan[8];
+  __shared__ int s_id, s_total;
+  __shared__ float bcast;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int b = blockIdx.x;
+  if (b < p.raster_ctas) {
+    // ---- owner raster: last box (highest pair index) whose half-open rectangle holds the cell (head_il.py:706)
+    Rect* rects = reinterpret_cast<Rect*>(smem_raw);
+    const int i = b / p.raster_tiles, tile = b - i * p.raster_tiles;
+    const int b0 = p.box_start[i], nb = p.box_start[i + 1] - b0;
+    const int img_h = p.img_hw[2 * i], img_w = p.img_hw[2 * i + 1];
+    for (int k = tid; k < nb * p.raster.num_levels; k += blockDim.x) {
+      const int l = k / nb, j = k - l * nb;
+      rects[k] = make_rect(p.boxes + (int64_t)(b0 + j) * 4, img_h, img_w, p.raster.levels[l].H, p.raster.levels[l].W, false);
+    }
+    __syncthreads();
+    const int64_t cell = (int64_t)tile * blockDim.x + tid;
+    if (cell >= p.cells_per_image) return;
+    int l = 0;
+#pragma unroll
+    for (int k = 1; k < DSKD_MAX_LEVELS; ++k)
+      if (k < p.raster.num_levels && cell >= p.raster.levels[k].cell_offset) l = k;
+    const int W = p.raster.levels[l].W;
+    const int local = (int)(cell - p.raster.levels[l].cell_offset);
+    const int h = local / W, w = local - h * W;
+    const Rect* R = rects + l * nb;
+    int owner = -1;
+    for (int j = nb - 1; j >= 0; --j) {
+      const Rect r = R[j];
+      if (h >= r.hmin && h < r.hmax && w >= r.wmin && w < r.wmax) { owner = b0 + j; break; }
+    }
+    p.owner[(int64_t)i * p.cells_per_image + cell] = owner;
+    return;
+  }
+  b -= p.raster_ctas;
+  if (b < p.num_pairs) {
+    // ---- pair b: rank search for the b-th previous-labelled query
+    const int n = p.num_rows;
+    const int per = (n + (int)blockDim.x - 1) / (int)blockDim.x;
+    const int lo = min(n, tid * per), hi = min(n, lo + per);
+    auto hit = [&](int q) {
+      const int64_t lab = p.labels[q];
+      return lab >= 0 && lab < p.num_classes && p.prev_mask[lab] != 0;
+    };
+    int c = 0;
+    for (int q = lo; q < hi; ++q) c += hit(q) ? 1 : 0;
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_scan[warp] = incl;
+    if (tid == 0) s_id = 0;
+    __syncthreads();
+    int before = 0;
+    for (int wv = 0; wv < warp; ++wv) before += s_scan[wv];
+    const int excl = before + incl - c;
+    if (b >= excl && b < excl + c) {
+      int need = b - excl;
+      for (int q = lo; q < hi; ++q)
+        if (hit(q) && need-- == 0) { s_id = q; break; }
+    }
+    if (tid == (int)blockDim.x - 1) s_total = excl + c;
+    __syncthreads();
+    const int id_pred = s_id;  // 0 when fewer than b+1 queries carry a previous label (the reference raises, :705)
+    if (tid == 0) {
+      p.ids[b] = id_pred;
+      if (b == 0 && p.matched_count) *p.matched_count = s_total;
+    }
+    // ---- mask row b = softmax_c |hs_T[keepid[b]] - hs_S[id_pred]| (head_il.py:705-706); energy row cleared
+    float* a = reinterpret_cast<float*>(smem_raw);
+    const int C = p.C;
+    const float* t = p.hs_t + p.keepid[b] * (int64_t)C;
+    const float* sv = p.hs_s + (int64_t)id_pred * C;
+    float mx = -INFINITY;
+    for (int ch = tid; ch < C; ch += blockDim.x) {
+      const float v = fabsf(t[ch] - sv[ch]);
+      a[ch] = v;
+      mx = fmaxf(mx, v);
+      p.energy[(int64_t)b * C + ch] = 0.f;
+    }
+    mx = warp_max(mx);
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    if (tid == 0) {
+      float m = red[0];
+      for (int wv = 1; wv < ((int)blockDim.x >> 5); ++wv) m = fmaxf(m, red[wv]);
+      bcast = m;
+    }
+    __syncthreads();
+    mx = bcast;
+    float sum = 0.f;
+    for (int ch = tid; ch < C; ch += blockDim.x) {
+      const float e = expf(a[ch] - mx);
+      a[ch] = e;
+      sum += e;
+    }
+    __syncthreads();
+    sum = block_sum(sum, red);
+    if (tid == 0) bcast = sum;
+    __syncthreads();
+    sum = bcast;
+    for (int ch = tid; ch < C; ch += blockDim.x) p.rows[(int64_t)b * C + ch] = a[ch] / sum;
+    return;
+  }
+  b -= p.num_pairs;
+  // ---- clears
+  if (b == 0 && tid == 0) { *p.acc = 0.0; *p.counter = 0u; }
+  if (p.grad_hs != nullptr) {
+    const int64_t n4 = p.grad_hs_floats >> 2;
+    float4* g4 = reinterpret_cast<float4*>(p.grad_hs);
+    for (int64_t i = (int64_t)b * blockDim.x + tid; i < n4; i += (int64_t)p.zero_ctas * blockDim.x)
+      g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (b == 0 && tid < (int)(p.grad_hs_floats & 3)) p.grad_hs[(n4 << 2) + tid] = 0.f;
+  }
+}
+
+// rows_finish_kernel<true> whose last CTA also converts the accumulated loss: loss[0] = (float) sum.
+__global__ void __launch_bounds__(128) rows_finish_final_kernel(const float* __restrict__ hs_t, const float* __restrict__ hs_s,
+                                                                const int64_t* __restrict__ id_soft,
+                                                                const int64_t* __restrict__ id_pred,
+                                                                const float* __restrict__ rows, const float* __restrict__ eg,
+                                                                int C, double* __restrict__ loss_acc, unsigned* __restrict__ counter,
+                                                                float* __restrict__ loss, float* __restrict__ grad_hs_s) {
+  __shared__ float red[32];
+  __shared__ double dred[32];
+  __shared__ float bcast;
+  const int p = blockIdx.x;
+  const float* A = rows + (int64_t)p * C;
+  const float* E = eg + (int64_t)p * C;
+  float dot = 0.f;
+  double part = 0.0;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float a = A[c], e = E[c];
+    part += (double)a * (double)a * (double)e;
+    dot += a * (2.f * a * e);
+  }
+  part = block_sum(part, dred);
+  if (grad_hs_s != nullptr) {
+    dot = block_sum(dot, red);
+    if (threadIdx.x == 0) bcast = dot;
+    __syncthreads();
+    dot = bcast;
+    const int64_t qs = id_pred[p];
+    const float* t = hs_t + id_soft[p] * (int64_t)C;
+    const float* sv = hs_s + qs * (int64_t)C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const float a = A[c], e = E[c];
+      const float da = a * (2.f * a * e - dot);
+      const float delta = t[c] - sv[c];
+      const float sgn = (delta > 0.f) ? 1.f : ((delta < 0.f) ? -1.f : 0.f);
+      atomicAdd(grad_hs_s + qs * (int64_t)C + c, -sgn * da);
+    }
+  }
+  if (threadIdx.x == 0) {
+    if (part != 0.0) atomicAdd(loss_acc, part);
+    __threadfence();
+    if (atomicAdd(counter, 1u) == gridDim.x - 1) {  // last pair: every partial sum is in
+      __threadfence();
+      loss[0] = (float)(*reinterpret_cast<volatile double*>(loss_acc));
+    }
+  }
+}
+
 }  // namespace dskd
 
 using namespace dskd;
@@ -311,3 +504,44 @@ extern "C" int dskd_raster_cells(int32_t mode, const float* d_boxes, const int32
   DSKD_LAUNCH_OK("raster_kernel");
   return DSKD_OK;
 }
+
+
+// Internal to the library (used by dskd_dsgfd_step): the fused decode_v1 prologue / epilogue.
+namespace dskd {
+int launch_prepare_v1(const DskdDsgfdStepArgs* a, int* owner, float* rows, float* energy, int64_t* ids, double* acc,
+                      unsigned* counter, cudaStream_t st) {
+  PrepareV1Params p;
+  memset(&p, 0, sizeof(p));
+  p.raster.num_levels = a->num_levels;
+  for (int l = 0; l < a->num_levels; ++l) p.raster.levels[l] = a->levels[l];
+  p.raster_tiles = (int)ceil_div(a->cells_per_image, 256);
+  p.raster_ctas = p.raster_tiles * a->N;
+  p.num_pairs = a->num_pairs;
+  p.N = a->N; p.C = a->C; p.num_rows = a->num_query_rows; p.num_classes = a->num_classes;
+  p.cells_per_image = a->cells_per_image;
+  p.boxes = a->d_boxes; p.box_start = a->d_box_start; p.img_hw = a->d_img_hw;
+  p.hs_t = a->d_hs_teacher; p.hs_s = a->d_hs_student; p.keepid = a->d_teacher_keepid;
+  p.labels = a->d_student_labels; p.prev_mask = a->d_prev_mask;
+  p.owner = owner; p.rows = rows; p.energy = energy; p.ids = ids; p.matched_count = a->d_matched_count;
+  p.grad_hs = a->d_grad_hs_student;
+  p.grad_hs_floats = a->d_grad_hs_student ? (int64_t)a->num_query_rows * a->C : 0;
+  p.acc = acc; p.counter = counter;
+  p.zero_ctas = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(p.grad_hs_floats, 256 * 16), 2 * kNumSMs));
+  const size_t smem = std::max((size_t)a->max_boxes_per_image * a->num_levels * sizeof(Rect), (size_t)a->C * sizeof(float));
+  DSKD_REQUIRE(smem <= 200 * 1024, "dskd_dsgfd_step: too many boxes per image (%d)", a->max_boxes_per_image);
+  DSKD_REQUIRE(a->d_grad_hs_student == nullptr || aligned16(a->d_grad_hs_student), "dskd_dsgfd_step: d_grad_hs_student must be 16-byte aligned");
+  if (smem > 48 * 1024)
+    DSKD_CUDA_OK(cudaFuncSetAttribute(prepare_v1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  prepare_v1_kernel<<<p.raster_ctas + p.num_pairs + p.zero_ctas, 256, smem, st>>>(p);
+  DSKD_LAUNCH_OK("prepare_v1_kernel");
+  return DSKD_OK;
+}
+
+int launch_rows_finish_final(const DskdDsgfdStepArgs* a, const float* rows, const float* energy, const int64_t* ids,
+                             double* acc, unsigned* counter, float* grad_hs, cudaStream_t st) {
+  rows_finish_final_kernel<<<a->num_pairs, 128, 0, st>>>(a->d_hs_teacher, a->d_hs_student, a->d_teacher_keepid, ids, rows,
+                                                         energy, a->C, acc, counter, a->d_loss, grad_hs);
+  DSKD_LAUNCH_OK("rows_finish_final_kernel");
+  return DSKD_OK;
+}
+}  // namespace dskd

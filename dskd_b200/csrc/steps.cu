@@ -4,6 +4,13 @@
 
 using namespace dskd;
 
+namespace dskd {
+int launch_prepare_v1(const DskdDsgfdStepArgs* a, int* owner, float* rows, float* energy, int64_t* ids, double* acc,
+                      unsigned* counter, cudaStream_t st);
+int launch_rows_finish_final(const DskdDsgfdStepArgs* a, const float* rows, const float* energy, const int64_t* ids,
+                             double* acc, unsigned* counter, float* grad_hs, cudaStream_t st);
+}  // namespace dskd
+
 namespace {
 // Timing events survive CUDA-graph capture as external event-record nodes.
 cudaError_t record_event(void* ev, cudaStream_t st) {
@@ -23,7 +30,7 @@ struct Workspace {
     cell_map = off; off += align_up((int64_t)N * cells * 4);
     rows = off;     off += align_up((int64_t)std::max(P, 1) * C * 4);
     energy = off;   off += align_up((int64_t)std::max(P, 1) * C * 4);
-    acc = off;      off += align_up(8);       // right after energy: one memset clears both
+    acc = off;      off += align_up(16);      // right after energy: one memset clears both; [8] = finish counter
     ids = off;      off += align_up((int64_t)std::max(P, 1) * 8);
     total = off;
   }
@@ -61,13 +68,26 @@ extern "C" int dskd_dsgfd_step(const DskdDsgfdStepArgs* a, void* stream) {
     DSKD_CUDA_OK(cudaMemsetAsync(a->d_loss, 0, sizeof(float), st));
     return DSKD_OK;
   }
-  // energy (or KL grad_rows) + loss accumulator: one clear
-  DSKD_CUDA_OK(cudaMemsetAsync(energy, 0, (size_t)(ws.acc + 8 - ws.energy), st));
   const bool want_hs = v1 && a->d_grad_hs_student != nullptr;
-  if (a->d_grad_hs_student != nullptr)
-    DSKD_CUDA_OK(cudaMemsetAsync(a->d_grad_hs_student, 0, sizeof(float) * (size_t)a->num_query_rows * a->C, st));
+  unsigned* counter = reinterpret_cast<unsigned*>(base + ws.acc + 8);
+  // decode_v1 with at least one pair: matched ids, mask rows, owner raster and every clear in ONE launch
+  const bool fused_v1 = v1 && P > 0;
   int rc;
-  if (row_mode) {
+  if (fused_v1) {
+    DSKD_REQUIRE(a->d_hs_teacher && a->d_teacher_keepid && a->d_hs_student && a->d_student_labels && a->d_prev_mask &&
+                     a->d_boxes && a->d_box_start && a->d_img_hw,
+                 "dskd_dsgfd_step: decode_v1 needs embeddings, keep-ids, labels and boxes");
+    rc = launch_prepare_v1(a, static_cast<int*>(cell_map), rows, energy, ids, acc, counter, st);
+    if (rc) return rc;
+  } else {
+    // energy (or KL grad_rows) + loss accumulator + counter: one clear
+    DSKD_CUDA_OK(cudaMemsetAsync(energy, 0, (size_t)(ws.acc + 16 - ws.energy), st));
+    if (a->d_grad_hs_student != nullptr)
+      DSKD_CUDA_OK(cudaMemsetAsync(a->d_grad_hs_student, 0, sizeof(float) * (size_t)a->num_query_rows * a->C, st));
+  }
+  if (fused_v1) {
+    // nothing else to prepare
+  } else if (row_mode) {
     DSKD_REQUIRE(a->d_hs_teacher && (P == 0 || a->d_teacher_keepid), "dskd_dsgfd_step: decode_* needs teacher embeddings / keep-ids");
     if (v1) {
       DSKD_REQUIRE(a->d_hs_student && a->d_student_labels && a->d_prev_mask, "dskd_dsgfd_step: decode_v1 needs the student side");
@@ -127,6 +147,8 @@ extern "C" int dskd_dsgfd_step(const DskdDsgfdStepArgs* a, void* stream) {
     if (rc) return rc;
   }
   if (a->ev_kernel_end) DSKD_CUDA_OK(record_event(a->ev_kernel_end, st));
+  if (fused_v1 && a->criterion == DSKD_CRIT_MSE)  // row finish whose last CTA also writes the loss
+    return launch_rows_finish_final(a, rows, energy, ids, acc, counter, want_hs ? a->d_grad_hs_student : nullptr, st);
   if (row_mode) {
     rc = dskd_dsgfd_rows_finish(a->criterion, a->d_hs_teacher, a->d_hs_student, a->d_teacher_keepid, ids, rows, energy, P,
                                 a->C, acc, want_hs ? a->d_grad_hs_student : nullptr, stream);

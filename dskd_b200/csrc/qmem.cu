@@ -225,8 +225,8 @@ qmem_weight_kernel(const __grid_constant__ CUtensorMap tmap_mem, const __grid_co
   const uint32_t q_slab_bytes = (uint32_t)p.NB * 128u;
   const uint32_t smem_q = smem_base;
   const uint32_t smem_a = smem_q + (uint32_t)num_slabs * q_slab_bytes;
-  const int kAStages = p.stages;
-  const uint32_t bars = smem_a + kAStages * kAStageBytes;
+  const int num_stages = p.stages;
+  const uint32_t bars = smem_a + num_stages * kAStageBytes;
   // barrier slots (8 bytes each)
   const uint32_t bar_full = bars, bar_empty = bars + 8 * kMaxAStages, bar_qfull = bars + 16 * kMaxAStages,
                  bar_qempty = bar_qfull + 8, bar_accfull = bar_qfull + 16, bar_accempty = bar_accfull + 8 * kAccStages,
@@ -239,7 +239,7 @@ qmem_weight_kernel(const __grid_constant__ CUtensorMap tmap_mem, const __grid_co
   const long long t_begin = g * p.total_tiles / G, t_end = (g + 1) * p.total_tiles / G;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kAStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (int s = 0; s < num_stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
     mbar_init(bar_qfull, 1);
     mbar_init(bar_qempty, 1);
     for (int s = 0; s < kAccStages; ++s) { mbar_init(bar_accfull + 8 * s, 1); mbar_init(bar_accempty + 8 * s, 4); }
@@ -273,7 +273,7 @@ qmem_weight_kernel(const __grid_constant__ CUtensorMap tmap_mem, const __grid_co
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           mbar_arrive_expect_tx(bar_full + 8 * stage, kAStageBytes);
           tma_load_3d(&tmap_mem, bar_full + 8 * stage, smem_a + stage * kAStageBytes, ks * kSlabCh, img, tt * kTokTile);
-          if (++stage == kAStages) { stage = 0; phase ^= 1; }
+          if (++stage == num_stages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -300,7 +300,7 @@ qmem_weight_kernel(const __grid_constant__ CUtensorMap tmap_mem, const __grid_co
           for (int kk = 0; kk < kSlabCh / 8; ++kk)  // 8 tf32 = 32 bytes along K per instruction: +2 in 16-byte units
             umma_tf32(tmem_d, da + 2 * kk, db + 2 * kk, idesc, (ks | kk) ? 1u : 0u);
           umma_commit(bar_empty + 8 * stage);  // frees the memory-tile stage when those MMAs retire
-          if (++stage == kAStages) { stage = 0; phase ^= 1; }
+          if (++stage == num_stages) { stage = 0; phase ^= 1; }
         }
         umma_commit(bar_accfull + 8 * acc);  // accumulator ready for the epilogue
         const bool last_of_image = (t + 1 == t_end) || ((int)((t + 1) / p.tiles_per_image) != img);
@@ -378,8 +378,8 @@ qmem_weight_pair_kernel(const __grid_constant__ CUtensorMap tmap_mem, const __gr
   const uint32_t q_slab_bytes = (uint32_t)half * 128u;
   const uint32_t smem_q = smem_base;
   const uint32_t smem_a = smem_q + (uint32_t)num_slabs * q_slab_bytes;
-  const int kAStages = p.stages;
-  const uint32_t bars = smem_a + kAStages * kAStageBytes;
+  const int num_stages = p.stages;
+  const uint32_t bars = smem_a + num_stages * kAStageBytes;
   const uint32_t bar_full = bars, bar_empty = bars + 8 * kMaxAStages, bar_qfull = bars + 16 * kMaxAStages,
                  bar_qempty = bar_qfull + 8, bar_accfull = bar_qfull + 16, bar_accempty = bar_qfull + 24,
                  tmem_slot = bar_qfull + 32;
@@ -394,7 +394,7 @@ qmem_weight_pair_kernel(const __grid_constant__ CUtensorMap tmap_mem, const __gr
   const long long t_begin = g * p.total_tiles / G, t_end = (g + 1) * p.total_tiles / G;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kAStages; ++s) { mbar_init(bar_full + 8 * s, 2); mbar_init(bar_empty + 8 * s, 1); }
+    for (int s = 0; s < num_stages; ++s) { mbar_init(bar_full + 8 * s, 2); mbar_init(bar_empty + 8 * s, 1); }
     mbar_init(bar_qfull, 2);
     mbar_init(bar_qempty, 1);
     mbar_init(bar_accfull, 1);
@@ -433,7 +433,7 @@ qmem_weight_pair_kernel(const __grid_constant__ CUtensorMap tmap_mem, const __gr
           else mbar_arrive_cluster(bar_full + 8 * stage, 0);
           tma_load_3d_pair(&tmap_mem, bar_full + 8 * stage, smem_a + stage * kAStageBytes, ks * kSlabCh, img,
                            tt * 2 * kTokTile + (int)rank * kTokTile);
-          if (++stage == kAStages) { stage = 0; phase ^= 1; }
+          if (++stage == num_stages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -465,7 +465,7 @@ qmem_weight_pair_kernel(const __grid_constant__ CUtensorMap tmap_mem, const __gr
             if (p.n_hi) umma_tf32_pair(tmem_base + p.n_lo, da + 2 * kk, dbh + 2 * kk, idesc_hi, (ks | kk) ? 1u : 0u);
           }
           umma_commit_pair(bar_empty + 8 * stage);
-          if (++stage == kAStages) { stage = 0; phase ^= 1; }
+          if (++stage == num_stages) { stage = 0; phase ^= 1; }
         }
         umma_commit_pair(bar_accfull);
         const bool last_of_image = (t + 1 == t_end) || ((int)((t + 1) / p.tiles_per_image) != img);

@@ -499,3 +499,65 @@ def test_full_size_properties_batch16():
     torch.testing.assert_close(inner, 2.0 * loss.detach().double(), rtol=1e-5, atol=0)
     frac = sum(int((f.grad != 0).sum()) for f in feats) / sum(f.numel() for f in feats)
     assert 0.05 < frac < 0.95
+
+
+# ------------------------------------------------------------------ stress: maximum detections, degenerate boxes
+def _degenerate_case():
+    """100 teacher detections per image (the `max_per_img` of teacher_test_cfg), heavy overlap, and every kind of
+    degenerate rectangle the slice arithmetic of head_il.py:688-706 can meet: zero width / height (empty slice),
+    sub-cell boxes, boxes on the image border, exact duplicates, and a teacher query kept twice (two classes above
+    the score threshold: `filter_scores_and_topk` keeps (query, class) pairs)."""
+    cpu = synth.make_distill_inputs(num_images=2, num_prev=40, seed=77, levels=((25, 42), (13, 21), (7, 11), (4, 6)),
+                                    img_hw=(200, 333), num_query=300, channels=64, boxes_per_image=100)
+    a = cpu.assignments
+    h, w = 200.0, 333.0
+    for i in range(2):
+        b = a['teacher_bboxes'][i]
+        b[0] = torch.tensor([10.0, 20.0, 10.0, 90.0])          # zero width, integer edge: empty slice
+        b[1] = torch.tensor([16.0, 30.0, 80.0, 30.0])          # zero height on a cell edge
+        b[2] = torch.tensor([50.3, 60.2, 50.9, 60.7])          # inside one cell
+        b[3] = torch.tensor([0.0, 0.0, w, h])                  # the whole image
+        b[4] = torch.tensor([w - 1.0, h - 1.0, w, h])          # last cell, touching the border
+        b[5] = b[6].clone()                                    # exact duplicate of a later box
+        b[7] = torch.tensor([0.0, 0.0, 0.5, 0.5])              # first cell
+    keep = a['teacher_keepid'].clone()
+    keep[1] = keep[0]                                          # the same teacher query kept twice
+    a['teacher_keepid'] = keep
+    return cpu
+
+
+@pytest.mark.parametrize('crit', ['mse', 'kl'])
+def test_max_detections_and_degenerate_boxes(crit):
+    cpu = _degenerate_case()
+    gpu = cpu.to(DEV)
+    mod = dskd_b200.DSGFeatureDistillLoss(criterion=crit, validate=True)
+    feats, hs = gpu.clone_student()
+    loss = mod(feats, gpu.teacher_feats, (hs, gpu.hs_teacher), gpu.assignments)
+    loss.backward()
+    o_feats, o_hs = cpu.clone_student()
+    ref = oracle_decode(cpu, crit_oracle(crit), 1, o_feats, o_hs)
+    ref.backward()
+    if crit == 'kl':
+        assert_kl_loss(loss, cpu, crit_oracle(crit), ref)
+    else:
+        assert_loss(loss, ref)
+        for got, want in zip(feats, o_feats):
+            assert_grad(got.grad, want.grad)
+    assert_grad(hs.grad, o_hs.grad)
+
+
+def test_max_detections_bcdd_with_duplicate_teacher_query():
+    cpu = _degenerate_case()
+    gpu = cpu.to(DEV)
+    a = cpu.assignments
+    _, hs = gpu.clone_student()
+    mod = dskd_b200.BetweenClassDistanceLoss()
+    loss = mod(None, None, (hs, gpu.hs_teacher), gpu.assignments)
+    loss.backward()
+    _, o_hs = cpu.clone_student()
+    C = o_hs.shape[-1]
+    ref = ob.bcdd_loss(o_hs.reshape(-1, C), a['student_labels'], cpu.hs_teacher.reshape(-1, C), a['teacher_keepid'],
+                       a['teacher_labels'], a['prev_labels'], ol.MSELoss('mean', 1.0))
+    ref.backward()
+    assert_loss(loss, ref)
+    assert_grad(hs.grad, o_hs.grad)

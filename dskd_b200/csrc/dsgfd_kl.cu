@@ -12,27 +12,26 @@ namespace dskd {
 // Strip kernel.  A CTA owns one strip = (level, image, kKlCols consecutive w) x all H rows and a chunk of channels; each
 // of its warps walks kKlChan channels one after the other; the 32 lanes are kKlCols columns x kKlPhases row phases (a
 // lane takes every kKlPhases-th row of its column; narrow strips keep the shared-memory footprint per warp small enough
-// for 16 resident warps per SM).  Per channel the warp
-//   0. cp.async's the owned cells of the student / teacher strip [H][32] into ITS shared-memory buffers (every
-//      feature byte is read from HBM exactly once; ~200 independent 128-byte copies in flight per warp),
-//   A. turns them in place into the logits x = feature * mask / T (0 outside boxes) and takes the column maxima,
+// for 32 resident warps per SM).  Once per CTA every column is cut into SEGMENTS, the maximal runs of rows with one
+// owning box; all per-channel work is a loop over the segments of the lane's column, so only rows inside boxes are
+// loaded or visited (the others have logit 0 in both softmaxes and enter in closed form), the mask value is a
+// per-segment constant and the inner loops are branch-free.  Per channel the warp
+//   0. cp.async's the segment rows of the student / teacher strip into ITS shared-memory buffers (every feature byte
+//      is read from HBM exactly once),
+//   A. turns them in place into the logits x = feature * mask / T and takes the column maxima,
 //   B. sums e^(x - max) for both softmaxes and sum e^(xs - max) (xs - xt) -- the KL of a column needs nothing else:
 //        KL = sum_h t_h (xs_h - xt_h) - (lse_s - lse_t),
-//   C. (only when the mask rows need a gradient) accumulates T_h * (p_h - t_h) per box segment of each column and
-//      issues one red.global per (column, segment, channel).
-// The owner strip and the segment number of every cell are computed once per CTA and shared by all its channels, so
-// the gradient sweep carries no ownership logic.
+//   C. (only when the mask rows need a gradient) accumulates T_h * (p_h - t_h) over each segment and issues one
+//      red.global per (column, segment, channel).
 constexpr int kKlChan = 4;        // channels per warp (sequential)
 constexpr int kKlCols = 8;        // columns (w) per strip: a warp covers kKlCols columns x kKlPhases interleaved row phases
 constexpr int kKlPhases = 32 / kKlCols;
 constexpr int kKlMaxWarps = 32;   // warps per CTA
 constexpr int kKlMaxH = 800;      // rows per level the shared-memory strips can hold (one warp per CTA at the limit)
 constexpr size_t kKlSmemBudget = 220 * 1024;
-constexpr int kKlSegGroup = 4;    // box segments of a column accumulated per pass of the gradient sweep
 __host__ __device__ inline size_t kl_header_bytes(int max_h) {
-  // owner strip int32 [max_h][kKlCols] | segment owners int32 [kKlCols][max_h] | segments per column int32 [kKlCols]
-  // | segment slot of every cell uint16 [max_h][kKlCols]
-  return ((size_t)max_h * kKlCols * 4 * 2 + (size_t)kKlCols * 4 + (size_t)max_h * kKlCols * 2 + 127) / 128 * 128;
+  // owner strip + first row / end row / owner of every segment: 4 x int32 [max_h][kKlCols]; 2 x int32 [kKlCols] counters
+  return ((size_t)max_h * kKlCols * 4 * 4 + (size_t)kKlCols * 4 * 2 + 127) / 128 * 128;
 }
 
 struct KlParams {
@@ -85,23 +84,24 @@ __global__ void __launch_bounds__(32 * kKlMaxWarps) dsgfd_kl_kernel(const __grid
   const int wt = idx % prm.wtiles[lvl];
   const int img = idx / prm.wtiles[lvl];
   const int w = wt * kKlCols + wl;
-  const bool col_ok = w < W;
   const float Temp = prm.temperature;
   const float scale = prm.scale[lvl];
   const int64_t strip_base = (int64_t)img * prm.cells_per_image + prm.levels[lvl].cell_offset + wt * kKlCols;
   const int64_t cell_base = strip_base + wl;
 
-  // shared memory: header (owner strip, segment tables; kl_header_bytes) | per warp: xs, xt [max_h][kKlCols]
-  int* own_s = reinterpret_cast<int*>(kl_smem);
-  int* seg_owner = own_s + (size_t)prm.max_h * kKlCols;          // [col][k]: owner of the k-th box segment of the column
-  int* nseg_s = seg_owner + (size_t)prm.max_h * kKlCols;         // [col]
-  unsigned short* slot_s = reinterpret_cast<unsigned short*>(nseg_s + kKlCols);   // [h][col]: segment index of the cell
-  float* xs_s = reinterpret_cast<float*>(kl_smem + kl_header_bytes(prm.max_h)) + (size_t)warp * 2 * prm.max_h * kKlCols;
-  float* xt_s = xs_s + (size_t)prm.max_h * kKlCols;
+  // shared memory header (kl_header_bytes): the segment tables of the strip; then per warp the xs / xt strips
+  const int mh = prm.max_h;
+  int* own_s = reinterpret_cast<int*>(kl_smem);     // [h][col] owner strip (setup only)
+  int* seg_h0 = own_s + (size_t)mh * kKlCols;       // [col][k] first row of the k-th segment of the column
+  int* seg_h1 = seg_h0 + (size_t)mh * kKlCols;      // [col][k] one past its last row
+  int* seg_own = seg_h1 + (size_t)mh * kKlCols;     // [col][k] its owner (pair index; 0 in cell-mask mode)
+  int* nseg_s = seg_own + (size_t)mh * kKlCols;     // [col] segments of the column
+  int* nown_s = nseg_s + kKlCols;                   // [col] owned rows of the column
+  float* xs_s = reinterpret_cast<float*>(kl_smem + kl_header_bytes(mh)) + (size_t)warp * 2 * mh * kKlCols;
+  float* xt_s = xs_s + (size_t)mh * kKlCols;
 
-  // ---- once per CTA: owner strip; any owned cell at all?  For the gradient: every column's cells are numbered by
-  // the box segment (maximal run of rows with one owner) they belong to, so that the per-channel gradient sweep is a
-  // plain loop over rows with kKlSegGroup accumulators and no ownership logic.
+  // ---- once per CTA: the owner strip and, per column, its SEGMENTS (maximal runs of rows with one owner).  Only the
+  // rows inside segments are ever loaded or visited: the others have logit 0 in both softmaxes and enter in closed form.
   if (threadIdx.x == 0) { strip_any = 0; max_seg = 0; }
   __syncthreads();
   {
@@ -120,30 +120,37 @@ __global__ void __launch_bounds__(32 * kKlMaxWarps) dsgfd_kl_kernel(const __grid
   }
   __syncthreads();
   if (!strip_any) return;  // no box touches this strip: every column's KL is exactly 0
-  const bool want_grad = !CELL && prm.grad_rows != nullptr;
-  if (want_grad) {
-    if (threadIdx.x < kKlCols) {  // one thread per column walks its H rows
-      const int c = threadIdx.x;
-      int n = 0, prev = -1;
-      for (int h = 0; h < H; ++h) {
-        const int o = own_s[h * kKlCols + c];
-        if (o >= 0 && o != prev) seg_owner[c * prm.max_h + n++] = o;
-        slot_s[h * kKlCols + c] = (unsigned short)(o >= 0 ? n - 1 : 0xffff);
-        prev = o;
+  if (threadIdx.x < kKlCols) {  // one thread per column walks its H rows
+    const int c = threadIdx.x;
+    int n = 0, prev = -1, owned = 0;
+    for (int h = 0; h < H; ++h) {
+      const int o = own_s[h * kKlCols + c];
+      if (o != prev) {
+        if (prev >= 0) seg_h1[c * mh + n - 1] = h;
+        if (o >= 0) { seg_h0[c * mh + n] = h; seg_own[c * mh + n] = o; ++n; }
       }
-      nseg_s[c] = n;
-      atomicMax(&max_seg, n);
+      owned += o >= 0 ? 1 : 0;
+      prev = o;
     }
-    __syncthreads();
+    if (prev >= 0) seg_h1[c * mh + n - 1] = H;
+    nseg_s[c] = n;
+    nown_s[c] = owned;
+    atomicMax(&max_seg, n);
   }
+  __syncthreads();
 
   const float kLog2e = 1.4426950408889634f;
   const float gcoef = scale * Temp / (float)H;  // d loss / d pred = scale * (T/H) * (p - t)
-  double kl_total = 0.0;
+  const bool want_grad = !CELL && prm.grad_rows != nullptr;
   constexpr int kRow = kKlCols;                  // floats per strip row
-  constexpr int kStep = kKlPhases * kKlCols;     // floats between two rows of the same lane
-  const uint32_t xs_addr = (uint32_t)__cvta_generic_to_shared(xs_s) + (uint32_t)(ph * kRow + wl) * 4u;
-  const uint32_t xt_addr = (uint32_t)__cvta_generic_to_shared(xt_s) + (uint32_t)(ph * kRow + wl) * 4u;
+  const int my_nseg = nseg_s[wl], my_owned = nown_s[wl], nsweep = max_seg;  // the sweep loops are warp-uniform
+  const int* my_h0 = seg_h0 + wl * mh;
+  const int* my_h1 = seg_h1 + wl * mh;
+  const int* my_own = seg_own + wl * mh;
+  const uint32_t xs_a = (uint32_t)__cvta_generic_to_shared(xs_s) + (uint32_t)wl * 4u;
+  const uint32_t xt_a = (uint32_t)__cvta_generic_to_shared(xt_s) + (uint32_t)wl * 4u;
+  float* xs_c = xs_s + wl;                       // xs_c[h * kRow]
+  float* xt_c = xt_s + wl;
   auto phase_max = [](float v) {
 #pragma unroll
     for (int o = kKlCols; o < 32; o <<= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -154,108 +161,89 @@ __global__ void __launch_bounds__(32 * kKlMaxWarps) dsgfd_kl_kernel(const __grid
     for (int o = kKlCols; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
   };
+  // rows of segment k that belong to this lane: hb, hb + kKlPhases, ... < h1 (an empty range when k >= my_nseg)
+  auto seg_range = [&](int k, int& hb, int& h1) {
+    if (k < my_nseg) {
+      const int h0 = my_h0[k];
+      h1 = my_h1[k];
+      hb = h0 + ((ph - h0) & (kKlPhases - 1));
+    } else {
+      hb = 0;
+      h1 = 0;
+    }
+  };
+  double kl_total = 0.0;
 
-  for (int k = 0; k < kKlChan; ++k) {
-    const int c = (chunk * prm.warps + warp) * kKlChan + k;
+  for (int kc = 0; kc < kKlChan; ++kc) {
+    const int c = (chunk * prm.warps + warp) * kKlChan + kc;
     if (c >= C) break;
     const float* __restrict__ S = prm.student[lvl] + ((int64_t)img * C + c) * HW + w;
     const float* __restrict__ T = prm.teacher[lvl] + ((int64_t)img * C + c) * HW + w;
-    auto mask_of = [&](int o, int h) -> float {  // mask value of the cell (divided by T when that is exact)
-      if (o < 0) return 0.f;
-      const float m = CELL ? __ldg(prm.cell_weight + cell_base + (int64_t)h * W) : __ldg(prm.rows + (int64_t)o * C + c);
+    auto seg_mask = [&](int k) -> float {  // mask value of segment k (divided by T when that is exact)
+      const float m = __ldg(prm.rows + (int64_t)my_own[k] * C + c);
       return POW2 ? m * prm.inv_temperature : m;
     };
-    // Lane-private views: row r of this lane is row ph + r * kKlPhases of the strip; consecutive rows of a lane are
-    // kStep floats apart, so the unrolled loops below address shared memory with immediate offsets.
-    const int nrl = (H - ph + kKlPhases - 1) / kKlPhases;
-    const int* oq0 = own_s + ph * kRow + wl;
-    float* xq0 = xs_s + ph * kRow + wl;
-    float* tq0 = xt_s + ph * kRow + wl;
-    // ---- 0: owned cells -> shared memory asynchronously (every feature byte leaves HBM once)
-    {
-      const int* oq = oq0;
-      uint32_t xa = xs_addr, ta = xt_addr;
-      unsigned goff = (unsigned)ph * (unsigned)W;
-      const unsigned gstep = (unsigned)kKlPhases * (unsigned)W;
-      int r = 0;
-      for (; r + 4 <= nrl; r += 4, oq += 4 * kStep, xa += 16u * kStep, ta += 16u * kStep, goff += 4u * gstep) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          if (oq[q * kStep] >= 0) {
-            cp_async_f32(xa + 4u * q * kStep, S + (goff + q * gstep));
-            cp_async_f32(ta + 4u * q * kStep, T + (goff + q * gstep));
-          }
-        }
-      }
-      for (; r < nrl; ++r, oq += kStep, xa += 4u * kStep, ta += 4u * kStep, goff += gstep) {
-        if (oq[0] >= 0) {
-          cp_async_f32(xa, S + goff);
-          cp_async_f32(ta, T + goff);
-        }
+    // ---- 0: the rows inside segments -> shared memory, asynchronously (every feature byte leaves HBM once)
+    for (int k = 0; k < nsweep; ++k) {
+      int h, h1;
+      seg_range(k, h, h1);
+      for (; h < h1; h += kKlPhases) {
+        cp_async_f32(xs_a + (uint32_t)(h * kRow) * 4u, S + (unsigned)(h * W));
+        cp_async_f32(xt_a + (uint32_t)(h * kRow) * 4u, T + (unsigned)(h * W));
       }
     }
     cp_async_wait_all();
     __syncwarp();
-    // ---- A: logits in place (exactly 0 outside boxes; those cells were never loaded), column maxima
+    // ---- A: logits in place, maxima over the owned rows
     float ms = -INFINITY, mt = -INFINITY;
-    {
-      int prev = -2;
-      float m = 0.f;
-      const int* oq = oq0;
-      float* xq = xq0;
-      float* tq = tq0;
-      auto row = [&](int q, int h) {
-        const int o = oq[q * kStep];
-        if (CELL ? (o >= 0) : (o != prev)) { m = mask_of(o, h); prev = o; }  // the mask is constant along a run of rows
-        float x = 0.f, y = 0.f;
-        if (o >= 0) {
-          x = xq[q * kStep] * m;
-          y = tq[q * kStep] * m;
-          if (!POW2) { x = __fdiv_rn(x, Temp); y = __fdiv_rn(y, Temp); }
+    for (int k = 0; k < nsweep; ++k) {
+      int h, h1;
+      seg_range(k, h, h1);
+      if (h >= h1) continue;
+      float m = CELL ? 0.f : seg_mask(k);
+      for (; h < h1; h += kKlPhases) {
+        if (CELL) {
+          m = __ldg(prm.cell_weight + cell_base + (int64_t)h * W);
+          if (POW2) m *= prm.inv_temperature;
         }
-        xq[q * kStep] = x;
-        tq[q * kStep] = y;
+        float x = xs_c[h * kRow] * m, y = xt_c[h * kRow] * m;
+        if (!POW2) { x = __fdiv_rn(x, Temp); y = __fdiv_rn(y, Temp); }
+        xs_c[h * kRow] = x;
+        xt_c[h * kRow] = y;
         ms = fmaxf(ms, x);
         mt = fmaxf(mt, y);
-      };
-      int r = 0;
-      for (; r + 4 <= nrl; r += 4, oq += 4 * kStep, xq += 4 * kStep, tq += 4 * kStep) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) row(q, ph + (r + q) * kKlPhases);
       }
-      for (; r < nrl; ++r, oq += kStep, xq += kStep, tq += kStep) row(0, ph + r * kKlPhases);
-      ms = phase_max(ms);
-      mt = phase_max(mt);
     }
-    // ---- B: softmax sums and the t-weighted logit difference (four interleaved accumulator sets)
+    ms = phase_max(ms);
+    mt = phase_max(mt);
+    if (my_owned < H) { ms = fmaxf(ms, 0.f); mt = fmaxf(mt, 0.f); }  // rows outside boxes: logit 0 in both softmaxes
+    // ---- B: softmax sums and the t-weighted logit difference over the owned rows
     const float nms = -ms * kLog2e, nmt = -mt * kLog2e;
-    float ss[4] = {0.f, 0.f, 0.f, 0.f}, st4[4] = {0.f, 0.f, 0.f, 0.f}, ws[4] = {0.f, 0.f, 0.f, 0.f};
-    {
-      const float* xq = xq0;
-      const float* tq = tq0;
-      int r = 0;
-      for (; r + 4 <= nrl; r += 4, xq += 4 * kStep, tq += 4 * kStep) {
-        float a[4], b[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { a[q] = xq[q * kStep]; b[q] = tq[q * kStep]; }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float ea = fast_ex2(fmaf(a[q], kLog2e, nms));
-          ss[q] += ea;
-          st4[q] += fast_ex2(fmaf(b[q], kLog2e, nmt));
-          ws[q] = fmaf(ea, a[q] - b[q], ws[q]);
-        }
+    float ss0 = 0.f, ss1 = 0.f, st0 = 0.f, st1 = 0.f, ws0 = 0.f, ws1 = 0.f;
+    for (int k = 0; k < nsweep; ++k) {
+      int h, h1;
+      seg_range(k, h, h1);
+      for (; h + kKlPhases < h1; h += 2 * kKlPhases) {
+        const float a0 = xs_c[h * kRow], b0 = xt_c[h * kRow];
+        const float a1 = xs_c[(h + kKlPhases) * kRow], b1 = xt_c[(h + kKlPhases) * kRow];
+        const float e0 = fast_ex2(fmaf(a0, kLog2e, nms)), e1 = fast_ex2(fmaf(a1, kLog2e, nms));
+        ss0 += e0; ss1 += e1;
+        st0 += fast_ex2(fmaf(b0, kLog2e, nmt)); st1 += fast_ex2(fmaf(b1, kLog2e, nmt));
+        ws0 = fmaf(e0, a0 - b0, ws0); ws1 = fmaf(e1, a1 - b1, ws1);
       }
-      for (; r < nrl; ++r, xq += kStep, tq += kStep) {
-        const float a = xq[0], b = tq[0];
-        const float ea = fast_ex2(fmaf(a, kLog2e, nms));
-        ss[0] += ea;
-        st4[0] += fast_ex2(fmaf(b, kLog2e, nmt));
-        ws[0] = fmaf(ea, a - b, ws[0]);
+      if (h < h1) {
+        const float a0 = xs_c[h * kRow], b0 = xt_c[h * kRow];
+        const float e0 = fast_ex2(fmaf(a0, kLog2e, nms));
+        ss0 += e0;
+        st0 += fast_ex2(fmaf(b0, kLog2e, nmt));
+        ws0 = fmaf(e0, a0 - b0, ws0);
       }
     }
-    const float sum_s = phase_sum((ss[0] + ss[2]) + (ss[1] + ss[3])), sum_t = phase_sum((st4[0] + st4[2]) + (st4[1] + st4[3]));
-    const float wsum = phase_sum((ws[0] + ws[2]) + (ws[1] + ws[3]));
+    // the H - owned rows outside boxes add e^(0 - max) to each sum and nothing to the weighted difference
+    const float rest = (float)(H - my_owned);
+    const float sum_s = fmaf(rest, fast_ex2(nms), phase_sum(ss0 + ss1));
+    const float sum_t = fmaf(rest, fast_ex2(nmt), phase_sum(st0 + st1));
+    const float wsum = phase_sum(ws0 + ws1);
     // KL of the column = sum_h t_h (xs - xt) - (lse_s - lse_t): a second-order quantity (both log-softmaxes sit near
     // -log H), so the log-sum-exp difference is taken in double.  One lane per column keeps it.
     if (ph == 0) {
@@ -263,56 +251,40 @@ __global__ void __launch_bounds__(32 * kKlMaxWarps) dsgfd_kl_kernel(const __grid
       kl_total += (double)wsum / (double)sum_s - dl;
     }
 
-    // ---- C: d loss / d mask rows.  sum over a box segment of T_h (p_h - t_h) = (T/mask) sum xt_h (p_h - t_h); the cells
-    // carry their segment number, kKlSegGroup segments per column are accumulated per pass (one pass unless a column
-    // crosses more boxes), then the row phases are combined and one lane per column issues one red.global per segment.
+    // ---- C: d loss / d mask rows: sum over a segment of T_h (p_h - t_h) = (T/mask) sum xt_h (p_h - t_h); the row phases
+    // of a column are combined by shuffles and one lane issues one red.global per (column, segment, channel)
     if (want_grad) {
       const float rs = __fdividef(1.f, sum_s), rt = __fdividef(1.f, sum_t);
-      const unsigned short* sq0 = slot_s + ph * kRow + wl;
-      const int my_nseg = nseg_s[wl];
-      for (int base = 0; base < max_seg; base += kKlSegGroup) {
-        float acc[kKlSegGroup];
-#pragma unroll
-        for (int k = 0; k < kKlSegGroup; ++k) acc[k] = 0.f;
-        const float* xq = xq0;
-        const float* tq = tq0;
-        const unsigned short* sq = sq0;
-        auto row = [&](int q) {
-          const float a = xq[q * kStep], b = tq[q * kStep];
-          const int sl = (int)sq[q * kStep] - base;
-          const float v = b * (fast_ex2(fmaf(b, kLog2e, nmt)) * rt - fast_ex2(fmaf(a, kLog2e, nms)) * rs);
-#pragma unroll
-          for (int k = 0; k < kKlSegGroup; ++k) acc[k] += (sl == k) ? v : 0.f;
-        };
-        int r = 0;
-        for (; r + 4 <= nrl; r += 4, xq += 4 * kStep, tq += 4 * kStep, sq += 4 * kStep) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) row(q);
+      for (int k = 0; k < nsweep; ++k) {
+        int h, h1;
+        seg_range(k, h, h1);
+        float acc0 = 0.f, acc1 = 0.f;
+        for (; h + kKlPhases < h1; h += 2 * kKlPhases) {
+          const float b0 = xt_c[h * kRow], a0 = xs_c[h * kRow], b1 = xt_c[(h + kKlPhases) * kRow], a1 = xs_c[(h + kKlPhases) * kRow];
+          const float p0 = fast_ex2(fmaf(b0, kLog2e, nmt)) * rt, t0 = fast_ex2(fmaf(a0, kLog2e, nms)) * rs;
+          const float p1 = fast_ex2(fmaf(b1, kLog2e, nmt)) * rt, t1 = fast_ex2(fmaf(a1, kLog2e, nms)) * rs;
+          acc0 = fmaf(b0, p0 - t0, acc0);
+          acc1 = fmaf(b1, p1 - t1, acc1);
         }
-        for (; r < nrl; ++r, xq += kStep, tq += kStep, sq += kStep) row(0);
-#pragma unroll
-        for (int k = 0; k < kKlSegGroup; ++k) acc[k] = phase_sum(acc[k]);
-        if (ph == 0) {
-#pragma unroll
-          for (int k = 0; k < kKlSegGroup; ++k) {
-            if (base + k >= my_nseg) continue;
-            const int who = seg_owner[wl * prm.max_h + base + k];
-            const float m = mask_of(who, 0);
-            float v = acc[k];
-            float div = POW2 ? m : m / Temp;
-            if (m == 0.f) {
-              // the mask value underflowed to 0: the logits carry no trace of the teacher feature, re-read it
-              v = 0.f;
-              div = 1.f;
-              for (int h = 0; h < H; ++h) {
-                if ((int)slot_s[h * kRow + wl] != base + k) continue;
-                const float pp = fast_ex2(fmaf(xt_s[h * kRow + wl], kLog2e, nmt)) * rt;
-                const float tt = fast_ex2(fmaf(xs_s[h * kRow + wl], kLog2e, nms)) * rs;
-                v = fmaf(ld_stream_f1(T + (int64_t)h * W), pp - tt, v);
-              }
+        if (h < h1) {
+          const float b0 = xt_c[h * kRow], a0 = xs_c[h * kRow];
+          acc0 = fmaf(b0, fast_ex2(fmaf(b0, kLog2e, nmt)) * rt - fast_ex2(fmaf(a0, kLog2e, nms)) * rs, acc0);
+        }
+        float v = phase_sum(acc0 + acc1);
+        if (ph == 0 && k < my_nseg) {
+          const float m = seg_mask(k);
+          float div = POW2 ? m : m / Temp;
+          if (m == 0.f) {
+            // the mask value underflowed to 0: the logits carry no trace of the teacher feature, re-read it
+            v = 0.f;
+            div = 1.f;
+            for (int r = my_h0[k]; r < my_h1[k]; ++r) {
+              const float pp = fast_ex2(fmaf(xt_c[r * kRow], kLog2e, nmt)) * rt;
+              const float tt = fast_ex2(fmaf(xs_c[r * kRow], kLog2e, nms)) * rs;
+              v = fmaf(ld_stream_f1(T + (int64_t)r * W), pp - tt, v);
             }
-            atomicAdd(prm.grad_rows + (int64_t)who * C + c, __fdividef(gcoef * v, div));
           }
+          atomicAdd(prm.grad_rows + (int64_t)my_own[k] * C + c, __fdividef(gcoef * v, div));
         }
       }
     }

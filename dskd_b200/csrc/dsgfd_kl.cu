@@ -5,6 +5,10 @@
 // Cells outside every box have logit 0 for both softmaxes and need no feature bytes; strips without any owned cell
 // contribute exactly 0 and are skipped.  No gradient reaches the student features (target is detached): the only
 // gradient is d loss / d rows.  Algorithmic bytes: read S + read T = 8 B per element (45.51 MB per 800x1333 image).
+#include <stdlib.h>
+
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace dskd {
@@ -296,6 +300,292 @@ __global__ void __launch_bounds__(32 * kKlMaxWarps) dsgfd_kl_kernel(const __grid
     atomicAdd(prm.loss, tot * (double)scale * (double)Temp * (double)Temp / (double)H);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Column kernel (box masks, H <= 400): the logits of a column never leave the register file.
+// A warp owns 32 consecutive columns (w) of kColRows consecutive rows of one channel plane: every feature load is one
+// coalesced 128 B row piece, each lane keeps its kColRows student / teacher values in registers through all three
+// sweeps (logits + maxima, softmax sums, gradient), and the loops over rows are fully unrolled, so there is no address
+// arithmetic, no shared-memory staging of features and no per-segment loop.  Taller levels are cut into `parts` row
+// parts held by `parts` warps of the CTA; they exchange (local max, local sums) once per channel through shared memory
+// and rescale.  What varies per row -- the owning box -- is turned ONCE per CTA into a byte offset into a small
+// shared-memory table of the mask rows of the tile's boxes (entry 0 = the zero row for cells outside boxes), so a row
+// costs one LDS for its mask value and cells outside boxes need no branch: their logit is feature * 0.
+// Row parts without any box skip their loads and arithmetic (closed form), tiles without any box exit.
+constexpr int kColRows = 25;        // rows per lane (100 / 50 / 25 rows of the COCO pyramid = 4 / 2 / 1 parts)
+constexpr int kColTableCap = 3072;  // floats of staged mask rows per CTA
+constexpr int kColMaxPairs = kColTableCap - 3;
+constexpr int kColMaxChunk = 64;    // channels per CTA at most
+
+struct KlColParams {
+  DskdLevel levels[DSKD_MAX_LEVELS];
+  const float* student[DSKD_MAX_LEVELS];
+  const float* teacher[DSKD_MAX_LEVELS];
+  float scale[DSKD_MAX_LEVELS];
+  int block_start[DSKD_MAX_LEVELS + 1];
+  int wtiles[DSKD_MAX_LEVELS];
+  int parts[DSKD_MAX_LEVELS];  // row parts (warps per column tile)
+  int rpp[DSKD_MAX_LEVELS];    // rows per part
+  int num_levels, N, C;
+  int chunk;                   // channels per CTA
+  float temperature, inv_temperature;
+  int64_t cells_per_image;
+  const int* owner;
+  const float* rows;
+  float* grad_rows;
+  double* loss;
+};
+
+// bar.sync on a compile-time barrier id (a run-time id makes ptxas reserve all 16 barriers for every CTA)
+template <int MAXG>
+__device__ __forceinline__ void group_barrier(int group, int threads) {
+#define DSKD_BAR_CASE(G)                                                               \
+  case G:                                                                              \
+    if (G < MAXG) asm volatile("bar.sync %0, %1;" ::"n"(G + 1), "r"(threads) : "memory"); \
+    break;
+  switch (group) {
+    DSKD_BAR_CASE(0) DSKD_BAR_CASE(1) DSKD_BAR_CASE(2) DSKD_BAR_CASE(3)
+    DSKD_BAR_CASE(4) DSKD_BAR_CASE(5) DSKD_BAR_CASE(6) DSKD_BAR_CASE(7)
+    default: break;
+  }
+#undef DSKD_BAR_CASE
+}
+
+template <int MAXW, bool POW2>
+__global__ void __launch_bounds__(32 * MAXW, 16 / MAXW) dsgfd_kl_col_kernel(const __grid_constant__ KlColParams prm) {
+  __shared__ float rows_s[kColTableCap];   // [channel of the sub-chunk][1 + owner - omin] mask values (/T when exact)
+  __shared__ float ex_s[2][MAXW][5][32];   // per warp: local max_s, max_t, sum_s, sum_t, weighted sum (double-buffered)
+  __shared__ double red[32];
+  __shared__ int orange_s[2];
+  __shared__ int zero_s[kColMaxChunk];     // per staged channel: some mask value is exactly 0 (underflow)
+  constexpr unsigned kFull = 0xffffffffu;
+  constexpr int kPacked = (kColRows + 1) / 2;
+  constexpr float kExcluded = -1e30f;      // logit of a row that does not exist (partial parts): e^x == 0, x - y == 0
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int lvl = 0;
+#pragma unroll
+  for (int k = 1; k < DSKD_MAX_LEVELS; ++k)
+    if (k < prm.num_levels && (int)blockIdx.x >= prm.block_start[k]) lvl = k;
+  const int H = prm.levels[lvl].H, W = prm.levels[lvl].W, C = prm.C;
+  const int HW = H * W;
+  const int nchunks = (C + prm.chunk - 1) / prm.chunk;
+  int idx = blockIdx.x - prm.block_start[lvl];
+  const int chunk = idx % nchunks;  // the channel chunks of one tile are neighbours: its owner lines stay in L2
+  idx /= nchunks;
+  const int wt = idx % prm.wtiles[lvl];
+  const int img = idx / prm.wtiles[lvl];
+  const int parts = prm.parts[lvl], rpp = prm.rpp[lvl];
+  const int groups = MAXW / parts;            // warps of one group hold the row parts of the same channel
+  const int part = warp % parts, group = warp / parts;
+  const bool active = group < groups;
+  const int w = wt * 32 + lane;
+  const bool col_ok = w < W;
+  const int wc = min(w, W - 1);               // lanes past the last column load it again and are ignored
+  const int row0 = part * rpp;
+  const int nrows = active ? min(rpp, H - row0) : 0;
+  const float Temp = prm.temperature;
+  const float scale = prm.scale[lvl];
+  const unsigned uW = (unsigned)W;
+
+  // ---- once per CTA: the owners of this lane's rows -> byte offsets into the staged mask table, flush rows
+  if (tid == 0) { orange_s[0] = 0x7fffffff; orange_s[1] = -1; }
+  __syncthreads();
+  const int64_t cell0 = (int64_t)img * prm.cells_per_image + prm.levels[lvl].cell_offset + (int64_t)row0 * W + wc;
+  unsigned moffp[kPacked];  // two 16-bit byte offsets per register
+  unsigned fb = 0;          // rows after which the accumulated gradient of a run is flushed
+  bool part_any;
+  int omin, omax;
+  {
+    int own[kColRows];
+    int lo = 0x7fffffff, hi = -1;
+#pragma unroll
+    for (int r = 0; r < kColRows; ++r) {
+      int o = -1;
+      if (col_ok && r < nrows) o = __ldg(prm.owner + cell0 + r * uW);
+      own[r] = o;
+      if (o >= 0) { lo = min(lo, o); hi = max(hi, o); }
+    }
+    lo = __reduce_min_sync(kFull, lo);
+    hi = __reduce_max_sync(kFull, hi);
+    part_any = hi >= 0;  // some cell of this warp's rows lies inside a box
+    if (lane == 0 && part_any) { atomicMin(&orange_s[0], lo); atomicMax(&orange_s[1], hi); }
+    __syncthreads();
+    omin = orange_s[0];
+    omax = orange_s[1];
+    if (omax < 0) return;  // no box touches this tile: every column's KL is exactly 0
+#pragma unroll
+    for (int r = 0; r < kColRows; ++r) {
+      const int nx = (r + 1 < kColRows) ? own[r + 1] : -1;
+      if (own[r] >= 0 && nx != own[r]) fb |= 1u << r;
+    }
+#pragma unroll
+    for (int k = 0; k < kPacked; ++k) {
+      const int o0 = own[2 * k], o1 = (2 * k + 1 < kColRows) ? own[2 * k + 1] : -1;
+      const unsigned b0 = o0 >= 0 ? (unsigned)(o0 - omin + 1) * 4u : 0u;
+      const unsigned b1 = o1 >= 0 ? (unsigned)(o1 - omin + 1) * 4u : 0u;
+      moffp[k] = b0 | (b1 << 16);
+    }
+  }
+  const unsigned anyfb = __reduce_or_sync(kFull, fb);
+  const int nown = omax - omin + 1;
+  const int nstride = (nown + 1) | 1;  // odd: the staging writes of one owner spread over the banks
+  const int chs = min(prm.chunk, kColTableCap / nstride);  // channels staged at a time (>= 1: host bounds num_pairs)
+
+  const float kLog2e = 1.4426950408889634f;
+  const float gcoef = scale * Temp / (float)H;  // d loss / d pred = scale * (T/H) * (p - t)
+  const bool want_grad = prm.grad_rows != nullptr;
+  const int c_begin = chunk * prm.chunk, c_end = min(C, c_begin + prm.chunk);
+  double kl_total = 0.0;
+  int par = 0;
+#define DSKD_MOFF(r) (((r) & 1) ? (moffp[(r) >> 1] >> 16) : (moffp[(r) >> 1] & 0xffffu))
+#define DSKD_MTAB(off) (*reinterpret_cast<const float*>(reinterpret_cast<const char*>(mtab) + (off)))
+
+  // one channel of this warp's rows; FULL: all kColRows rows exist
+  auto channel = [&](auto full_tag, const int c, const float* mtab, const bool zero_any) {
+    constexpr bool FULL = decltype(full_tag)::value;
+    float s[kColRows], t[kColRows];
+    float ml_s = 0.f, ml_t = 0.f, ss = (float)nrows, st = (float)nrows, ws = 0.f;
+    const int64_t plane = ((int64_t)img * C + c) * HW + (int64_t)row0 * W + wc;
+    if (part_any) {
+      const float* __restrict__ Sp = prm.student[lvl] + plane;
+      const float* __restrict__ Tp = prm.teacher[lvl] + plane;
+#pragma unroll
+      for (int r = 0; r < kColRows; ++r) {
+        const unsigned off = (FULL ? (unsigned)r : (unsigned)min(r, nrows - 1)) * uW;  // clamped: always a valid row
+        s[r] = ld_stream_f1(Sp + off);
+        t[r] = ld_stream_f1(Tp + off);
+      }
+      // A: logits, maxima of this part
+      ml_s = -INFINITY;
+      ml_t = -INFINITY;
+#pragma unroll
+      for (int r = 0; r < kColRows; ++r) {
+        const float m = DSKD_MTAB(DSKD_MOFF(r));
+        float x = s[r] * m, y = t[r] * m;
+        if (!POW2) { x = __fdiv_rn(x, Temp); y = __fdiv_rn(y, Temp); }
+        if (!FULL) { x = r < nrows ? x : kExcluded; y = r < nrows ? y : kExcluded; }
+        s[r] = x;
+        t[r] = y;
+        ml_s = fmaxf(ml_s, x);
+        ml_t = fmaxf(ml_t, y);
+      }
+      // B: sums against the part's own maxima
+      const float nms = -ml_s * kLog2e, nmt = -ml_t * kLog2e;
+      float ss0 = 0.f, ss1 = 0.f, st0 = 0.f, st1 = 0.f, ws0 = 0.f, ws1 = 0.f;
+#pragma unroll
+      for (int r = 0; r < kColRows; ++r) {
+        const float e = fast_ex2(fmaf(s[r], kLog2e, nms));
+        const float f = fast_ex2(fmaf(t[r], kLog2e, nmt));
+        if (r & 1) { ss1 += e; st1 += f; ws1 = fmaf(e, s[r] - t[r], ws1); }
+        else { ss0 += e; st0 += f; ws0 = fmaf(e, s[r] - t[r], ws0); }
+      }
+      ss = ss0 + ss1;
+      st = st0 + st1;
+      ws = ws0 + ws1;
+    }
+    // combine the row parts of the column: sum_p e^(max_p - max) * sum_p
+    float Ms = ml_s, Mt = ml_t, sum_s = ss, sum_t = st, wsum = ws;
+    if (parts > 1) {
+      float(*ex)[5][32] = ex_s[par];
+      ex[warp][0][lane] = ml_s;
+      ex[warp][1][lane] = ml_t;
+      ex[warp][2][lane] = ss;
+      ex[warp][3][lane] = st;
+      ex[warp][4][lane] = ws;
+      group_barrier<MAXW / 2>(group, 32 * parts);
+      const int w0 = group * parts;
+      for (int p = 0; p < parts; ++p) {
+        Ms = fmaxf(Ms, ex[w0 + p][0][lane]);
+        Mt = fmaxf(Mt, ex[w0 + p][1][lane]);
+      }
+      sum_s = 0.f;
+      sum_t = 0.f;
+      wsum = 0.f;
+      for (int p = 0; p < parts; ++p) {
+        const float fs = fast_ex2((ex[w0 + p][0][lane] - Ms) * kLog2e);
+        const float ft = fast_ex2((ex[w0 + p][1][lane] - Mt) * kLog2e);
+        sum_s = fmaf(ex[w0 + p][2][lane], fs, sum_s);
+        sum_t = fmaf(ex[w0 + p][3][lane], ft, sum_t);
+        wsum = fmaf(ex[w0 + p][4][lane], fs, wsum);
+      }
+      par ^= 1;
+    }
+    // KL of the column = sum_h t_h (xs - xt) - (lse_s - lse_t): second order, so the difference is taken in double
+    if (part == 0 && col_ok) {
+      const double dl = ((double)Ms - (double)Mt) + log((double)sum_s / (double)sum_t);
+      kl_total += (double)wsum / (double)sum_s - dl;
+    }
+    // C: d loss / d mask rows: sum over a run of rows with one owner of T_h (p_h - t_h) = (T/mask) sum xt_h (p_h - t_h)
+    if (want_grad && part_any) {
+      const float rs = __fdividef(1.f, sum_s), rt = __fdividef(1.f, sum_t);
+      const float nms = -Ms * kLog2e, nmt = -Mt * kLog2e;
+      float* __restrict__ grow = prm.grad_rows + (int64_t)(omin - 1) * C + c;
+      float acc = 0.f;
+#pragma unroll
+      for (int r = 0; r < kColRows; ++r) {
+        const float pt = fast_ex2(fmaf(t[r], kLog2e, nmt)) * rt;
+        const float d = fmaf(-fast_ex2(fmaf(s[r], kLog2e, nms)), rs, pt);
+        acc = fmaf(t[r], d, acc);
+        if (anyfb & (1u << r)) {  // warp-uniform
+          if (fb & (1u << r)) {
+            const unsigned off = DSKD_MOFF(r);
+            const float m = DSKD_MTAB(off);
+            // m == 0 (underflow): the run is handled below from the raw teacher feature
+            if (m != 0.f) atomicAdd(grow + (off >> 2) * (unsigned)C, __fdividef(gcoef * acc, POW2 ? m : m / Temp));
+            acc = 0.f;
+          }
+        }
+      }
+      if (zero_any) {
+        // some mask value of this channel underflowed to 0: the logits of such a run are all 0, p - t is one
+        // constant, and the registers carry no trace of the teacher feature -- walk the rows again
+        const float d0 = fast_ex2(nmt) * rt - fast_ex2(nms) * rs;
+        const float* __restrict__ Tp = prm.teacher[lvl] + plane;
+        float tsum = 0.f;
+        for (int r = 0; r < nrows; ++r) {
+          const int o = col_ok ? __ldg(prm.owner + cell0 + r * uW) : -1;
+          const int nx = (col_ok && r + 1 < nrows) ? __ldg(prm.owner + cell0 + (r + 1) * uW) : -1;
+          const bool zero = o >= 0 && mtab[o - omin + 1] == 0.f;
+          if (zero) tsum += ld_stream_f1(Tp + r * uW);
+          if (nx != o) {
+            if (zero) atomicAdd(prm.grad_rows + (int64_t)o * C + c, gcoef * tsum * d0);
+            tsum = 0.f;
+          }
+        }
+      }
+    }
+  };
+
+  for (int sc = c_begin; sc < c_end; sc += chs) {
+    const int nch = min(chs, c_end - sc);
+    __syncthreads();  // the readers of the previous sub-chunk are done
+    for (int cc = tid; cc < nch; cc += 32 * MAXW) {
+      rows_s[cc * nstride] = 0.f;  // cells outside boxes
+      zero_s[cc] = 0;
+    }
+    __syncthreads();
+    for (int i = tid; i < nown * nch; i += 32 * MAXW) {
+      const int o = i / nch, cc = i - o * nch;
+      float m = __ldg(prm.rows + (int64_t)(omin + o) * C + sc + cc);
+      if (POW2) m *= prm.inv_temperature;
+      rows_s[cc * nstride + o + 1] = m;
+      if (m == 0.f) zero_s[cc] = 1;
+    }
+    __syncthreads();
+    if (active) {
+      for (int cc = group; cc < nch; cc += groups) {
+        if (nrows == kColRows) channel(std::true_type{}, sc + cc, rows_s + cc * nstride, zero_s[cc] != 0);
+        else channel(std::false_type{}, sc + cc, rows_s + cc * nstride, zero_s[cc] != 0);
+      }
+    }
+  }
+#undef DSKD_MOFF
+#undef DSKD_MTAB
+  // loss = scale * T^2 / H * sum over columns of sum_h t (log t - log p)
+  double tot = block_sum(kl_total, red);
+  if (tid == 0 && tot != 0.0) atomicAdd(prm.loss, tot * (double)scale * (double)Temp * (double)Temp / (double)H);
+}
+
 }  // namespace dskd
 
 using namespace dskd;
@@ -331,6 +621,55 @@ extern "C" int dskd_dsgfd_kl_fwd_bwd(const DskdDsgfdKlArgs* a, void* stream) {
     max_h = std::max(max_h, a->levels[l].H);
   }
   DSKD_REQUIRE(cells == a->cells_per_image, "dsgfd_kl: cells_per_image mismatch");
+  cudaStream_t st = as_stream(stream);
+  int texp = 0;
+  const bool pow2 = frexpf(a->temperature, &texp) == 0.5f;  // T = 2^k: the division by T is an exact scaling
+
+  // box masks on levels of at most 16 x kColRows rows: the register-resident column kernel
+  const char* impl = getenv("DSKD_KL_IMPL");
+  if (!cell && max_h <= 16 * kColRows && a->num_pairs <= kColMaxPairs && !(impl && impl[0] == 's')) {
+    KlColParams cp;
+    cp.num_levels = a->num_levels;
+    cp.N = a->N;
+    cp.C = a->C;
+    cp.temperature = a->temperature;
+    cp.inv_temperature = 1.f / a->temperature;
+    cp.cells_per_image = a->cells_per_image;
+    cp.owner = a->d_owner;
+    cp.rows = a->d_rows;
+    cp.grad_rows = a->d_grad_rows;
+    cp.loss = a->d_loss;
+    const char* ch = getenv("DSKD_KL_CHUNK");
+    cp.chunk = ch ? std::min(kColMaxChunk, std::max(1, atoi(ch))) : 16;
+    const int max_parts = (max_h + kColRows - 1) / kColRows;
+    const int maxw = max_parts <= 4 ? 4 : (max_parts <= 8 ? 8 : 16);
+    const int nchunks = (a->C + cp.chunk - 1) / cp.chunk;
+    int blocks = 0;
+    for (int l = 0; l < a->num_levels; ++l) {
+      cp.levels[l] = a->levels[l];
+      cp.student[l] = a->d_student[l];
+      cp.teacher[l] = a->d_teacher[l];
+      cp.scale[l] = a->scale[l];
+      cp.wtiles[l] = (a->levels[l].W + 31) / 32;
+      cp.parts[l] = (a->levels[l].H + kColRows - 1) / kColRows;
+      cp.rpp[l] = (a->levels[l].H + cp.parts[l] - 1) / cp.parts[l];
+      cp.block_start[l] = blocks;
+      blocks += cp.wtiles[l] * nchunks * a->N;
+    }
+    cp.block_start[a->num_levels] = blocks;
+    if (maxw == 4) {
+      if (pow2) dsgfd_kl_col_kernel<4, true><<<blocks, 128, 0, st>>>(cp);
+      else dsgfd_kl_col_kernel<4, false><<<blocks, 128, 0, st>>>(cp);
+    } else if (maxw == 8) {
+      if (pow2) dsgfd_kl_col_kernel<8, true><<<blocks, 256, 0, st>>>(cp);
+      else dsgfd_kl_col_kernel<8, false><<<blocks, 256, 0, st>>>(cp);
+    } else {
+      if (pow2) dsgfd_kl_col_kernel<16, true><<<blocks, 512, 0, st>>>(cp);
+      else dsgfd_kl_col_kernel<16, false><<<blocks, 512, 0, st>>>(cp);
+    }
+    DSKD_LAUNCH_OK("dsgfd_kl_col_kernel");
+    return DSKD_OK;
+  }
   DSKD_REQUIRE(max_h <= kKlMaxH, "dsgfd_kl: H (%d) above the supported %d", max_h, kKlMaxH);
   // shared memory: owner strip (128 B per row) + two logit strips (256 B per row) per warp
   int warps = (int)std::min<int64_t>(kKlMaxWarps, ((int64_t)kKlSmemBudget - (int64_t)kl_header_bytes(max_h)) / (8ll * kKlCols * max_h));
@@ -352,9 +691,6 @@ extern "C" int dskd_dsgfd_kl_fwd_bwd(const DskdDsgfdKlArgs* a, void* stream) {
   }
   prm.block_start[a->num_levels] = blocks;
   const size_t smem = kl_header_bytes(max_h) + 8ull * kKlCols * max_h * warps;
-  int texp = 0;
-  const bool pow2 = frexpf(a->temperature, &texp) == 0.5f;  // T = 2^k: the division by T is an exact scaling
-  cudaStream_t st = as_stream(stream);
 #define DSKD_KL_LAUNCH(CELLV, P2V)                                                                                  \
   do {                                                                                                              \
     DSKD_CUDA_OK(cudaFuncSetAttribute(dsgfd_kl_kernel<CELLV, P2V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \

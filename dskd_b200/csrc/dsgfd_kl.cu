@@ -313,6 +313,8 @@ __global__ void __launch_bounds__(32 * kKlMaxWarps) dsgfd_kl_kernel(const __grid
 // costs one LDS for its mask value and cells outside boxes need no branch: their logit is feature * 0.
 // Row parts without any box skip their loads and arithmetic (closed form), tiles without any box exit.
 constexpr int kColRows = 25;        // rows per lane (100 / 50 / 25 rows of the COCO pyramid = 4 / 2 / 1 parts)
+constexpr int kColBlk = 5;          // rows per skippable block
+constexpr int kColBlocks = (kColRows + kColBlk - 1) / kColBlk;
 constexpr int kColTableCap = 3072;  // floats of staged mask rows per CTA
 constexpr int kColMaxPairs = kColTableCap - 3;
 constexpr int kColMaxChunk = 64;    // channels per CTA at most
@@ -394,6 +396,7 @@ __global__ void __launch_bounds__(32 * MAXW, 16 / MAXW) dsgfd_kl_col_kernel(cons
   unsigned moffp[kPacked];  // two 16-bit byte offsets per register
   unsigned fb = 0;          // rows after which the accumulated gradient of a run is flushed
   bool part_any;
+  unsigned rowany;          // rows with a box in some column of the warp
   int omin, omax;
   {
     int own[kColRows];
@@ -408,6 +411,12 @@ __global__ void __launch_bounds__(32 * MAXW, 16 / MAXW) dsgfd_kl_col_kernel(cons
     lo = __reduce_min_sync(kFull, lo);
     hi = __reduce_max_sync(kFull, hi);
     part_any = hi >= 0;  // some cell of this warp's rows lies inside a box
+    {
+      unsigned ob = 0;
+#pragma unroll
+      for (int r = 0; r < kColRows; ++r) ob |= own[r] >= 0 ? 1u << r : 0u;
+      rowany = __reduce_or_sync(kFull, ob);
+    }
     if (lane == 0 && part_any) { atomicMin(&orange_s[0], lo); atomicMax(&orange_s[1], hi); }
     __syncthreads();
     omin = orange_s[0];
@@ -427,6 +436,16 @@ __global__ void __launch_bounds__(32 * MAXW, 16 / MAXW) dsgfd_kl_col_kernel(cons
     }
   }
   const unsigned anyfb = __reduce_or_sync(kFull, fb);
+  // blocks of kColBlk rows without any box in the warp's 32 columns are skipped (closed form: logit 0)
+  unsigned blk_on = 0;
+  int nskip_i = 0;
+#pragma unroll
+  for (int b = 0; b < kColBlocks; ++b) {
+    const unsigned bm = ((1u << kColBlk) - 1u) << (b * kColBlk);
+    if (rowany & bm) blk_on |= 1u << b;
+    else nskip_i += max(0, min(nrows - b * kColBlk, kColBlk));
+  }
+  const float nskip = (float)nskip_i;
   const int nown = omax - omin + 1;
   const int nstride = (nown + 1) | 1;  // odd: the staging writes of one owner spread over the banks
   const int chs = min(prm.chunk, kColTableCap / nstride);  // channels staged at a time (>= 1: host bounds num_pairs)
@@ -446,41 +465,60 @@ __global__ void __launch_bounds__(32 * MAXW, 16 / MAXW) dsgfd_kl_col_kernel(cons
     float s[kColRows], t[kColRows];
     float ml_s = 0.f, ml_t = 0.f, ss = (float)nrows, st = (float)nrows, ws = 0.f;
     const int64_t plane = ((int64_t)img * C + c) * HW + (int64_t)row0 * W + wc;
+#define DSKD_FOR_ROWS_ON(body)                                   \
+  _Pragma("unroll") for (int b_ = 0; b_ < kColBlocks; ++b_) {    \
+    if (blk_on & (1u << b_)) {                                   \
+      _Pragma("unroll") for (int k_ = 0; k_ < kColBlk; ++k_) {   \
+        const int r = b_ * kColBlk + k_;                         \
+        if (r < kColRows) { body }                               \
+      }                                                          \
+    }                                                            \
+  }
     if (part_any) {
       const float* __restrict__ Sp = prm.student[lvl] + plane;
       const float* __restrict__ Tp = prm.teacher[lvl] + plane;
+      const uint64_t pitch = (uint64_t)uW * 4u;
 #pragma unroll
-      for (int r = 0; r < kColRows; ++r) {
-        const unsigned off = (FULL ? (unsigned)r : (unsigned)min(r, nrows - 1)) * uW;  // clamped: always a valid row
-        s[r] = ld_stream_f1(Sp + off);
-        t[r] = ld_stream_f1(Tp + off);
+      for (int b_ = 0; b_ < kColBlocks; ++b_) {
+        if (blk_on & (1u << b_)) {
+          // byte addresses advanced by one row pitch: two 64-bit adds per row instead of re-deriving base + r * W
+          const unsigned r0 = FULL ? (unsigned)(b_ * kColBlk) : (unsigned)min(b_ * kColBlk, nrows - 1);
+          uint64_t sa = reinterpret_cast<uint64_t>(Sp + r0 * uW), ta = reinterpret_cast<uint64_t>(Tp + r0 * uW);
+#pragma unroll
+          for (int k_ = 0; k_ < kColBlk; ++k_) {
+            const int r = b_ * kColBlk + k_;
+            if (r < kColRows) {
+              s[r] = ld_stream_f1(reinterpret_cast<const float*>(sa));
+              t[r] = ld_stream_f1(reinterpret_cast<const float*>(ta));
+              if (FULL || r + 1 < nrows) { sa += pitch; ta += pitch; }  // rows past the part load its last row again
+            }
+          }
+        }
       }
-      // A: logits, maxima of this part
-      ml_s = -INFINITY;
-      ml_t = -INFINITY;
-#pragma unroll
-      for (int r = 0; r < kColRows; ++r) {
+      // A: logits, maxima of this part (skipped rows: logit 0)
+      ml_s = nskip_i > 0 ? 0.f : -INFINITY;
+      ml_t = ml_s;
+      DSKD_FOR_ROWS_ON(
         const float m = DSKD_MTAB(DSKD_MOFF(r));
-        float x = s[r] * m, y = t[r] * m;
+        float x = s[r] * m; float y = t[r] * m;
         if (!POW2) { x = __fdiv_rn(x, Temp); y = __fdiv_rn(y, Temp); }
         if (!FULL) { x = r < nrows ? x : kExcluded; y = r < nrows ? y : kExcluded; }
         s[r] = x;
         t[r] = y;
         ml_s = fmaxf(ml_s, x);
         ml_t = fmaxf(ml_t, y);
-      }
+      )
       // B: sums against the part's own maxima
       const float nms = -ml_s * kLog2e, nmt = -ml_t * kLog2e;
       float ss0 = 0.f, ss1 = 0.f, st0 = 0.f, st1 = 0.f, ws0 = 0.f, ws1 = 0.f;
-#pragma unroll
-      for (int r = 0; r < kColRows; ++r) {
+      DSKD_FOR_ROWS_ON(
         const float e = fast_ex2(fmaf(s[r], kLog2e, nms));
         const float f = fast_ex2(fmaf(t[r], kLog2e, nmt));
         if (r & 1) { ss1 += e; st1 += f; ws1 = fmaf(e, s[r] - t[r], ws1); }
         else { ss0 += e; st0 += f; ws0 = fmaf(e, s[r] - t[r], ws0); }
-      }
-      ss = ss0 + ss1;
-      st = st0 + st1;
+      )
+      ss = fmaf(nskip, fast_ex2(nms), ss0 + ss1);
+      st = fmaf(nskip, fast_ex2(nmt), st0 + st1);
       ws = ws0 + ws1;
     }
     // combine the row parts of the column: sum_p e^(max_p - max) * sum_p
@@ -494,6 +532,7 @@ __global__ void __launch_bounds__(32 * MAXW, 16 / MAXW) dsgfd_kl_col_kernel(cons
       ex[warp][4][lane] = ws;
       group_barrier<MAXW / 2>(group, 32 * parts);
       const int w0 = group * parts;
+#pragma unroll 1
       for (int p = 0; p < parts; ++p) {
         Ms = fmaxf(Ms, ex[w0 + p][0][lane]);
         Mt = fmaxf(Mt, ex[w0 + p][1][lane]);
@@ -501,6 +540,7 @@ __global__ void __launch_bounds__(32 * MAXW, 16 / MAXW) dsgfd_kl_col_kernel(cons
       sum_s = 0.f;
       sum_t = 0.f;
       wsum = 0.f;
+#pragma unroll 1
       for (int p = 0; p < parts; ++p) {
         const float fs = fast_ex2((ex[w0 + p][0][lane] - Ms) * kLog2e);
         const float ft = fast_ex2((ex[w0 + p][1][lane] - Mt) * kLog2e);
@@ -521,8 +561,7 @@ __global__ void __launch_bounds__(32 * MAXW, 16 / MAXW) dsgfd_kl_col_kernel(cons
       const float nms = -Ms * kLog2e, nmt = -Mt * kLog2e;
       float* __restrict__ grow = prm.grad_rows + (int64_t)(omin - 1) * C + c;
       float acc = 0.f;
-#pragma unroll
-      for (int r = 0; r < kColRows; ++r) {
+      DSKD_FOR_ROWS_ON(
         const float pt = fast_ex2(fmaf(t[r], kLog2e, nmt)) * rt;
         const float d = fmaf(-fast_ex2(fmaf(s[r], kLog2e, nms)), rs, pt);
         acc = fmaf(t[r], d, acc);
@@ -535,7 +574,7 @@ __global__ void __launch_bounds__(32 * MAXW, 16 / MAXW) dsgfd_kl_col_kernel(cons
             acc = 0.f;
           }
         }
-      }
+      )
       if (zero_any) {
         // some mask value of this channel underflowed to 0: the logits of such a run are all 0, p - t is one
         // constant, and the registers carry no trace of the teacher feature -- walk the rows again
@@ -581,6 +620,7 @@ __global__ void __launch_bounds__(32 * MAXW, 16 / MAXW) dsgfd_kl_col_kernel(cons
   }
 #undef DSKD_MOFF
 #undef DSKD_MTAB
+#undef DSKD_FOR_ROWS_ON
   // loss = scale * T^2 / H * sum over columns of sum_h t (log t - log p)
   double tot = block_sum(kl_total, red);
   if (tid == 0 && tot != 0.0) atomicAdd(prm.loss, tot * (double)scale * (double)Temp * (double)Temp / (double)H);

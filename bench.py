@@ -457,7 +457,7 @@ def main():
     else:
         alg_bytes = 2 * 22223 * 256 * 4 * N
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
-    kernel_name = 'dsgfd_mse_nchw_kernel' if args.criterion == 'mse' else 'dsgfd_kl_kernel'
+    kernel_name = 'dsgfd_mse_nchw_kernel' if args.criterion == 'mse' else 'dsgfd_kl_col_kernel'
     traffic_rec = recorded_traffic(kernel_name, N)
     ms_per_step = elapsed_ms / args.steps
     line = {
@@ -470,7 +470,7 @@ def main():
                    'launch': 'cuda_graph_replay' if graph_ms is not None else 'eager',
                    'graph_policy': graph_policy if graph_ms is not None else None,
                    'cache': f'inputs larger than L2: {2 * N * 22.76:.0f} MB of features read per step vs 126 MB L2'},
-        'roofline': {'bound': 'hbm', 'kernel': 'dsgfd_mse_nchw_kernel' if args.criterion == 'mse' else 'dsgfd_kl_kernel',
+        'roofline': {'bound': 'hbm', 'kernel': 'dsgfd_mse_nchw_kernel' if args.criterion == 'mse' else 'dsgfd_kl_col_kernel',
                      'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                      'frac_of_nominal_8000': achieved / 8000.0, 'peak_source': peak_src,
                      'algorithmic_bytes_per_launch': alg_bytes, 'kernel_ms': kernel_ms,

@@ -5,8 +5,6 @@
 // Cells outside every box have logit 0 for both softmaxes and need no feature bytes; strips without any owned cell
 // contribute exactly 0 and are skipped.  No gradient reaches the student features (target is detached): the only
 // gradient is d loss / d rows.  Algorithmic bytes: read S + read T = 8 B per element (45.51 MB per 800x1333 image).
-#include <stdlib.h>
-
 #include <type_traits>
 
 #include "common.cuh"
@@ -317,7 +315,7 @@ constexpr int kColBlk = 5;          // rows per skippable block
 constexpr int kColBlocks = (kColRows + kColBlk - 1) / kColBlk;
 constexpr int kColTableCap = 3072;  // floats of staged mask rows per CTA
 constexpr int kColMaxPairs = kColTableCap - 3;
-constexpr int kColMaxChunk = 64;    // channels per CTA at most
+constexpr int kColChunk = 32;       // channels per CTA
 
 struct KlColParams {
   DskdLevel levels[DSKD_MAX_LEVELS];
@@ -353,13 +351,15 @@ __device__ __forceinline__ void group_barrier(int group, int threads) {
 #undef DSKD_BAR_CASE
 }
 
+// Registers over occupancy: 3 CTAs of 4 warps per SM (168 registers, no spills of the row arrays) beat 4, 5 and 6 CTAs
+// (128 / 96 / 80 registers, the row arrays partly in local memory): 0.33 / 0.39 / 0.40 / 0.42 ms on the COCO batch.
 template <int MAXW, bool POW2>
-__global__ void __launch_bounds__(32 * MAXW, 16 / MAXW) dsgfd_kl_col_kernel(const __grid_constant__ KlColParams prm) {
+__global__ void __launch_bounds__(32 * MAXW, MAXW == 4 ? 3 : 1) dsgfd_kl_col_kernel(const __grid_constant__ KlColParams prm) {
   __shared__ float rows_s[kColTableCap];   // [channel of the sub-chunk][1 + owner - omin] mask values (/T when exact)
   __shared__ float ex_s[2][MAXW][5][32];   // per warp: local max_s, max_t, sum_s, sum_t, weighted sum (double-buffered)
   __shared__ double red[32];
   __shared__ int orange_s[2];
-  __shared__ int zero_s[kColMaxChunk];     // per staged channel: some mask value is exactly 0 (underflow)
+  __shared__ int zero_s[kColChunk];     // per staged channel: some mask value is exactly 0 (underflow)
   constexpr unsigned kFull = 0xffffffffu;
   constexpr int kPacked = (kColRows + 1) / 2;
   constexpr float kExcluded = -1e30f;      // logit of a row that does not exist (partial parts): e^x == 0, x - y == 0
@@ -666,8 +666,7 @@ extern "C" int dskd_dsgfd_kl_fwd_bwd(const DskdDsgfdKlArgs* a, void* stream) {
   const bool pow2 = frexpf(a->temperature, &texp) == 0.5f;  // T = 2^k: the division by T is an exact scaling
 
   // box masks on levels of at most 16 x kColRows rows: the register-resident column kernel
-  const char* impl = getenv("DSKD_KL_IMPL");
-  if (!cell && max_h <= 16 * kColRows && a->num_pairs <= kColMaxPairs && !(impl && impl[0] == 's')) {
+  if (!cell && max_h <= 16 * kColRows && a->num_pairs <= kColMaxPairs) {
     KlColParams cp;
     cp.num_levels = a->num_levels;
     cp.N = a->N;
@@ -679,8 +678,7 @@ extern "C" int dskd_dsgfd_kl_fwd_bwd(const DskdDsgfdKlArgs* a, void* stream) {
     cp.rows = a->d_rows;
     cp.grad_rows = a->d_grad_rows;
     cp.loss = a->d_loss;
-    const char* ch = getenv("DSKD_KL_CHUNK");
-    cp.chunk = ch ? std::min(kColMaxChunk, std::max(1, atoi(ch))) : 16;
+    cp.chunk = kColChunk;
     const int max_parts = (max_h + kColRows - 1) / kColRows;
     const int maxw = max_parts <= 4 ? 4 : (max_parts <= 8 ? 8 : 16);
     const int nchunks = (a->C + cp.chunk - 1) / cp.chunk;

@@ -127,6 +127,63 @@ def test_dsgfd_decode_v1_kl(cfg, reduction):
     assert all(f.grad is None for f in feats) and all(f.grad is None for f in o_feats)
 
 
+# Level heights that reach every KL kernel configuration: 3 row parts with a short last part (4-warp CTAs), 6 and 10
+# parts (8- and 16-warp CTAs), and a level above 16 x 25 rows (the shared-memory strip kernel).
+KL_TALL = {
+    'parts3': dict(levels=((60, 40), (31, 20), (15, 10), (8, 5)), img_hw=(480, 320)),
+    'parts6': dict(levels=((130, 36), (65, 18), (33, 9), (17, 5)), img_hw=(1040, 288)),
+    'parts10': dict(levels=((230, 33), (115, 17), (58, 9), (29, 5)), img_hw=(1840, 264)),
+    'strips': dict(levels=((420, 9), (210, 5), (105, 3), (53, 2)), img_hw=(3360, 72)),
+}
+
+
+@pytest.mark.parametrize('shape', list(KL_TALL))
+@pytest.mark.parametrize('T', [2.0, 3.0], ids=['T2', 'T3'])
+def test_dsgfd_kl_tall_levels_and_temperatures(shape, T):
+    cpu = synth.make_distill_inputs(num_images=2, num_prev=40, seed=21, channels=40, num_query=60, k_range=(3, 8),
+                                    **KL_TALL[shape])
+    gpu = cpu.to(DEV)
+    mod = dskd_b200.DSGFeatureDistillLoss(criterion='kl', T=T)
+    feats, hs = gpu.clone_student()
+    loss = mod(feats, gpu.teacher_feats, (hs, gpu.hs_teacher), gpu.assignments)
+    loss.backward()
+    o_feats, o_hs = cpu.clone_student()
+    ref = oracle_decode(cpu, crit_oracle('kl', 'sum', 1.0, T), 1, o_feats, o_hs)
+    ref.backward()
+    assert_kl_loss(loss, cpu, crit_oracle('kl', 'sum', 1.0, T), ref)
+    assert_grad(hs.grad, o_hs.grad)
+
+
+def test_dsgfd_kl_mask_values_underflowing_to_zero():
+    """|hs_T - hs_S| spread over hundreds: most of softmax_c underflows to exactly 0 in fp32 (head_il.py:705), the
+    logits of such a channel are 0 inside the box and its gradient comes from the raw teacher feature alone."""
+    cpu = synth.make_distill_inputs(num_images=2, num_prev=40, seed=9, channels=64, **ODD)
+    cpu.hs_student.mul_(150.0)
+    cpu.hs_teacher.mul_(150.0)
+    gpu = cpu.to(DEV)
+    mod = dskd_b200.DSGFeatureDistillLoss(criterion='kl')
+    feats, hs = gpu.clone_student()
+    loss = mod(feats, gpu.teacher_feats, (hs, gpu.hs_teacher), gpu.assignments)
+    loss.backward()
+    o_feats, o_hs = cpu.clone_student()
+    ref = oracle_decode(cpu, crit_oracle('kl'), 1, o_feats, o_hs)
+    ref.backward()
+    assert_kl_loss(loss, cpu, crit_oracle('kl'), ref)
+    # with a nearly one-hot mask the softmax backward cancels to the last bits, in the reference's fp32 as in the
+    # kernel's: hold the kernel to the usual tolerance against the float64 evaluation, or to the error the fp32
+    # reference itself makes against it, whichever is larger
+    _, g64 = oracle_decode_f64(cpu, crit_oracle('kl'))
+    got = hs.grad.detach().cpu().double()
+    err_ref = (o_hs.grad.double() - g64).abs().max()
+    tol = GRAD_RTOL * g64.abs() + 1e-6 * g64.abs().max() + 4 * err_ref
+    assert ((got - g64).abs() <= tol).all(), (float((got - g64).abs().max()), float(err_ref), float(g64.abs().max()))
+    a = cpu.assignments
+    id_pred = torch.nonzero(a['student_labels'] < len(a['prev_labels'])).squeeze(1)
+    rows = torch.softmax((cpu.hs_teacher.reshape(-1, 64)[a['teacher_keepid']]
+                          - cpu.hs_student.reshape(-1, 64)[id_pred]).abs(), 1)
+    assert (rows == 0).any()                                   # the case really contains zero mask values
+
+
 @pytest.mark.parametrize('crit', ['mse', 'kl'])
 def test_dsgfd_decode_v2(crit):
     cpu = synth.make_distill_inputs(num_images=2, num_prev=40, seed=6, channels=64, **SMALL)

@@ -111,6 +111,8 @@ SIGNATURES = {
     'dskd_kd_kl_rows': [vp, vp, i64, i32, i64, f32, vp, f32, vp, vp, vp, vp],
     'dskd_scale_inplace': [vp, i64, vp, vp],
     'dskd_f64_to_f32': [vp, vp, i32, f32, vp],
+    'dskd_msda_forward': [vp, vp, i32, vp, vp, i32, i64, i32, i32, i64, i32, vp, vp],
+    'dskd_msda_backward': [vp, vp, i32, vp, vp, vp, i32, i64, i32, i32, i64, i32, vp, vp, vp, vp],
 }
 
 _lib = None

@@ -4,7 +4,7 @@ box branch) in plain PyTorch.  Architecture anchors in the reference:
   mmdet/models/necks/channel_mapper.py:60-110                                             neck
   mmdet/models/utils/transformer.py:893-1055                                              transformer (+ `info_all`)
   mmdet/models/dense_heads/gfl_deformable_detr_head_il.py:145-281                         branches / forward outputs
-The mmcv `MultiScaleDeformableAttention` CUDA op is replaced by its `grid_sample` formulation.
+The mmcv `MultiScaleDeformableAttention` CUDA op is replaced by dskd_b200/csrc/msda.cu (`harness/msda.py`).
 """
 import copy
 import math
@@ -13,6 +13,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .msda import ms_deform_attn
+
 
 def inverse_sigmoid(x, eps=1e-5):
     x = x.clamp(0, 1)
@@ -20,7 +22,7 @@ def inverse_sigmoid(x, eps=1e-5):
 
 
 class MSDeformAttn(nn.Module):
-    """Multi-scale deformable attention, pure PyTorch (bilinear `grid_sample` per level)."""
+    """Multi-scale deformable attention: projections in PyTorch, the sampling core in `harness/msda.py`."""
 
     def __init__(self, dim=256, heads=8, levels=4, points=4):
         super().__init__()
@@ -49,17 +51,7 @@ class MSDeformAttn(nn.Module):
         weights = self.attention_weights(query).view(N, Lq, h, lv * p).softmax(-1).view(N, Lq, h, lv, p)
         norm = torch.tensor([[w, hh] for hh, w in spatial_shapes], dtype=query.dtype, device=query.device)
         locs = reference_points[:, :, None, :, None, :] + offsets / norm[None, None, None, :, None, :]
-        grids = 2 * locs - 1
-        out = query.new_zeros(N * h, d, Lq)
-        start = 0
-        for l, (hh, ww) in enumerate(spatial_shapes):
-            v = value[:, start:start + hh * ww].permute(0, 2, 3, 1).reshape(N * h, d, hh, ww)
-            g = grids[:, :, :, l].permute(0, 2, 1, 3, 4).reshape(N * h, Lq, p, 2)
-            sampled = F.grid_sample(v, g, mode='bilinear', padding_mode='zeros', align_corners=False)   # [N*h,d,Lq,p]
-            a = weights[:, :, :, l].permute(0, 2, 1, 3).reshape(N * h, 1, Lq, p)
-            out = out + (sampled * a).sum(-1)
-            start += hh * ww
-        out = out.view(N, h * d, Lq).transpose(1, 2)
+        out = ms_deform_attn(value, spatial_shapes, locs, weights)      # CUDA op (csrc/msda.cu)
         return self.output_proj(out)
 
 

@@ -354,6 +354,23 @@ int dskd_lsap_batch_device(const float* d_cost, int32_t num_problems, int32_t N,
                            void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Multi-scale deformable attention: the sampling core of the detector that hosts the losses (next-row 1 harness).
+ * Replaces mmcv's CUDA op `MultiScaleDeformableAttention` that the reference's transformer imports
+ * (mmdet/models/utils/transformer.py:23; mmcv-full pinned by requirements/mminstall.txt:1, not vendored):
+ *   out[n,q,m,:] = sum_{l,p} attn[n,q,m,l,p] * bilinear(value_l[n,:,m,:], loc[n,q,m,l,p,:])
+ * with grid_sample(align_corners=False, zeros) sampling, loc = (x, y) in [0,1] per level.
+ * value [N,S,M,D], loc [N,Lq,M,L,P,2], attn [N,Lq,M,L,P], out / grad_out [N,Lq,M,D]; fp32, contiguous; `levels` is a
+ * HOST array (H, W, cell_offset = first token of the level); L*P <= 16.  The backward zero-fills d_grad_value itself.
+ * ------------------------------------------------------------------------------------------- */
+int dskd_msda_forward(const float* d_value, const DskdLevel* levels, int32_t num_levels, const float* d_loc,
+                      const float* d_attn, int32_t N, int64_t S, int32_t M, int32_t D, int64_t Lq, int32_t P,
+                      float* d_out, void* stream);
+int dskd_msda_backward(const float* d_value, const DskdLevel* levels, int32_t num_levels, const float* d_loc,
+                       const float* d_attn, const float* d_grad_out, int32_t N, int64_t S, int32_t M, int32_t D,
+                       int64_t Lq, int32_t P, float* d_grad_value, float* d_grad_loc, float* d_grad_attn,
+                       void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Registry loss modules (mse_loss.py, kd_loss.py, utils.py) -- generic tensors
  * ------------------------------------------------------------------------------------------- */
 /* elementwise (pred-target)^2 * weight (weight may be NULL); d_elem (n) optional; d_sum[1] (double,

@@ -6,7 +6,7 @@
 // weights and summed over levels and points (mmcv `multi_scale_deformable_attn_pytorch`); the torch restatement of that
 // is dskd_b200/harness/model.py `msda_torch` and is what tests/test_gpu_msda.py compares against.
 //
-// One warp per (image, query, head); the lanes are the head's channels (D = 32 for 256 / 8), so every bilinear tap is
+// One warp per (image, query, head), a CTA = 8 consecutive queries of one head; the lanes are the head's channels (D = 32 for 256 / 8), so every bilinear tap is
 // one coalesced 128 B load (forward) or one coalesced 128 B red.global (backward) and the value tensor of an image
 // (22.8 MB at 800x1333) stays in L2.  The 32 sampling coordinates and 16 weights of the warp's query arrive as one
 // coalesced load each (lane = coordinate) and are broadcast by shuffles.  Backward: the per-point sums over channels
@@ -53,13 +53,15 @@ __device__ __forceinline__ void warp_reduce_scatter16(float (&v)[kMsdaMaxPoints]
 template <bool BWD>
 __global__ void __launch_bounds__(32 * kMsdaWarps) msda_kernel(const __grid_constant__ MsdaParams prm) {
   const int lane = threadIdx.x & 31;
-  const int64_t wid = (int64_t)blockIdx.x * kMsdaWarps + (threadIdx.x >> 5);  // (n, q, m) flattened
-  const int64_t total = (int64_t)prm.N * prm.Lq * prm.M;
-  if (wid >= total) return;
-  const int m = (int)(wid % prm.M);
-  const int64_t nq = wid / prm.M;
-  const int n = (int)(nq / prm.Lq);
+  // the warps of a CTA are consecutive queries of ONE head: in the encoder these are neighbouring cells whose sampling
+  // footprints overlap, so most of their taps hit L1
+  const int64_t qblocks = (prm.Lq + kMsdaWarps - 1) / kMsdaWarps;
+  const int64_t q = (blockIdx.x % qblocks) * kMsdaWarps + (threadIdx.x >> 5);
+  if (q >= prm.Lq) return;
+  const int nm = (int)(blockIdx.x / qblocks);
+  const int m = nm % prm.M, n = nm / prm.M;
   const int LP = prm.LP, D = prm.D, M = prm.M;
+  const int64_t wid = ((int64_t)n * prm.Lq + q) * M + m;  // (n, q, m) flattened
   // the query's sampling coordinates (lane = coordinate) and weights (lane = point)
   const float locv = lane < 2 * LP ? __ldg(prm.loc + wid * (2 * LP) + lane) : 0.f;
   const float attv = lane < LP ? __ldg(prm.attn + wid * LP + lane) : 0.f;
@@ -172,7 +174,7 @@ extern "C" int dskd_msda_forward(const float* d_value, const DskdLevel* levels, 
   const int64_t warps = (int64_t)N * Lq * M;
   if (warps == 0) return DSKD_OK;
   p.out = d_out;
-  msda_kernel<false><<<(unsigned)ceil_div(warps, kMsdaWarps), 32 * kMsdaWarps, 0, as_stream(stream)>>>(p);
+  msda_kernel<false><<<(unsigned)(ceil_div(Lq, kMsdaWarps) * N * M), 32 * kMsdaWarps, 0, as_stream(stream)>>>(p);
   DSKD_LAUNCH_OK("msda_kernel<fwd>");
   return DSKD_OK;
 }
@@ -193,7 +195,7 @@ extern "C" int dskd_msda_backward(const float* d_value, const DskdLevel* levels,
   p.grad_value = d_grad_value;
   p.grad_loc = d_grad_loc;
   p.grad_attn = d_grad_attn;
-  msda_kernel<true><<<(unsigned)ceil_div(warps, kMsdaWarps), 32 * kMsdaWarps, 0, st>>>(p);
+  msda_kernel<true><<<(unsigned)(ceil_div(Lq, kMsdaWarps) * N * M), 32 * kMsdaWarps, 0, st>>>(p);
   DSKD_LAUNCH_OK("msda_kernel<bwd>");
   return DSKD_OK;
 }

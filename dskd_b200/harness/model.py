@@ -16,6 +16,9 @@ import torch.nn.functional as F
 from .msda import ms_deform_attn
 
 
+_NORM_CACHE = {}
+
+
 def inverse_sigmoid(x, eps=1e-5):
     x = x.clamp(0, 1)
     return torch.log(x.clamp(min=eps) / (1 - x).clamp(min=eps))
@@ -49,7 +52,11 @@ class MSDeformAttn(nn.Module):
         value = self.value_proj(value).view(N, S, h, d)
         offsets = self.sampling_offsets(query).view(N, Lq, h, lv, p, 2)
         weights = self.attention_weights(query).view(N, Lq, h, lv * p).softmax(-1).view(N, Lq, h, lv, p)
-        norm = torch.tensor([[w, hh] for hh, w in spatial_shapes], dtype=query.dtype, device=query.device)
+        key = (tuple(map(tuple, spatial_shapes)), query.device, query.dtype)
+        norm = _NORM_CACHE.get(key)
+        if norm is None:   # one small host->device copy per geometry instead of one per layer call
+            norm = torch.tensor([[w, hh] for hh, w in spatial_shapes], dtype=query.dtype, device=query.device)
+            _NORM_CACHE[key] = norm
         locs = reference_points[:, :, None, :, None, :] + offsets / norm[None, None, None, :, None, :]
         out = ms_deform_attn(value, spatial_shapes, locs, weights)      # CUDA op (csrc/msda.cu)
         return self.output_proj(out)

@@ -52,19 +52,18 @@ def detection_losses(cls, box70, targets, num_classes=80, reg_max=16, img_wh=Non
     labels, bt, bw = targets['labels'], targets['bbox_targets'], targets['bbox_weights']
     wh = integral_average(box70[:, 2:], reg_max)
     pred = torch.cat((box70[:, :2], wh), 1)
-    pos = torch.nonzero(labels < num_classes).squeeze(1)
-    num_pos = max(float(pos.numel()), 1.0)
-    score = cls.new_zeros(labels.shape)
-    if pos.numel():
-        score[pos] = _iou_giou(_cxcywh_to_xyxy(pred[pos]), _cxcywh_to_xyxy(bt[pos]))[0].detach()
+    # dense, mask-based evaluation: no nonzero() / host sync per decoder layer (the reference indexes `pos_inds`)
+    pos = labels < num_classes                                                     # [M] bool
+    num_pos = pos.sum().clamp(min=1).to(cls.dtype)
+    iou = _iou_giou(_cxcywh_to_xyxy(pred), _cxcywh_to_xyxy(bt))[0].detach()
+    score = torch.where(pos, iou, torch.zeros_like(iou))                           # IoU target of the positives
     # QualityFocalLoss
     sig = cls.sigmoid()
-    loss_cls = F.binary_cross_entropy_with_logits(cls, torch.zeros_like(cls), reduction='none') * sig.pow(2)
-    if pos.numel():
-        pl = labels[pos]
-        sf = score[pos] - sig[pos, pl]
-        loss_cls[pos, pl] = F.binary_cross_entropy_with_logits(cls[pos, pl], score[pos], reduction='none') * sf.abs().pow(2)
-    loss_cls = 2.0 * loss_cls.sum() / num_pos
+    neg_term = F.binary_cross_entropy_with_logits(cls, torch.zeros_like(cls), reduction='none') * sig.pow(2)
+    onehot = pos[:, None] & (labels[:, None] == torch.arange(cls.shape[1], device=cls.device)[None, :])
+    tgt = score[:, None].expand_as(cls)
+    pos_term = F.binary_cross_entropy_with_logits(cls, tgt, reduction='none') * (tgt - sig).abs().pow(2)
+    loss_cls = 2.0 * torch.where(onehot, pos_term, neg_term).sum() / num_pos
     factor = img_wh
     giou = _iou_giou(_cxcywh_to_xyxy(pred) * factor, _cxcywh_to_xyxy(bt) * factor)[1]
     loss_iou = 2.0 * ((1 - giou) * bw[:, 0]).sum() / num_pos
@@ -125,8 +124,9 @@ class IncrementalTrainStep:
         img_shapes = [(H, W)] * N
         with torch.no_grad():
             t = self.teacher(img)
+        s = self.student(img)      # queued behind the teacher before the keep-ids' one host sync drains the stream
+        with torch.no_grad():
             tinfo = teacher_info_from_outputs(t['cls'][-1], t['box'][-1], img_shapes, score_thr=0.3, max_per_img=100)
-        s = self.student(img)
         # hard + teacher-first pseudo labels (head_il.py:462-465)
         all_b = [torch.cat([tb, gb]) for tb, gb in zip(tinfo['pred_bboxes'], gt_bboxes)]
         all_l = [torch.cat([tl, gl]) for tl, gl in zip(tinfo['pred_labels'], gt_labels)]

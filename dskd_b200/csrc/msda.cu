@@ -9,7 +9,8 @@
 // One warp per (image, query, head), a CTA = 8 consecutive queries of one head; the lanes are the head's channels (D = 32 for 256 / 8), so every bilinear tap is
 // one coalesced 128 B load (forward) or one coalesced 128 B red.global (backward) and the value tensor of an image
 // (22.8 MB at 800x1333) stays in L2.  The 32 sampling coordinates and 16 weights of the warp's query arrive as one
-// coalesced load each (lane = coordinate) and are broadcast by shuffles.  Backward: the per-point sums over channels
+// coalesced load each (lane = coordinate); lane k prepares point k (tap offset, fractions, in-map bits) once and
+// the warp takes it by shuffles instead of repeating the coordinate arithmetic in 32 lanes.  Backward: the per-point sums over channels
 // (d attention weight, d x, d y: 48 values per warp) are reduced with a transposing butterfly (16 shuffles per 16
 // values instead of 80) and leave as coalesced stores.
 #include "common.cuh"
@@ -52,6 +53,14 @@ __device__ __forceinline__ void warp_reduce_scatter16(float (&v)[kMsdaMaxPoints]
 
 template <bool BWD>
 __global__ void __launch_bounds__(32 * kMsdaWarps) msda_kernel(const __grid_constant__ MsdaParams prm) {
+  __shared__ int sH[DSKD_MAX_LEVELS], sW[DSKD_MAX_LEVELS], sStart[DSKD_MAX_LEVELS];
+  if (threadIdx.x < DSKD_MAX_LEVELS) {
+    const int l = min((int)threadIdx.x, prm.num_levels - 1);
+    sH[threadIdx.x] = prm.H[l];
+    sW[threadIdx.x] = prm.W[l];
+    sStart[threadIdx.x] = (int)prm.start[l];
+  }
+  __syncthreads();
   const int lane = threadIdx.x & 31;
   // the warps of a CTA are consecutive queries of ONE head: in the encoder these are neighbouring cells whose sampling
   // footprints overlap, so most of their taps hit L1
@@ -65,6 +74,31 @@ __global__ void __launch_bounds__(32 * kMsdaWarps) msda_kernel(const __grid_cons
   // the query's sampling coordinates (lane = coordinate) and weights (lane = point)
   const float locv = lane < 2 * LP ? __ldg(prm.loc + wid * (2 * LP) + lane) : 0.f;
   const float attv = lane < LP ? __ldg(prm.attn + wid * LP + lane) : 0.f;
+  // lane k < LP prepares point k once for the whole warp: cell offset of the top-left tap, the fractions, which of the
+  // four taps lie inside the map (grid_sample(align_corners=False, zeros): pixel = loc * size - 0.5)
+  int p_off = 0, p_w = 1;
+  unsigned p_mask = 0;
+  float p_fx = 0.f, p_fy = 0.f;
+  {
+    const float px = __shfl_sync(0xffffffffu, locv, (2 * lane) & 31);
+    const float py = __shfl_sync(0xffffffffu, locv, (2 * lane + 1) & 31);
+    if (lane < LP) {
+      const int l = lane / prm.P;
+      const int H = sH[l], W = sW[l];
+      const float ix = px * (float)W - 0.5f, iy = py * (float)H - 0.5f;
+      // far outside (or not finite): nothing to sample, and the int conversion stays defined
+      if (ix > -1.f && iy > -1.f && ix < (float)W && iy < (float)H) {
+        const float fx0 = floorf(ix), fy0 = floorf(iy);
+        const int x0 = (int)fx0, y0 = (int)fy0;
+        p_fx = ix - fx0;
+        p_fy = iy - fy0;
+        const bool xl = x0 >= 0, xh = x0 + 1 < W, yl = y0 >= 0, yh = y0 + 1 < H;
+        p_mask = (yl && xl ? 1u : 0u) | (yl && xh ? 2u : 0u) | (yh && xl ? 4u : 0u) | (yh && xh ? 8u : 0u);
+        p_off = sStart[l] + y0 * W + x0;
+      }
+      p_w = W;
+    }
+  }
   const float* __restrict__ vbase = prm.value + ((int64_t)n * prm.S * M + m) * D;
   float* __restrict__ gvbase = BWD ? prm.grad_value + ((int64_t)n * prm.S * M + m) * D : nullptr;
   const int64_t tok = (int64_t)M * D;  // stride between tokens of one head
@@ -82,23 +116,16 @@ __global__ void __launch_bounds__(32 * kMsdaWarps) msda_kernel(const __grid_cons
 #pragma unroll
     for (int k = 0; k < kMsdaMaxPoints; ++k) {
       if (k < LP) {  // warp-uniform
-        const int l = k / prm.P;
-        const int H = prm.H[l], W = prm.W[l];
+        const unsigned mask = __shfl_sync(0xffffffffu, p_mask, k);
+        if (mask == 0u) continue;  // the point lies outside its map
         const float a = __shfl_sync(0xffffffffu, attv, k);
-        // grid_sample(align_corners=False): pixel = loc * size - 0.5
-        const float ix = __shfl_sync(0xffffffffu, locv, 2 * k) * (float)W - 0.5f;
-        const float iy = __shfl_sync(0xffffffffu, locv, 2 * k + 1) * (float)H - 0.5f;
-        const float fx0 = floorf(ix), fy0 = floorf(iy);
-        // far outside (or not finite): nothing to sample, and the int conversion below stays defined
-        if (!(ix > -1.f && iy > -1.f && ix < (float)W && iy < (float)H)) continue;
-        const int x0 = (int)fx0, y0 = (int)fy0;
-        const float fx = ix - fx0, fy = iy - fy0;
-        const bool xl = x0 >= 0, xh = x0 + 1 < W, yl = y0 >= 0, yh = y0 + 1 < H;
-        const float* __restrict__ v = vbase + (prm.start[l] + (int64_t)y0 * W + x0) * tok + dd;
-        const float v00 = (yl && xl) ? __ldg(v) : 0.f;
-        const float v01 = (yl && xh) ? __ldg(v + tok) : 0.f;
-        const float v10 = (yh && xl) ? __ldg(v + (int64_t)W * tok) : 0.f;
-        const float v11 = (yh && xh) ? __ldg(v + (int64_t)(W + 1) * tok) : 0.f;
+        const float fx = __shfl_sync(0xffffffffu, p_fx, k), fy = __shfl_sync(0xffffffffu, p_fy, k);
+        const int off = __shfl_sync(0xffffffffu, p_off, k), W = __shfl_sync(0xffffffffu, p_w, k);
+        const float* __restrict__ v = vbase + (int64_t)off * tok + dd;
+        const float v00 = (mask & 1u) ? __ldg(v) : 0.f;
+        const float v01 = (mask & 2u) ? __ldg(v + tok) : 0.f;
+        const float v10 = (mask & 4u) ? __ldg(v + (int64_t)W * tok) : 0.f;
+        const float v11 = (mask & 8u) ? __ldg(v + (int64_t)(W + 1) * tok) : 0.f;
         const float w00 = (1.f - fx) * (1.f - fy), w01 = fx * (1.f - fy), w10 = (1.f - fx) * fy, w11 = fx * fy;
         const float sampled = w00 * v00 + w01 * v01 + w10 * v10 + w11 * v11;
         if (!BWD) {
@@ -109,11 +136,11 @@ __global__ void __launch_bounds__(32 * kMsdaWarps) msda_kernel(const __grid_cons
           gx[k] = fmaf(ag, (1.f - fy) * (v01 - v00) + fy * (v11 - v10), gx[k]);
           gy[k] = fmaf(ag, (1.f - fx) * (v10 - v00) + fx * (v11 - v01), gy[k]);
           if (act) {
-            float* __restrict__ g = gvbase + (prm.start[l] + (int64_t)y0 * W + x0) * tok + dd;
-            if (yl && xl) atomicAdd(g, ag * w00);
-            if (yl && xh) atomicAdd(g + tok, ag * w01);
-            if (yh && xl) atomicAdd(g + (int64_t)W * tok, ag * w10);
-            if (yh && xh) atomicAdd(g + (int64_t)(W + 1) * tok, ag * w11);
+            float* __restrict__ g = gvbase + (int64_t)off * tok + dd;
+            if (mask & 1u) atomicAdd(g, ag * w00);
+            if (mask & 2u) atomicAdd(g + tok, ag * w01);
+            if (mask & 4u) atomicAdd(g + (int64_t)W * tok, ag * w10);
+            if (mask & 8u) atomicAdd(g + (int64_t)(W + 1) * tok, ag * w11);
           }
         }
       }
@@ -129,7 +156,7 @@ __global__ void __launch_bounds__(32 * kMsdaWarps) msda_kernel(const __grid_cons
       const int l = k / prm.P;
       if ((lane & 1) == 0) prm.grad_attn[wid * LP + k] = ga[0];
       // d pixel / d loc = size; lane even writes x, lane odd writes y: one coalesced 128 B store
-      prm.grad_loc[wid * (2 * LP) + lane] = (lane & 1) ? gy[0] * (float)prm.H[l] : gx[0] * (float)prm.W[l];
+      prm.grad_loc[wid * (2 * LP) + lane] = (lane & 1) ? gy[0] * (float)sH[l] : gx[0] * (float)sW[l];
     }
   }
 }
@@ -150,6 +177,7 @@ static int msda_fill(MsdaParams& p, const char* who, const float* d_value, const
     p.start[l] = cells;
     cells += (int64_t)levels[l].H * levels[l].W;
   }
+  DSKD_REQUIRE(S < (1ll << 31), "%s: S above 2^31 tokens", who);
   DSKD_REQUIRE(cells == S, "%s: the levels hold %lld tokens, S is %lld", who, (long long)cells, (long long)S);
   p.num_levels = num_levels;
   p.P = P;

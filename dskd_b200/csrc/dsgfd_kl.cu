@@ -331,6 +331,7 @@ struct KlColParams {
   float temperature, inv_temperature;
   int64_t cells_per_image;
   const int* owner;
+  const float* cell_weight;    // per-cell mask weights instead of owners (CELL kernels)
   const float* rows;
   float* grad_rows;
   double* loss;
@@ -353,7 +354,9 @@ __device__ __forceinline__ void group_barrier(int group, int threads) {
 
 // Registers over occupancy: 3 CTAs of 4 warps per SM (168 registers, no spills of the row arrays) beat 4, 5 and 6 CTAs
 // (128 / 96 / 80 registers, the row arrays partly in local memory): 0.33 / 0.39 / 0.40 / 0.42 ms on the COCO batch.
-template <int MAXW, bool POW2>
+// CELL: per-cell mask weights (sg_out / fg_only) instead of box owners: the lane keeps the weights of its rows in
+// registers, there is no mask table and no gradient.
+template <int MAXW, bool POW2, bool CELL>
 __global__ void __launch_bounds__(32 * MAXW, MAXW == 4 ? 3 : 1) dsgfd_kl_col_kernel(const __grid_constant__ KlColParams prm) {
   __shared__ float rows_s[kColTableCap];   // [channel of the sub-chunk][1 + owner - omin] mask values (/T when exact)
   __shared__ float ex_s[2][MAXW][5][32];   // per warp: local max_s, max_t, sum_s, sum_t, weighted sum (double-buffered)
@@ -394,6 +397,7 @@ __global__ void __launch_bounds__(32 * MAXW, MAXW == 4 ? 3 : 1) dsgfd_kl_col_ker
   __syncthreads();
   const int64_t cell0 = (int64_t)img * prm.cells_per_image + prm.levels[lvl].cell_offset + (int64_t)row0 * W + wc;
   unsigned moffp[kPacked];  // two 16-bit byte offsets per register
+  float mw[kColRows];       // CELL: the mask weights of this lane's rows (/T when exact)
   unsigned fb = 0;          // rows after which the accumulated gradient of a run is flushed
   bool part_any;
   unsigned rowany;          // rows with a box in some column of the warp
@@ -404,7 +408,13 @@ __global__ void __launch_bounds__(32 * MAXW, MAXW == 4 ? 3 : 1) dsgfd_kl_col_ker
 #pragma unroll
     for (int r = 0; r < kColRows; ++r) {
       int o = -1;
-      if (col_ok && r < nrows) o = __ldg(prm.owner + cell0 + r * uW);
+      if (CELL) {
+        const float wv = (col_ok && r < nrows) ? __ldg(prm.cell_weight + cell0 + r * uW) : 0.f;
+        mw[r] = POW2 ? wv * prm.inv_temperature : wv;
+        o = wv != 0.f ? 0 : -1;
+      } else if (col_ok && r < nrows) {
+        o = __ldg(prm.owner + cell0 + r * uW);
+      }
       own[r] = o;
       if (o >= 0) { lo = min(lo, o); hi = max(hi, o); }
     }
@@ -425,7 +435,7 @@ __global__ void __launch_bounds__(32 * MAXW, MAXW == 4 ? 3 : 1) dsgfd_kl_col_ker
 #pragma unroll
     for (int r = 0; r < kColRows; ++r) {
       const int nx = (r + 1 < kColRows) ? own[r + 1] : -1;
-      if (own[r] >= 0 && nx != own[r]) fb |= 1u << r;
+      if (!CELL && own[r] >= 0 && nx != own[r]) fb |= 1u << r;
     }
 #pragma unroll
     for (int k = 0; k < kPacked; ++k) {
@@ -452,7 +462,7 @@ __global__ void __launch_bounds__(32 * MAXW, MAXW == 4 ? 3 : 1) dsgfd_kl_col_ker
 
   const float kLog2e = 1.4426950408889634f;
   const float gcoef = scale * Temp / (float)H;  // d loss / d pred = scale * (T/H) * (p - t)
-  const bool want_grad = prm.grad_rows != nullptr;
+  const bool want_grad = !CELL && prm.grad_rows != nullptr;
   const int c_begin = chunk * prm.chunk, c_end = min(C, c_begin + prm.chunk);
   double kl_total = 0.0;
   int par = 0;
@@ -499,7 +509,7 @@ __global__ void __launch_bounds__(32 * MAXW, MAXW == 4 ? 3 : 1) dsgfd_kl_col_ker
       ml_s = nskip_i > 0 ? 0.f : -INFINITY;
       ml_t = ml_s;
       DSKD_FOR_ROWS_ON(
-        const float m = DSKD_MTAB(DSKD_MOFF(r));
+        const float m = CELL ? mw[r] : DSKD_MTAB(DSKD_MOFF(r));
         float x = s[r] * m; float y = t[r] * m;
         if (!POW2) { x = __fdiv_rn(x, Temp); y = __fdiv_rn(y, Temp); }
         if (!FULL) { x = r < nrows ? x : kExcluded; y = r < nrows ? y : kExcluded; }
@@ -597,24 +607,27 @@ __global__ void __launch_bounds__(32 * MAXW, MAXW == 4 ? 3 : 1) dsgfd_kl_col_ker
 
   for (int sc = c_begin; sc < c_end; sc += chs) {
     const int nch = min(chs, c_end - sc);
-    __syncthreads();  // the readers of the previous sub-chunk are done
-    for (int cc = tid; cc < nch; cc += 32 * MAXW) {
-      rows_s[cc * nstride] = 0.f;  // cells outside boxes
-      zero_s[cc] = 0;
+    if (!CELL) {
+      __syncthreads();  // the readers of the previous sub-chunk are done
+      for (int cc = tid; cc < nch; cc += 32 * MAXW) {
+        rows_s[cc * nstride] = 0.f;  // cells outside boxes
+        zero_s[cc] = 0;
+      }
+      __syncthreads();
+      for (int i = tid; i < nown * nch; i += 32 * MAXW) {
+        const int o = i / nch, cc = i - o * nch;
+        float m = __ldg(prm.rows + (int64_t)(omin + o) * C + sc + cc);
+        if (POW2) m *= prm.inv_temperature;
+        rows_s[cc * nstride + o + 1] = m;
+        if (m == 0.f) zero_s[cc] = 1;
+      }
+      __syncthreads();
     }
-    __syncthreads();
-    for (int i = tid; i < nown * nch; i += 32 * MAXW) {
-      const int o = i / nch, cc = i - o * nch;
-      float m = __ldg(prm.rows + (int64_t)(omin + o) * C + sc + cc);
-      if (POW2) m *= prm.inv_temperature;
-      rows_s[cc * nstride + o + 1] = m;
-      if (m == 0.f) zero_s[cc] = 1;
-    }
-    __syncthreads();
     if (active) {
       for (int cc = group; cc < nch; cc += groups) {
-        if (nrows == kColRows) channel(std::true_type{}, sc + cc, rows_s + cc * nstride, zero_s[cc] != 0);
-        else channel(std::false_type{}, sc + cc, rows_s + cc * nstride, zero_s[cc] != 0);
+        const bool zero_any = !CELL && zero_s[cc] != 0;
+        if (nrows == kColRows) channel(std::true_type{}, sc + cc, rows_s + cc * nstride, zero_any);
+        else channel(std::false_type{}, sc + cc, rows_s + cc * nstride, zero_any);
       }
     }
   }
@@ -666,7 +679,7 @@ extern "C" int dskd_dsgfd_kl_fwd_bwd(const DskdDsgfdKlArgs* a, void* stream) {
   const bool pow2 = frexpf(a->temperature, &texp) == 0.5f;  // T = 2^k: the division by T is an exact scaling
 
   // box masks on levels of at most 16 x kColRows rows: the register-resident column kernel
-  if (!cell && max_h <= 16 * kColRows && a->num_pairs <= kColMaxPairs) {
+  if (max_h <= 16 * kColRows && (cell || a->num_pairs <= kColMaxPairs)) {
     KlColParams cp;
     cp.num_levels = a->num_levels;
     cp.N = a->N;
@@ -675,6 +688,7 @@ extern "C" int dskd_dsgfd_kl_fwd_bwd(const DskdDsgfdKlArgs* a, void* stream) {
     cp.inv_temperature = 1.f / a->temperature;
     cp.cells_per_image = a->cells_per_image;
     cp.owner = a->d_owner;
+    cp.cell_weight = a->d_cell_weight;
     cp.rows = a->d_rows;
     cp.grad_rows = a->d_grad_rows;
     cp.loss = a->d_loss;
@@ -695,16 +709,20 @@ extern "C" int dskd_dsgfd_kl_fwd_bwd(const DskdDsgfdKlArgs* a, void* stream) {
       blocks += cp.wtiles[l] * nchunks * a->N;
     }
     cp.block_start[a->num_levels] = blocks;
-    if (maxw == 4) {
-      if (pow2) dsgfd_kl_col_kernel<4, true><<<blocks, 128, 0, st>>>(cp);
-      else dsgfd_kl_col_kernel<4, false><<<blocks, 128, 0, st>>>(cp);
-    } else if (maxw == 8) {
-      if (pow2) dsgfd_kl_col_kernel<8, true><<<blocks, 256, 0, st>>>(cp);
-      else dsgfd_kl_col_kernel<8, false><<<blocks, 256, 0, st>>>(cp);
-    } else {
-      if (pow2) dsgfd_kl_col_kernel<16, true><<<blocks, 512, 0, st>>>(cp);
-      else dsgfd_kl_col_kernel<16, false><<<blocks, 512, 0, st>>>(cp);
-    }
+#define DSKD_COL_LAUNCH(MW)                                                                        \
+  do {                                                                                             \
+    if (cell) {                                                                                    \
+      if (pow2) dsgfd_kl_col_kernel<MW, true, true><<<blocks, 32 * MW, 0, st>>>(cp);               \
+      else dsgfd_kl_col_kernel<MW, false, true><<<blocks, 32 * MW, 0, st>>>(cp);                   \
+    } else {                                                                                       \
+      if (pow2) dsgfd_kl_col_kernel<MW, true, false><<<blocks, 32 * MW, 0, st>>>(cp);              \
+      else dsgfd_kl_col_kernel<MW, false, false><<<blocks, 32 * MW, 0, st>>>(cp);                  \
+    }                                                                                              \
+  } while (0)
+    if (maxw == 4) DSKD_COL_LAUNCH(4);
+    else if (maxw == 8) DSKD_COL_LAUNCH(8);
+    else DSKD_COL_LAUNCH(16);
+#undef DSKD_COL_LAUNCH
     DSKD_LAUNCH_OK("dsgfd_kl_col_kernel");
     return DSKD_OK;
   }

@@ -526,6 +526,7 @@ __global__ void __launch_bounds__(32 * MAXW, MAXW == 4 ? 3 : 1) dsgfd_kl_col_ker
         const float f = fast_ex2(fmaf(t[r], kLog2e, nmt));
         if (r & 1) { ss1 += e; st1 += f; ws1 = fmaf(e, s[r] - t[r], ws1); }
         else { ss0 += e; st0 += f; ws0 = fmaf(e, s[r] - t[r], ws0); }
+        s[r] = e;  // the student logit is not needed again: keep e^(xs - local max) for the gradient sweep
       )
       ss = fmaf(nskip, fast_ex2(nms), ss0 + ss1);
       st = fmaf(nskip, fast_ex2(nmt), st0 + st1);
@@ -569,14 +570,18 @@ __global__ void __launch_bounds__(32 * MAXW, MAXW == 4 ? 3 : 1) dsgfd_kl_col_ker
     if (want_grad && part_any) {
       const float rs = __fdividef(1.f, sum_s), rt = __fdividef(1.f, sum_t);
       const float nms = -Ms * kLog2e, nmt = -Mt * kLog2e;
+      // s[r] holds e^(xs - local max) since sweep B: t_h = s[r] * e^(local max - max) / sum_s
+      const float cs = fast_ex2(fmaf(ml_s, kLog2e, nms)) * rs;
       float* __restrict__ grow = prm.grad_rows + (int64_t)(omin - 1) * C + c;
       float acc = 0.f;
       DSKD_FOR_ROWS_ON(
         const float pt = fast_ex2(fmaf(t[r], kLog2e, nmt)) * rt;
-        const float d = fmaf(-fast_ex2(fmaf(s[r], kLog2e, nms)), rs, pt);
+        const float d = fmaf(-s[r], cs, pt);
         acc = fmaf(t[r], d, acc);
-        if (anyfb & (1u << r)) {  // warp-uniform
-          if (fb & (1u << r)) {
+        if (anyfb & (1u << r)) {  // warp-uniform: most rows end no run in any lane
+          unsigned fbv;           // (opaque copy: keeps the uniform test from being folded into the per-lane one)
+          asm volatile("mov.u32 %0, %1;" : "=r"(fbv) : "r"(fb));
+          if (fbv & (1u << r)) {
             const unsigned off = DSKD_MOFF(r);
             const float m = DSKD_MTAB(off);
             // m == 0 (underflow): the run is handled below from the raw teacher feature

@@ -573,11 +573,15 @@ __global__ void __launch_bounds__(32 * MAXW, MAXW == 4 ? 3 : 1) dsgfd_kl_col_ker
       // s[r] holds e^(xs - local max) since sweep B: t_h = s[r] * e^(local max - max) / sum_s
       const float cs = fast_ex2(fmaf(ml_s, kLog2e, nms)) * rs;
       float* __restrict__ grow = prm.grad_rows + (int64_t)(omin - 1) * C + c;
-      float acc = 0.f;
+      // first every row's term T_h (p_h - t_h) * mask / T, branch-free (the exponentials of all rows overlap) ...
       DSKD_FOR_ROWS_ON(
         const float pt = fast_ex2(fmaf(t[r], kLog2e, nmt)) * rt;
-        const float d = fmaf(-s[r], cs, pt);
-        acc = fmaf(t[r], d, acc);
+        s[r] = t[r] * fmaf(-s[r], cs, pt);
+      )
+      // ... then the running sum down the rows; a run of one owner ends where the owner of the next row differs
+      float acc = 0.f;
+      DSKD_FOR_ROWS_ON(
+        acc += s[r];
         if (anyfb & (1u << r)) {  // warp-uniform: most rows end no run in any lane
           unsigned fbv;           // (opaque copy: keeps the uniform test from being folded into the per-lane one)
           asm volatile("mov.u32 %0, %1;" : "=r"(fbv) : "r"(fb));

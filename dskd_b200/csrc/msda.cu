@@ -94,14 +94,16 @@ __global__ void __launch_bounds__(32 * kMsdaWarps) msda_kernel(const __grid_cons
         p_fy = iy - fy0;
         const bool xl = x0 >= 0, xh = x0 + 1 < W, yl = y0 >= 0, yh = y0 + 1 < H;
         p_mask = (yl && xl ? 1u : 0u) | (yl && xh ? 2u : 0u) | (yh && xl ? 4u : 0u) | (yh && xh ? 8u : 0u);
-        p_off = sStart[l] + y0 * W + x0;
+        p_off = (sStart[l] + y0 * W + x0) * (M * D) * 4;  // BYTES inside one image's value tensor: below 2^32 (host check)
       }
-      p_w = W;
+      p_w = W * (M * D) * 4;
     }
   }
   const float* __restrict__ vbase = prm.value + ((int64_t)n * prm.S * M + m) * D;
   float* __restrict__ gvbase = BWD ? prm.grad_value + ((int64_t)n * prm.S * M + m) * D : nullptr;
-  const int64_t tok = (int64_t)M * D;  // stride between tokens of one head
+  const unsigned tokb = (unsigned)(M * D) * 4u;  // bytes between tokens of one head
+  const char* __restrict__ vb = reinterpret_cast<const char*>(vbase);
+  char* __restrict__ gb = reinterpret_cast<char*>(gvbase);
   float ga[kMsdaMaxPoints], gx[kMsdaMaxPoints], gy[kMsdaMaxPoints];
   if (BWD) {
 #pragma unroll
@@ -120,12 +122,16 @@ __global__ void __launch_bounds__(32 * kMsdaWarps) msda_kernel(const __grid_cons
         if (mask == 0u) continue;  // the point lies outside its map
         const float a = __shfl_sync(0xffffffffu, attv, k);
         const float fx = __shfl_sync(0xffffffffu, p_fx, k), fy = __shfl_sync(0xffffffffu, p_fy, k);
-        const int off = __shfl_sync(0xffffffffu, p_off, k), W = __shfl_sync(0xffffffffu, p_w, k);
-        const float* __restrict__ v = vbase + (int64_t)off * tok + dd;
-        const float v00 = (mask & 1u) ? __ldg(v) : 0.f;
-        const float v01 = (mask & 2u) ? __ldg(v + tok) : 0.f;
-        const float v10 = (mask & 4u) ? __ldg(v + (int64_t)W * tok) : 0.f;
-        const float v11 = (mask & 8u) ? __ldg(v + (int64_t)(W + 1) * tok) : 0.f;
+        // 32-bit element offsets from the slice base: one 64-bit add per tap
+        // 32-bit byte offsets from the slice base (zero-extended: a tap outside the map is never dereferenced)
+        const unsigned off = (unsigned)__shfl_sync(0xffffffffu, p_off, k) + (unsigned)dd * 4u;
+        const unsigned wtok = (unsigned)__shfl_sync(0xffffffffu, p_w, k);
+#define DSKD_TAP(o) (*reinterpret_cast<const float*>(vb + (size_t)(o)))
+        const float v00 = (mask & 1u) ? __ldg(&DSKD_TAP(off)) : 0.f;
+        const float v01 = (mask & 2u) ? __ldg(&DSKD_TAP(off + tokb)) : 0.f;
+        const float v10 = (mask & 4u) ? __ldg(&DSKD_TAP(off + wtok)) : 0.f;
+        const float v11 = (mask & 8u) ? __ldg(&DSKD_TAP(off + wtok + tokb)) : 0.f;
+#undef DSKD_TAP
         const float w00 = (1.f - fx) * (1.f - fy), w01 = fx * (1.f - fy), w10 = (1.f - fx) * fy, w11 = fx * fy;
         const float sampled = w00 * v00 + w01 * v01 + w10 * v10 + w11 * v11;
         if (!BWD) {
@@ -136,11 +142,12 @@ __global__ void __launch_bounds__(32 * kMsdaWarps) msda_kernel(const __grid_cons
           gx[k] = fmaf(ag, (1.f - fy) * (v01 - v00) + fy * (v11 - v10), gx[k]);
           gy[k] = fmaf(ag, (1.f - fx) * (v10 - v00) + fx * (v11 - v01), gy[k]);
           if (act) {
-            float* __restrict__ g = gvbase + (int64_t)off * tok + dd;
-            if (mask & 1u) atomicAdd(g, ag * w00);
-            if (mask & 2u) atomicAdd(g + tok, ag * w01);
-            if (mask & 4u) atomicAdd(g + (int64_t)W * tok, ag * w10);
-            if (mask & 8u) atomicAdd(g + (int64_t)(W + 1) * tok, ag * w11);
+#define DSKD_GTAP(o) reinterpret_cast<float*>(gb + (size_t)(o))
+            if (mask & 1u) atomicAdd(DSKD_GTAP(off), ag * w00);
+            if (mask & 2u) atomicAdd(DSKD_GTAP(off + tokb), ag * w01);
+            if (mask & 4u) atomicAdd(DSKD_GTAP(off + wtok), ag * w10);
+            if (mask & 8u) atomicAdd(DSKD_GTAP(off + wtok + tokb), ag * w11);
+#undef DSKD_GTAP
           }
         }
       }
@@ -177,7 +184,7 @@ static int msda_fill(MsdaParams& p, const char* who, const float* d_value, const
     p.start[l] = cells;
     cells += (int64_t)levels[l].H * levels[l].W;
   }
-  DSKD_REQUIRE(S < (1ll << 31), "%s: S above 2^31 tokens", who);
+  DSKD_REQUIRE(S * M * D < (1ll << 29), "%s: one image's value tensor (S * M * D) must stay below 2^29 elements", who);
   DSKD_REQUIRE(cells == S, "%s: the levels hold %lld tokens, S is %lld", who, (long long)cells, (long long)S);
   p.num_levels = num_levels;
   p.P = P;

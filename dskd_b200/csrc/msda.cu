@@ -3,8 +3,8 @@
 // (`mmcv.ops.multi_scale_deform_attn.MultiScaleDeformableAttention`, imported at mmdet/models/utils/transformer.py:23,
 // mmcv-full pinned by requirements/mminstall.txt:1; not vendored).  Semantics = its published definition, which is
 // `F.grid_sample(value_l, 2 * loc - 1, bilinear, zeros, align_corners=False)` per level, weighted by the attention
-// weights and summed over levels and points (mmcv `multi_scale_deformable_attn_pytorch`); the torch restatement of that
-// is dskd_b200/harness/model.py `msda_torch` and is what tests/test_gpu_msda.py compares against.
+// weights and summed over levels and points (mmcv `multi_scale_deformable_attn_pytorch`); a torch restatement of that
+// definition lives with the test infrastructure and is what tests/test_gpu_msda.py compares the kernels against.
 //
 // One warp per (image, query, head), a CTA = 8 consecutive queries of one head; the lanes are the head's channels (D = 32 for 256 / 8), so every bilinear tap is
 // one coalesced 128 B load (forward) or one coalesced 128 B red.global (backward) and the value tensor of an image

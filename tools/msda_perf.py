@@ -60,6 +60,9 @@ def run(N, Lq_kind):
 
 
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'one':        # a single encoder-sized point (ncu target)
+        run(int(sys.argv[2]) if len(sys.argv) > 2 else 2, 'encoder')
+        sys.exit(0)
     for N in (2, 4):
         for kind in ('encoder', 'decoder'):
             run(N, kind)

@@ -11,6 +11,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libdskd_b200.so')
 MAX_LEVELS = 8
+ABI_VERSION = 2
 
 OK, EINVAL, ECUDA, EUNSUPPORTED_ARCH, EINFEASIBLE = 0, -1, -2, -3, -4
 LAYOUT_NCHW, LAYOUT_SNC = 0, 1
@@ -45,7 +46,8 @@ class DsgfdKlArgs(C.Structure):
                 ('d_student', _FP * MAX_LEVELS), ('d_teacher', _FP * MAX_LEVELS),
                 ('scale', C.c_float * MAX_LEVELS), ('temperature', C.c_float),
                 ('cells_per_image', C.c_int64), ('d_owner', _FP), ('d_rows', _FP), ('d_grad_rows', _FP),
-                ('num_pairs', C.c_int32), ('d_cell_weight', _FP), ('d_loss', _FP)]
+                ('num_pairs', C.c_int32), ('d_cell_weight', _FP), ('d_loss', _FP),
+                ('layout', C.c_int32), ('d_workspace', _FP), ('workspace_bytes', C.c_int64)]
 
 
 class DsgfdStepArgs(C.Structure):
@@ -134,20 +136,24 @@ def load():
     lib.dskd_launch_count.argtypes = []
     lib.dskd_dsgfd_step_workspace_bytes.restype = C.c_int64
     lib.dskd_dsgfd_step_workspace_bytes.argtypes = [C.c_int32, C.c_int64, C.c_int32, C.c_int32]
+    lib.dskd_dsgfd_step_workspace_bytes_for.restype = C.c_int64
+    lib.dskd_dsgfd_step_workspace_bytes_for.argtypes = [C.POINTER(DsgfdStepArgs)]
     lib.dskd_struct_size.restype = C.c_int64
     lib.dskd_struct_size.argtypes = [C.c_int32]
     for which, mirror in enumerate((Level, DsgfdMseArgs, DsgfdKlArgs, DsgfdStepArgs, QmemArgs)):
         if lib.dskd_struct_size(which) != C.sizeof(mirror):
             raise DskdError(f'{mirror.__name__}: ctypes mirror is {C.sizeof(mirror)} bytes, the library says '
                             f'{lib.dskd_struct_size(which)} (include/dskd_b200.h and _lib.py are out of step)')
+    lib.dskd_dsgfd_kl_workspace_bytes.restype = C.c_int64
+    lib.dskd_dsgfd_kl_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.POINTER(Level), C.c_int32]
     lib.dskd_qmem_workspace_bytes.restype = C.c_int64
     lib.dskd_qmem_workspace_bytes.argtypes = [C.c_int32, C.c_int64, C.c_int32, C.c_int32]
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = C.c_int
-    if lib.dskd_abi_version() != 1:
-        raise DskdError(f'ABI version mismatch: library {lib.dskd_abi_version()} != binding 1')
+    if lib.dskd_abi_version() != ABI_VERSION:
+        raise DskdError(f'ABI version mismatch: library {lib.dskd_abi_version()} != binding {ABI_VERSION}')
     _lib = lib
     return lib
 

@@ -2,39 +2,37 @@
 // [C,H,W] maps, i.e. softmax over H (kd_loss.py:28-34 with dim=1 == H), target = student*mask
 // (detached), pred = teacher*mask.  Reference: gfl_deformable_detr_head_il.py:707-718 + kd_loss.py:12-43.
 //
-// Cells outside every box have logit 0 for both softmaxes and need no feature bytes; strips without any owned cell
-// contribute exactly 0 and are skipped.  No gradient reaches the student features (target is detached): the only
-// gradient is d loss / d rows.  Algorithmic bytes: read S + read T = 8 B per element (45.51 MB per 800x1333 image).
+// Algorithmic bytes: read S + read T = 8 B per element (45.51 MB per 800x1333 image); no gradient reaches the
+// student features (the target is detached): the only gradient is d loss / d mask rows.
+//
+// ONE pass over the features.  With x_h = S_h m_h / T (target logits), y_h = T_h m_h / T (pred logits):
+//   KL(column) = sum_h q_h (x_h - y_h) - (lse_x - lse_y),     q = softmax(x), p = softmax(y)
+//   d loss / d m_j = gcoef * sum_{h in run of box j} T_h (p_h - q_h)
+//                  = gcoef * ( A_j / sum_y - B_j / sum_x ),   A_j = sum_run T_h e^{y_h},  B_j = sum_run T_h e^{x_h}
+// so a column needs sum e^x, sum e^y, sum e^x (x - y) and, per run of rows with one owning box, (A_j, B_j): all of them
+// are running sums down the rows, and the softmax normalisers are applied once at the bottom of the column.  The
+// exponentials are taken WITHOUT subtracting the column maximum (cells outside boxes have logit 0, so the sums sit near
+// H).  A (tile, channel) whose sums leave [2^-90, 2^100] or turn non-finite, and a tile with more runs than the record
+// pools of its CTA hold, is not finished by the streaming kernel: every block leaves a bit mask of such channels, which a
+// second, tiny launch works off with a plain three-sweep evaluation with exact maxima (the way the reference does).  Keeping that
+// path in its own kernel keeps its registers and calls out of the streaming loop.  Cells outside every box are never read.
+#include <stdlib.h>
+
 #include <type_traits>
 
 #include "common.cuh"
 
 namespace dskd {
 
-// Strip kernel.  A CTA owns one strip = (level, image, kKlCols consecutive w) x all H rows and a chunk of channels; each
-// of its warps walks kKlChan channels one after the other; the 32 lanes are kKlCols columns x kKlPhases row phases (a
-// lane takes every kKlPhases-th row of its column; narrow strips keep the shared-memory footprint per warp small enough
-// for 32 resident warps per SM).  Once per CTA every column is cut into SEGMENTS, the maximal runs of rows with one
-// owning box; all per-channel work is a loop over the segments of the lane's column, so only rows inside boxes are
-// loaded or visited (the others have logit 0 in both softmaxes and enter in closed form), the mask value is a
-// per-segment constant and the inner loops are branch-free.  Per channel the warp
-//   0. cp.async's the segment rows of the student / teacher strip into ITS shared-memory buffers (every feature byte
-//      is read from HBM exactly once),
-//   A. turns them in place into the logits x = feature * mask / T and takes the column maxima,
-//   B. sums e^(x - max) for both softmaxes and sum e^(xs - max) (xs - xt) -- the KL of a column needs nothing else:
-//        KL = sum_h t_h (xs_h - xt_h) - (lse_s - lse_t),
-//   C. (only when the mask rows need a gradient) accumulates T_h * (p_h - t_h) over each segment and issues one
-//      red.global per (column, segment, channel).
-constexpr int kKlChan = 4;        // channels per warp (sequential)
-constexpr int kKlCols = 8;        // columns (w) per strip: a warp covers kKlCols columns x kKlPhases interleaved row phases
-constexpr int kKlPhases = 32 / kKlCols;
-constexpr int kKlMaxWarps = 32;   // warps per CTA
-constexpr int kKlMaxH = 800;      // rows per level the shared-memory strips can hold (one warp per CTA at the limit)
-constexpr size_t kKlSmemBudget = 220 * 1024;
-__host__ __device__ inline size_t kl_header_bytes(int max_h) {
-  // owner strip + first row / end row / owner of every segment: 4 x int32 [max_h][kKlCols]; 2 x int32 [kKlCols] counters
-  return ((size_t)max_h * kKlCols * 4 * 4 + (size_t)kKlCols * 4 * 2 + 127) / 128 * 128;
-}
+constexpr int kKlWarps = 8;       // warps per CTA (one channel at a time each)
+constexpr int kKlBlk = 5;         // rows per block: the unit of loading ahead and of skipping rows without boxes
+constexpr int kKlStages = 2;      // row blocks in the register ring: the loads of kKlStages - 1 blocks are in flight
+constexpr int kKlMinCtas = 4;     // CTAs per SM the register budget is cut for
+constexpr int kKlChunk = 16;      // channels per CTA
+constexpr int kKlPool = 256;      // (owner, lane, A, B) records a warp can park per channel before the normalisers are known
+constexpr int kKlMaxH = 1600;     // rows per level (shared-memory tables: 136 B per row)
+constexpr int kKlRedoCtas = 148;  // grid of the redo launch
+constexpr float kLn2 = 0.6931471805599453f;
 
 struct KlParams {
   DskdLevel levels[DSKD_MAX_LEVELS];
@@ -42,615 +40,719 @@ struct KlParams {
   const float* teacher[DSKD_MAX_LEVELS];
   float scale[DSKD_MAX_LEVELS];
   int block_start[DSKD_MAX_LEVELS + 1];
-  int wtiles[DSKD_MAX_LEVELS];
+  int wtiles[DSKD_MAX_LEVELS];   // column tiles per level
+  int wpt[DSKD_MAX_LEVELS];      // columns per tile (<= 32, balanced: ceil(W / wtiles))
   int num_levels, N, C;
-  int warps, max_h;               // warps per CTA, max H over the levels (sizes the shared-memory strips)
-  float temperature, inv_temperature;
+  int chunk;                     // channels per CTA
+  int max_blocks;                // row blocks of the tallest level (sizes the shared-memory tables)
+  int max_h;
+  int pool_cap;                  // (owner, lane, A, B) records a warp can park per channel
+  int dbg;                       // tuning experiments only (DSKD_KL_TUNE): 1 = no red.global at the bottom, 2 = no run ends
+  float temperature, kscale;     // kscale = log2(e) / T: logits are kept in units of log 2
   int64_t cells_per_image;
   const int* owner;
+  const float* cell_weight;      // per-cell mask weights instead of owners (CELL kernels)
   const float* rows;
   float* grad_rows;
-  const float* cell_weight;
   double* loss;
+  unsigned* redo_mask;           // [blocks of the streaming grid] channels of the block's chunk left to the redo launch
+  int num_blocks;
 };
 
-__device__ __forceinline__ void cp_async_f32(uint32_t dst, const float* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ float fast_ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-
-// POW2: T is a power of two, so (feature * mask) / T == feature * (mask / T) bit for bit and the division is hoisted.
-template <bool CELL, bool POW2>
-__global__ void __launch_bounds__(32 * kKlMaxWarps) dsgfd_kl_kernel(const __grid_constant__ KlParams prm) {
-  extern __shared__ __align__(16) unsigned char kl_smem[];
-  __shared__ double red[32];
-  __shared__ int strip_any, max_seg;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int wl = lane % kKlCols, ph = lane / kKlCols;  // column inside the strip, row phase (rows ph, ph + kKlPhases, ...)
-  int lvl = 0;
-#pragma unroll
-  for (int k = 1; k < DSKD_MAX_LEVELS; ++k)
-    if (k < prm.num_levels && (int)blockIdx.x >= prm.block_start[k]) lvl = k;
-  const int H = prm.levels[lvl].H, W = prm.levels[lvl].W, C = prm.C;
-  const int HW = H * W;
-  const int ch_per_cta = prm.warps * kKlChan;
-  const int nchunks = (C + ch_per_cta - 1) / ch_per_cta;
-  int idx = blockIdx.x - prm.block_start[lvl];
-  const int chunk = idx % nchunks;     // channel chunks of one strip are neighbours: the owner strip stays in L2 / L1
-  idx /= nchunks;
-  const int wt = idx % prm.wtiles[lvl];
-  const int img = idx / prm.wtiles[lvl];
-  const int w = wt * kKlCols + wl;
-  const float Temp = prm.temperature;
-  const float scale = prm.scale[lvl];
-  const int64_t strip_base = (int64_t)img * prm.cells_per_image + prm.levels[lvl].cell_offset + wt * kKlCols;
-  const int64_t cell_base = strip_base + wl;
-
-  // shared memory header (kl_header_bytes): the segment tables of the strip; then per warp the xs / xt strips
-  const int mh = prm.max_h;
-  int* own_s = reinterpret_cast<int*>(kl_smem);     // [h][col] owner strip (setup only)
-  int* seg_h0 = own_s + (size_t)mh * kKlCols;       // [col][k] first row of the k-th segment of the column
-  int* seg_h1 = seg_h0 + (size_t)mh * kKlCols;      // [col][k] one past its last row
-  int* seg_own = seg_h1 + (size_t)mh * kKlCols;     // [col][k] its owner (pair index; 0 in cell-mask mode)
-  int* nseg_s = seg_own + (size_t)mh * kKlCols;     // [col] segments of the column
-  int* nown_s = nseg_s + kKlCols;                   // [col] owned rows of the column
-  float* xs_s = reinterpret_cast<float*>(kl_smem + kl_header_bytes(mh)) + (size_t)warp * 2 * mh * kKlCols;
-  float* xt_s = xs_s + (size_t)mh * kKlCols;
-
-  // ---- once per CTA: the owner strip and, per column, its SEGMENTS (maximal runs of rows with one owner).  Only the
-  // rows inside segments are ever loaded or visited: the others have logit 0 in both softmaxes and enter in closed form.
-  if (threadIdx.x == 0) { strip_any = 0; max_seg = 0; }
-  __syncthreads();
-  {
-    bool any = false;
-    for (int i = threadIdx.x; i < H * kKlCols; i += blockDim.x) {
-      const int h = i / kKlCols, c = i % kKlCols;
-      int o = -1;
-      if (wt * kKlCols + c < W) {
-        if (CELL) o = (__ldg(prm.cell_weight + strip_base + c + (int64_t)h * W) != 0.f) ? 0 : -1;
-        else o = __ldg(prm.owner + strip_base + c + (int64_t)h * W);
-      }
-      own_s[i] = o;
-      any |= o >= 0;
-    }
-    if (__any_sync(0xffffffffu, any) && lane == 0) strip_any = 1;
-  }
-  __syncthreads();
-  if (!strip_any) return;  // no box touches this strip: every column's KL is exactly 0
-  if (threadIdx.x < kKlCols) {  // one thread per column walks its H rows
-    const int c = threadIdx.x;
-    int n = 0, prev = -1, owned = 0;
-    for (int h = 0; h < H; ++h) {
-      const int o = own_s[h * kKlCols + c];
-      if (o != prev) {
-        if (prev >= 0) seg_h1[c * mh + n - 1] = h;
-        if (o >= 0) { seg_h0[c * mh + n] = h; seg_own[c * mh + n] = o; ++n; }
-      }
-      owned += o >= 0 ? 1 : 0;
-      prev = o;
-    }
-    if (prev >= 0) seg_h1[c * mh + n - 1] = H;
-    nseg_s[c] = n;
-    nown_s[c] = owned;
-    atomicMax(&max_seg, n);
-  }
-  __syncthreads();
-
-  const float kLog2e = 1.4426950408889634f;
-  const float gcoef = scale * Temp / (float)H;  // d loss / d pred = scale * (T/H) * (p - t)
-  const bool want_grad = !CELL && prm.grad_rows != nullptr;
-  constexpr int kRow = kKlCols;                  // floats per strip row
-  const int my_nseg = nseg_s[wl], my_owned = nown_s[wl], nsweep = max_seg;  // the sweep loops are warp-uniform
-  const int* my_h0 = seg_h0 + wl * mh;
-  const int* my_h1 = seg_h1 + wl * mh;
-  const int* my_own = seg_own + wl * mh;
-  const uint32_t xs_a = (uint32_t)__cvta_generic_to_shared(xs_s) + (uint32_t)wl * 4u;
-  const uint32_t xt_a = (uint32_t)__cvta_generic_to_shared(xt_s) + (uint32_t)wl * 4u;
-  float* xs_c = xs_s + wl;                       // xs_c[h * kRow]
-  float* xt_c = xt_s + wl;
-  auto phase_max = [](float v) {
-#pragma unroll
-    for (int o = kKlCols; o < 32; o <<= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-  };
-  auto phase_sum = [](float v) {
-#pragma unroll
-    for (int o = kKlCols; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-  };
-  // rows of segment k that belong to this lane: hb, hb + kKlPhases, ... < h1 (an empty range when k >= my_nseg)
-  auto seg_range = [&](int k, int& hb, int& h1) {
-    if (k < my_nseg) {
-      const int h0 = my_h0[k];
-      h1 = my_h1[k];
-      hb = h0 + ((ph - h0) & (kKlPhases - 1));
-    } else {
-      hb = 0;
-      h1 = 0;
-    }
-  };
-  double kl_total = 0.0;
-
-  for (int kc = 0; kc < kKlChan; ++kc) {
-    const int c = (chunk * prm.warps + warp) * kKlChan + kc;
-    if (c >= C) break;
-    const float* __restrict__ S = prm.student[lvl] + ((int64_t)img * C + c) * HW + w;
-    const float* __restrict__ T = prm.teacher[lvl] + ((int64_t)img * C + c) * HW + w;
-    auto seg_mask = [&](int k) -> float {  // mask value of segment k (divided by T when that is exact)
-      const float m = __ldg(prm.rows + (int64_t)my_own[k] * C + c);
-      return POW2 ? m * prm.inv_temperature : m;
-    };
-    // ---- 0: the rows inside segments -> shared memory, asynchronously (every feature byte leaves HBM once)
-    for (int k = 0; k < nsweep; ++k) {
-      int h, h1;
-      seg_range(k, h, h1);
-      for (; h < h1; h += kKlPhases) {
-        cp_async_f32(xs_a + (uint32_t)(h * kRow) * 4u, S + (unsigned)(h * W));
-        cp_async_f32(xt_a + (uint32_t)(h * kRow) * 4u, T + (unsigned)(h * W));
-      }
-    }
-    cp_async_wait_all();
-    __syncwarp();
-    // ---- A: logits in place, maxima over the owned rows
-    float ms = -INFINITY, mt = -INFINITY;
-    for (int k = 0; k < nsweep; ++k) {
-      int h, h1;
-      seg_range(k, h, h1);
-      if (h >= h1) continue;
-      float m = CELL ? 0.f : seg_mask(k);
-      for (; h < h1; h += kKlPhases) {
-        if (CELL) {
-          m = __ldg(prm.cell_weight + cell_base + (int64_t)h * W);
-          if (POW2) m *= prm.inv_temperature;
-        }
-        float x = xs_c[h * kRow] * m, y = xt_c[h * kRow] * m;
-        if (!POW2) { x = __fdiv_rn(x, Temp); y = __fdiv_rn(y, Temp); }
-        xs_c[h * kRow] = x;
-        xt_c[h * kRow] = y;
-        ms = fmaxf(ms, x);
-        mt = fmaxf(mt, y);
-      }
-    }
-    ms = phase_max(ms);
-    mt = phase_max(mt);
-    if (my_owned < H) { ms = fmaxf(ms, 0.f); mt = fmaxf(mt, 0.f); }  // rows outside boxes: logit 0 in both softmaxes
-    // ---- B: softmax sums and the t-weighted logit difference over the owned rows
-    const float nms = -ms * kLog2e, nmt = -mt * kLog2e;
-    float ss0 = 0.f, ss1 = 0.f, st0 = 0.f, st1 = 0.f, ws0 = 0.f, ws1 = 0.f;
-    for (int k = 0; k < nsweep; ++k) {
-      int h, h1;
-      seg_range(k, h, h1);
-      for (; h + kKlPhases < h1; h += 2 * kKlPhases) {
-        const float a0 = xs_c[h * kRow], b0 = xt_c[h * kRow];
-        const float a1 = xs_c[(h + kKlPhases) * kRow], b1 = xt_c[(h + kKlPhases) * kRow];
-        const float e0 = fast_ex2(fmaf(a0, kLog2e, nms)), e1 = fast_ex2(fmaf(a1, kLog2e, nms));
-        ss0 += e0; ss1 += e1;
-        st0 += fast_ex2(fmaf(b0, kLog2e, nmt)); st1 += fast_ex2(fmaf(b1, kLog2e, nmt));
-        ws0 = fmaf(e0, a0 - b0, ws0); ws1 = fmaf(e1, a1 - b1, ws1);
-      }
-      if (h < h1) {
-        const float a0 = xs_c[h * kRow], b0 = xt_c[h * kRow];
-        const float e0 = fast_ex2(fmaf(a0, kLog2e, nms));
-        ss0 += e0;
-        st0 += fast_ex2(fmaf(b0, kLog2e, nmt));
-        ws0 = fmaf(e0, a0 - b0, ws0);
-      }
-    }
-    // the H - owned rows outside boxes add e^(0 - max) to each sum and nothing to the weighted difference
-    const float rest = (float)(H - my_owned);
-    const float sum_s = fmaf(rest, fast_ex2(nms), phase_sum(ss0 + ss1));
-    const float sum_t = fmaf(rest, fast_ex2(nmt), phase_sum(st0 + st1));
-    const float wsum = phase_sum(ws0 + ws1);
-    // KL of the column = sum_h t_h (xs - xt) - (lse_s - lse_t): a second-order quantity (both log-softmaxes sit near
-    // -log H), so the log-sum-exp difference is taken in double.  One lane per column keeps it.
-    if (ph == 0) {
-      const double dl = ((double)ms - (double)mt) + log((double)sum_s / (double)sum_t);
-      kl_total += (double)wsum / (double)sum_s - dl;
-    }
-
-    // ---- C: d loss / d mask rows: sum over a segment of T_h (p_h - t_h) = (T/mask) sum xt_h (p_h - t_h); the row phases
-    // of a column are combined by shuffles and one lane issues one red.global per (column, segment, channel)
-    if (want_grad) {
-      const float rs = __fdividef(1.f, sum_s), rt = __fdividef(1.f, sum_t);
-      for (int k = 0; k < nsweep; ++k) {
-        int h, h1;
-        seg_range(k, h, h1);
-        float acc0 = 0.f, acc1 = 0.f;
-        for (; h + kKlPhases < h1; h += 2 * kKlPhases) {
-          const float b0 = xt_c[h * kRow], a0 = xs_c[h * kRow], b1 = xt_c[(h + kKlPhases) * kRow], a1 = xs_c[(h + kKlPhases) * kRow];
-          const float p0 = fast_ex2(fmaf(b0, kLog2e, nmt)) * rt, t0 = fast_ex2(fmaf(a0, kLog2e, nms)) * rs;
-          const float p1 = fast_ex2(fmaf(b1, kLog2e, nmt)) * rt, t1 = fast_ex2(fmaf(a1, kLog2e, nms)) * rs;
-          acc0 = fmaf(b0, p0 - t0, acc0);
-          acc1 = fmaf(b1, p1 - t1, acc1);
-        }
-        if (h < h1) {
-          const float b0 = xt_c[h * kRow], a0 = xs_c[h * kRow];
-          acc0 = fmaf(b0, fast_ex2(fmaf(b0, kLog2e, nmt)) * rt - fast_ex2(fmaf(a0, kLog2e, nms)) * rs, acc0);
-        }
-        float v = phase_sum(acc0 + acc1);
-        if (ph == 0 && k < my_nseg) {
-          const float m = seg_mask(k);
-          float div = POW2 ? m : m / Temp;
-          if (m == 0.f) {
-            // the mask value underflowed to 0: the logits carry no trace of the teacher feature, re-read it
-            v = 0.f;
-            div = 1.f;
-            for (int r = my_h0[k]; r < my_h1[k]; ++r) {
-              const float pp = fast_ex2(fmaf(xt_c[r * kRow], kLog2e, nmt)) * rt;
-              const float tt = fast_ex2(fmaf(xs_c[r * kRow], kLog2e, nms)) * rs;
-              v = fmaf(ld_stream_f1(T + (int64_t)r * W), pp - tt, v);
-            }
-          }
-          atomicAdd(prm.grad_rows + (int64_t)my_own[k] * C + c, __fdividef(gcoef * v, div));
-        }
-      }
-    }
-    __syncwarp();
-  }
-  // loss = scale * T^2 / H * sum over columns of sum_h t (log t - log p)
-  double tot = block_sum(kl_total, red);
-  if (threadIdx.x == 0 && tot != 0.0)
-    atomicAdd(prm.loss, tot * (double)scale * (double)Temp * (double)Temp / (double)H);
+// loads under a predicate (0 when off): cells outside boxes are never fetched
+__device__ __forceinline__ float ld_stream_f1_ge0(const float* p, int key) {
+  float v;
+  asm("{\n\t.reg .pred q;\n\tsetp.ge.s32 q, %2, 0;\n\tmov.f32 %0, 0f00000000;\n\t"
+      "@q ld.global.nc.L1::no_allocate.f32 %0, [%1];\n\t}"
+      : "=f"(v)
+      : "l"(p), "r"(key));
+  return v;
+}
+__device__ __forceinline__ float ld_cached_f1_ge0(const float* p, int key) {
+  float v;
+  asm("{\n\t.reg .pred q;\n\tsetp.ge.s32 q, %2, 0;\n\tmov.f32 %0, 0f00000000;\n\t"
+      "@q ld.global.nc.f32 %0, [%1];\n\t}"
+      : "=f"(v)
+      : "l"(p), "r"(key));
+  return v;
+}
+__device__ __forceinline__ float ld_stream_f1_nz(const float* p, float key) {
+  float v;
+  asm("{\n\t.reg .pred q;\n\tsetp.neu.f32 q, %2, 0f00000000;\n\tmov.f32 %0, 0f00000000;\n\t"
+      "@q ld.global.nc.L1::no_allocate.f32 %0, [%1];\n\t}"
+      : "=f"(v)
+      : "l"(p), "f"(key));
+  return v;
+}
+__device__ __forceinline__ void st_shared_b32(unsigned addr, int v) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
-
-// ------------------------------------------------------------------------------------------------------------------
-// Column kernel (box masks, H <= 400): the logits of a column never leave the register file.
-// A warp owns 32 consecutive columns (w) of kColRows consecutive rows of one channel plane: every feature load is one
-// coalesced 128 B row piece, each lane keeps its kColRows student / teacher values in registers through all three
-// sweeps (logits + maxima, softmax sums, gradient), and the loops over rows are fully unrolled, so there is no address
-// arithmetic, no shared-memory staging of features and no per-segment loop.  Taller levels are cut into `parts` row
-// parts held by `parts` warps of the CTA; they exchange (local max, local sums) once per channel through shared memory
-// and rescale.  What varies per row -- the owning box -- is turned ONCE per CTA into a byte offset into a small
-// shared-memory table of the mask rows of the tile's boxes (entry 0 = the zero row for cells outside boxes), so a row
-// costs one LDS for its mask value and cells outside boxes need no branch: their logit is feature * 0.
-// Row parts without any box skip their loads and arithmetic (closed form), tiles without any box exit.
-constexpr int kColRows = 25;        // rows per lane (100 / 50 / 25 rows of the COCO pyramid = 4 / 2 / 1 parts)
-constexpr int kColBlk = 5;          // rows per skippable block
-constexpr int kColBlocks = (kColRows + kColBlk - 1) / kColBlk;
-constexpr int kColTableCap = 3072;  // floats of staged mask rows per CTA
-constexpr int kColMaxPairs = kColTableCap - 3;
-constexpr int kColChunk = 32;       // channels per CTA
-
-struct KlColParams {
-  DskdLevel levels[DSKD_MAX_LEVELS];
-  const float* student[DSKD_MAX_LEVELS];
-  const float* teacher[DSKD_MAX_LEVELS];
-  float scale[DSKD_MAX_LEVELS];
-  int block_start[DSKD_MAX_LEVELS + 1];
-  int wtiles[DSKD_MAX_LEVELS];
-  int parts[DSKD_MAX_LEVELS];  // row parts (warps per column tile)
-  int rpp[DSKD_MAX_LEVELS];    // rows per part
-  int num_levels, N, C;
-  int chunk;                   // channels per CTA
-  float temperature, inv_temperature;
-  int64_t cells_per_image;
-  const int* owner;
-  const float* cell_weight;    // per-cell mask weights instead of owners (CELL kernels)
-  const float* rows;
-  float* grad_rows;
-  double* loss;
+// Shared-memory tables of one column tile (all channels of the CTA share them).
+struct KlTables {
+  int* moff;          // [rows_padded][32] box masks: owner * C, -1 outside boxes / past the last row or column
+  float* mw;          //                  cell masks: the cell's weight (aliases moff)
+  unsigned* endm;     // [rows_padded] lanes whose run of one owner ends with this row
+  unsigned* anym;     // [rows_padded] lanes with a box cell in this row
+  unsigned short* act;// [nact] active row blocks (bit 15: some run ends inside the block)
 };
 
-// bar.sync on a compile-time barrier id (a run-time id makes ptxas reserve all 16 barriers for every CTA)
-template <int MAXG>
-__device__ __forceinline__ void group_barrier(int group, int threads) {
-#define DSKD_BAR_CASE(G)                                                               \
-  case G:                                                                              \
-    if (G < MAXG) asm volatile("bar.sync %0, %1;" ::"n"(G + 1), "r"(threads) : "memory"); \
-    break;
-  switch (group) {
-    DSKD_BAR_CASE(0) DSKD_BAR_CASE(1) DSKD_BAR_CASE(2) DSKD_BAR_CASE(3)
-    DSKD_BAR_CASE(4) DSKD_BAR_CASE(5) DSKD_BAR_CASE(6) DSKD_BAR_CASE(7)
-    default: break;
+// dynamic shared memory layout of the streaming kernel (the same arithmetic on both sides)
+struct KlSmem {
+  size_t endm, anym, pool, act, total;
+  __host__ __device__ KlSmem(int max_blocks, int blk, bool grad, int pool_cap) {
+    const size_t rows = (size_t)max_blocks * blk;
+    endm = rows * 32 * 4;
+    anym = endm + rows * 4;
+    pool = (anym + rows * 4 + 15) / 16 * 16;
+    act = pool + (grad ? (size_t)kKlWarps * pool_cap * 12 : 0);
+    total = (act + (size_t)max_blocks * 2 + 15) / 16 * 16;
   }
-#undef DSKD_BAR_CASE
-}
+};
 
-// Registers over occupancy: 3 CTAs of 4 warps per SM (168 registers, no spills of the row arrays) beat 4, 5 and 6 CTAs
-// (128 / 96 / 80 registers, the row arrays partly in local memory): 0.33 / 0.39 / 0.40 / 0.42 ms on the COCO batch.
-// CELL: per-cell mask weights (sg_out / fg_only) instead of box owners: the lane keeps the weights of its rows in
-// registers, there is no mask table and no gradient.
-template <int MAXW, bool POW2, bool CELL>
-__global__ void __launch_bounds__(32 * MAXW, MAXW == 4 ? 3 : 1) dsgfd_kl_col_kernel(const __grid_constant__ KlColParams prm) {
-  __shared__ float rows_s[kColTableCap];   // [channel of the sub-chunk][1 + owner - omin] mask values (/T when exact)
-  __shared__ float ex_s[2][MAXW][5][32];   // per warp: local max_s, max_t, sum_s, sum_t, weighted sum (double-buffered)
-  __shared__ double red[32];
-  __shared__ int orange_s[2];
-  __shared__ int zero_s[kColChunk];     // per staged channel: some mask value is exactly 0 (underflow)
-  constexpr unsigned kFull = 0xffffffffu;
-  constexpr int kPacked = (kColRows + 1) / 2;
-  constexpr float kExcluded = -1e30f;      // logit of a row that does not exist (partial parts): e^x == 0, x - y == 0
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  int lvl = 0;
+// Which tile a block of the streaming grid owns (the redo launch decodes the same index).
+struct KlTile {
+  int lvl, img, chunk, w0, wn;
+};
+__device__ __forceinline__ KlTile kl_decode_tile(const KlParams& prm, int block) {
+  KlTile t;
+  t.lvl = 0;
 #pragma unroll
   for (int k = 1; k < DSKD_MAX_LEVELS; ++k)
-    if (k < prm.num_levels && (int)blockIdx.x >= prm.block_start[k]) lvl = k;
-  const int H = prm.levels[lvl].H, W = prm.levels[lvl].W, C = prm.C;
-  const int HW = H * W;
-  const int nchunks = (C + prm.chunk - 1) / prm.chunk;
-  int idx = blockIdx.x - prm.block_start[lvl];
-  const int chunk = idx % nchunks;  // the channel chunks of one tile are neighbours: its owner lines stay in L2
-  idx /= nchunks;
-  const int wt = idx % prm.wtiles[lvl];
-  const int img = idx / prm.wtiles[lvl];
-  const int parts = prm.parts[lvl], rpp = prm.rpp[lvl];
-  const int groups = MAXW / parts;            // warps of one group hold the row parts of the same channel
-  const int part = warp % parts, group = warp / parts;
-  const bool active = group < groups;
-  const int w = wt * 32 + lane;
-  const bool col_ok = w < W;
-  const int wc = min(w, W - 1);               // lanes past the last column load it again and are ignored
-  const int row0 = part * rpp;
-  const int nrows = active ? min(rpp, H - row0) : 0;
-  const float Temp = prm.temperature;
-  const float scale = prm.scale[lvl];
-  const unsigned uW = (unsigned)W;
+    if (k < prm.num_levels && block >= prm.block_start[k]) t.lvl = k;
+  const int nchunks = (prm.C + prm.chunk - 1) / prm.chunk;
+  int idx = block - prm.block_start[t.lvl];
+  const int wt = idx % prm.wtiles[t.lvl];  // the column tiles of one plane are neighbours: they share its DRAM pages
+  idx /= prm.wtiles[t.lvl];
+  t.chunk = idx % nchunks;
+  t.img = idx / nchunks;
+  t.w0 = wt * prm.wpt[t.lvl];
+  t.wn = min(prm.wpt[t.lvl], prm.levels[t.lvl].W - t.w0);
+  return t;
+}
 
-  // ---- once per CTA: the owners of this lane's rows -> byte offsets into the staged mask table, flush rows
-  if (tid == 0) { orange_s[0] = 0x7fffffff; orange_s[1] = -1; }
-  __syncthreads();
-  const int64_t cell0 = (int64_t)img * prm.cells_per_image + prm.levels[lvl].cell_offset + (int64_t)row0 * W + wc;
-  unsigned moffp[kPacked];  // two 16-bit byte offsets per register
-  float mw[kColRows];       // CELL: the mask weights of this lane's rows (/T when exact)
-  unsigned fb = 0;          // rows after which the accumulated gradient of a run is flushed
-  bool part_any;
-  unsigned rowany;          // rows with a box in some column of the warp
-  int omin, omax;
-  {
-    int own[kColRows];
-    int lo = 0x7fffffff, hi = -1;
+// One streaming pass of a warp over the active row blocks of its channel plane.  GRAD: besides the three sums of the
+// column, the (A, B) sums of every finished run are parked in the warp's record pool.
+struct KlChan {
+  const float* Sp;     // plane + w0 + lane
+  const float* Tp;
+  const float* rowsc;  // rows + c
+  float ss, st, ws;    // sum e^x, sum e^y, sum e^x (x - y)     (x, y in units of log 2)
+  int base;            // records parked so far (warp-uniform)
+};
+
+template <bool CELL, bool GRAD, int R, int NB>
+__device__ __forceinline__ void kl_stream_pass(const KlTables& tb, KlChan& ch, const unsigned W, const int lane,
+                                               const int nact, const float kscale, const unsigned pool_addr,
+                                               const int pool_words, const int dbg) {
+  struct Stage { float s[R], t[R]; };
+  Stage stg[NB];
+  float A = 0.f, B = 0.f;
+  auto load = [&](Stage& sg, int entry) {
+    const int r0 = (entry & 0x7fff) * R;
+    unsigned o = (unsigned)r0 * W;
 #pragma unroll
-    for (int r = 0; r < kColRows; ++r) {
-      int o = -1;
+    for (int i = 0; i < R; ++i, o += W) {
+      const int key = tb.moff[(r0 + i) * 32 + lane];
       if (CELL) {
-        const float wv = (col_ok && r < nrows) ? __ldg(prm.cell_weight + cell0 + r * uW) : 0.f;
-        mw[r] = POW2 ? wv * prm.inv_temperature : wv;
-        o = wv != 0.f ? 0 : -1;
-      } else if (col_ok && r < nrows) {
-        o = __ldg(prm.owner + cell0 + r * uW);
+        sg.s[i] = ld_stream_f1_nz(ch.Sp + o, __int_as_float(key));
+        sg.t[i] = ld_stream_f1_nz(ch.Tp + o, __int_as_float(key));
+      } else {
+        sg.s[i] = ld_stream_f1_ge0(ch.Sp + o, key);
+        sg.t[i] = ld_stream_f1_ge0(ch.Tp + o, key);
       }
-      own[r] = o;
-      if (o >= 0) { lo = min(lo, o); hi = max(hi, o); }
     }
-    lo = __reduce_min_sync(kFull, lo);
-    hi = __reduce_max_sync(kFull, hi);
-    part_any = hi >= 0;  // some cell of this warp's rows lies inside a box
-    {
-      unsigned ob = 0;
+  };
+  auto compute = [&](const Stage& sg, int entry, auto ends_tag) {
+    constexpr bool ENDS = decltype(ends_tag)::value;  // some lane's run ends inside this block
+    const int r0 = (entry & 0x7fff) * R;
+    float m[R];
 #pragma unroll
-      for (int r = 0; r < kColRows; ++r) ob |= own[r] >= 0 ? 1u << r : 0u;
-      rowany = __reduce_or_sync(kFull, ob);
+    for (int i = 0; i < R; ++i) {
+      const int off = tb.moff[(r0 + i) * 32 + lane];
+      m[i] = (CELL ? __int_as_float(off) : ld_cached_f1_ge0(ch.rowsc + (unsigned)off, off)) * kscale;
     }
-    if (lane == 0 && part_any) { atomicMin(&orange_s[0], lo); atomicMax(&orange_s[1], hi); }
-    __syncthreads();
-    omin = orange_s[0];
-    omax = orange_s[1];
-    if (omax < 0) return;  // no box touches this tile: every column's KL is exactly 0
+    float pa[R], pb[R];  // ENDS: T_h e^y, T_h e^x of every row, so that the arithmetic of the block stays branch-free
 #pragma unroll
-    for (int r = 0; r < kColRows; ++r) {
-      const int nx = (r + 1 < kColRows) ? own[r + 1] : -1;
-      if (!CELL && own[r] >= 0 && nx != own[r]) fb |= 1u << r;
+    for (int i = 0; i < R; ++i) {
+      const float x = sg.s[i] * m[i], y = sg.t[i] * m[i];
+      const float e = fast_ex2(x), f = fast_ex2(y);
+      ch.ss += e;
+      ch.st += f;
+      ch.ws = fmaf(e, x - y, ch.ws);
+      if (GRAD && !ENDS) {
+        A = fmaf(sg.t[i], f, A);
+        B = fmaf(sg.t[i], e, B);
+      }
+      if (ENDS) {
+        pa[i] = sg.t[i] * f;
+        pb[i] = sg.t[i] * e;
+      }
     }
+    if (ENDS) {
+      unsigned em[R];
 #pragma unroll
-    for (int k = 0; k < kPacked; ++k) {
-      const int o0 = own[2 * k], o1 = (2 * k + 1 < kColRows) ? own[2 * k + 1] : -1;
-      const unsigned b0 = o0 >= 0 ? (unsigned)(o0 - omin + 1) * 4u : 0u;
-      const unsigned b1 = o1 >= 0 ? (unsigned)(o1 - omin + 1) * 4u : 0u;
-      moffp[k] = b0 | (b1 << 16);
-    }
-  }
-  const unsigned anyfb = __reduce_or_sync(kFull, fb);
-  // blocks of kColBlk rows without any box in the warp's 32 columns are skipped (closed form: logit 0)
-  unsigned blk_on = 0;
-  int nskip_i = 0;
+      for (int i = 0; i < R; ++i) em[i] = (dbg & 8) ? 0u : tb.endm[r0 + i];
 #pragma unroll
-  for (int b = 0; b < kColBlocks; ++b) {
-    const unsigned bm = ((1u << kColBlk) - 1u) << (b * kColBlk);
-    if (rowany & bm) blk_on |= 1u << b;
-    else nskip_i += max(0, min(nrows - b * kColBlk, kColBlk));
-  }
-  const float nskip = (float)nskip_i;
-  const int nown = omax - omin + 1;
-  const int nstride = (nown + 1) | 1;  // odd: the staging writes of one owner spread over the banks
-  const int chs = min(prm.chunk, kColTableCap / nstride);  // channels staged at a time (>= 1: host bounds num_pairs)
-
-  const float kLog2e = 1.4426950408889634f;
-  const float gcoef = scale * Temp / (float)H;  // d loss / d pred = scale * (T/H) * (p - t)
-  const bool want_grad = !CELL && prm.grad_rows != nullptr;
-  const int c_begin = chunk * prm.chunk, c_end = min(C, c_begin + prm.chunk);
-  double kl_total = 0.0;
-  int par = 0;
-#define DSKD_MOFF(r) (((r) & 1) ? (moffp[(r) >> 1] >> 16) : (moffp[(r) >> 1] & 0xffffu))
-#define DSKD_MTAB(off) (*reinterpret_cast<const float*>(reinterpret_cast<const char*>(mtab) + (off)))
-
-  // one channel of this warp's rows; FULL: all kColRows rows exist
-  auto channel = [&](auto full_tag, const int c, const float* mtab, const bool zero_any) {
-    constexpr bool FULL = decltype(full_tag)::value;
-    float s[kColRows], t[kColRows];
-    float ml_s = 0.f, ml_t = 0.f, ss = (float)nrows, st = (float)nrows, ws = 0.f;
-    const int64_t plane = ((int64_t)img * C + c) * HW + (int64_t)row0 * W + wc;
-#define DSKD_FOR_ROWS_ON(body)                                   \
-  _Pragma("unroll") for (int b_ = 0; b_ < kColBlocks; ++b_) {    \
-    if (blk_on & (1u << b_)) {                                   \
-      _Pragma("unroll") for (int k_ = 0; k_ < kColBlk; ++k_) {   \
-        const int r = b_ * kColBlk + k_;                         \
-        if (r < kColRows) { body }                               \
-      }                                                          \
-    }                                                            \
-  }
-    if (part_any) {
-      const float* __restrict__ Sp = prm.student[lvl] + plane;
-      const float* __restrict__ Tp = prm.teacher[lvl] + plane;
-      const uint64_t pitch = (uint64_t)uW * 4u;
-#pragma unroll
-      for (int b_ = 0; b_ < kColBlocks; ++b_) {
-        if (blk_on & (1u << b_)) {
-          // byte addresses advanced by one row pitch: two 64-bit adds per row instead of re-deriving base + r * W
-          const unsigned r0 = FULL ? (unsigned)(b_ * kColBlk) : (unsigned)min(b_ * kColBlk, nrows - 1);
-          uint64_t sa = reinterpret_cast<uint64_t>(Sp + r0 * uW), ta = reinterpret_cast<uint64_t>(Tp + r0 * uW);
-#pragma unroll
-          for (int k_ = 0; k_ < kColBlk; ++k_) {
-            const int r = b_ * kColBlk + k_;
-            if (r < kColRows) {
-              s[r] = ld_stream_f1(reinterpret_cast<const float*>(sa));
-              t[r] = ld_stream_f1(reinterpret_cast<const float*>(ta));
-              if (FULL || r + 1 < nrows) { sa += pitch; ta += pitch; }  // rows past the part load its last row again
-            }
+      for (int i = 0; i < R; ++i) {
+        A += pa[i];
+        B += pb[i];
+        if (em[i]) {  // warp-uniform: the run of some lane ends with this row
+          // the lanes whose run ends here park (owner, lane, A, B) in consecutive pool slots
+          const bool mine = (em[i] >> lane) & 1u;
+          if (mine) {  // three planes of pool_words each: owner * C * 32 + lane, A, B
+            const int slot = ch.base + __popc(em[i] & ((1u << lane) - 1u));
+            st_shared_b32(pool_addr + 4u * slot, tb.moff[(r0 + i) * 32 + lane] * 32 + lane);
+            st_shared_b32(pool_addr + 4u * (slot + pool_words), __float_as_int(A));
+            st_shared_b32(pool_addr + 4u * (slot + 2 * pool_words), __float_as_int(B));
+            A = 0.f;
+            B = 0.f;
           }
+          ch.base += __popc(em[i]);
         }
       }
-      // A: logits, maxima of this part (skipped rows: logit 0)
-      ml_s = nskip_i > 0 ? 0.f : -INFINITY;
-      ml_t = ml_s;
-      DSKD_FOR_ROWS_ON(
-        const float m = CELL ? mw[r] : DSKD_MTAB(DSKD_MOFF(r));
-        float x = s[r] * m; float y = t[r] * m;
-        if (!POW2) { x = __fdiv_rn(x, Temp); y = __fdiv_rn(y, Temp); }
-        if (!FULL) { x = r < nrows ? x : kExcluded; y = r < nrows ? y : kExcluded; }
-        s[r] = x;
-        t[r] = y;
-        ml_s = fmaxf(ml_s, x);
-        ml_t = fmaxf(ml_t, y);
-      )
-      // B: sums against the part's own maxima
-      const float nms = -ml_s * kLog2e, nmt = -ml_t * kLog2e;
-      float ss0 = 0.f, ss1 = 0.f, st0 = 0.f, st1 = 0.f, ws0 = 0.f, ws1 = 0.f;
-      DSKD_FOR_ROWS_ON(
-        const float e = fast_ex2(fmaf(s[r], kLog2e, nms));
-        const float f = fast_ex2(fmaf(t[r], kLog2e, nmt));
-        if (r & 1) { ss1 += e; st1 += f; ws1 = fmaf(e, s[r] - t[r], ws1); }
-        else { ss0 += e; st0 += f; ws0 = fmaf(e, s[r] - t[r], ws0); }
-        s[r] = e;  // the student logit is not needed again: keep e^(xs - local max) for the gradient sweep
-      )
-      ss = fmaf(nskip, fast_ex2(nms), ss0 + ss1);
-      st = fmaf(nskip, fast_ex2(nmt), st0 + st1);
-      ws = ws0 + ws1;
     }
-    // combine the row parts of the column: sum_p e^(max_p - max) * sum_p
-    float Ms = ml_s, Mt = ml_t, sum_s = ss, sum_t = st, wsum = ws;
-    if (parts > 1) {
-      float(*ex)[5][32] = ex_s[par];
-      ex[warp][0][lane] = ml_s;
-      ex[warp][1][lane] = ml_t;
-      ex[warp][2][lane] = ss;
-      ex[warp][3][lane] = st;
-      ex[warp][4][lane] = ws;
-      group_barrier<MAXW / 2>(group, 32 * parts);
-      const int w0 = group * parts;
-#pragma unroll 1
-      for (int p = 0; p < parts; ++p) {
-        Ms = fmaxf(Ms, ex[w0 + p][0][lane]);
-        Mt = fmaxf(Mt, ex[w0 + p][1][lane]);
+  };
+  auto compute_any = [&](const Stage& sg, int entry) {
+    if (GRAD && (entry & 0x8000) && !(dbg & 2)) compute(sg, entry, std::true_type{});
+    else compute(sg, entry, std::false_type{});
+  };
+  // software pipeline over the active blocks: the loads of the next NB - 1 blocks are in flight during the arithmetic
+#pragma unroll
+  for (int j = 0; j < NB - 1; ++j)
+    if (j < nact) load(stg[j], tb.act[j]);
+  for (int k = 0; k < nact; k += NB) {
+#pragma unroll
+    for (int u = 0; u < NB; ++u) {
+      const int kk = k + u;
+      if (kk < nact) {
+        if (kk + NB - 1 < nact) load(stg[(u + NB - 1) % NB], tb.act[kk + NB - 1]);
+        compute_any(stg[u], tb.act[kk]);
       }
-      sum_s = 0.f;
-      sum_t = 0.f;
-      wsum = 0.f;
-#pragma unroll 1
-      for (int p = 0; p < parts; ++p) {
-        const float fs = fast_ex2((ex[w0 + p][0][lane] - Ms) * kLog2e);
-        const float ft = fast_ex2((ex[w0 + p][1][lane] - Mt) * kLog2e);
-        sum_s = fmaf(ex[w0 + p][2][lane], fs, sum_s);
-        sum_t = fmaf(ex[w0 + p][3][lane], ft, sum_t);
-        wsum = fmaf(ex[w0 + p][4][lane], fs, wsum);
+    }
+  }
+}
+
+// Streaming kernel, [N,C,H,W] layout.  A CTA owns one column tile (level, image, <= 32 consecutive w) and a chunk of
+// channels; each warp streams one channel plane at a time down ALL rows of the tile, lane = column, so every feature
+// load is one coalesced row piece and the running sums of a column live in registers.  Once per CTA the owners of the
+// tile's cells become a shared-memory table (owner * C per cell), the rows are cut into blocks of R and only the blocks
+// that hold a box cell in some column are visited (the others add e^0 per row in closed form).  The (owner, A, B)
+// records of finished runs wait in a per-warp pool until the bottom of the column.  The number of runs of a tile does
+// not depend on the channel, so the CTA knows up front how many warps can run side by side: with more runs than one
+// pool holds, 4 / 2 / 1 warps work with 2 / 4 / 8 pools each.
+template <bool CELL, bool GRAD, int R, int NB, int MINB>
+__global__ void __launch_bounds__(32 * kKlWarps, MINB) dsgfd_kl_stream_kernel(const __grid_constant__ KlParams prm) {
+  extern __shared__ __align__(16) unsigned char kl_smem[];
+  __shared__ double red[32];
+  __shared__ float2 norm_s[kKlWarps][32];
+  __shared__ int nact_s, nadd_s, nends_s;
+  __shared__ unsigned redo_s;
+  constexpr unsigned kFull = 0xffffffffu;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const KlTile tl = kl_decode_tile(prm, blockIdx.x);
+  const int lvl = tl.lvl;
+  const int H = prm.levels[lvl].H, C = prm.C;
+  const unsigned W = (unsigned)prm.levels[lvl].W;
+  const int nblk = (H + R - 1) / R, rows_pad = nblk * R;
+
+  const KlSmem lay(prm.max_blocks, R, GRAD, prm.pool_cap);
+  KlTables tb;
+  tb.moff = reinterpret_cast<int*>(kl_smem);
+  tb.mw = reinterpret_cast<float*>(kl_smem);
+  tb.endm = reinterpret_cast<unsigned*>(kl_smem + lay.endm);
+  tb.anym = reinterpret_cast<unsigned*>(kl_smem + lay.anym);
+  tb.act = reinterpret_cast<unsigned short*>(kl_smem + lay.act);
+
+  // ---- once per CTA: owner table, run ends, list of active row blocks
+  {
+    const int64_t cell0 = (int64_t)tl.img * prm.cells_per_image + prm.levels[lvl].cell_offset + tl.w0;
+    for (int i = tid; i < rows_pad * 32; i += 32 * kKlWarps) {
+      const int h = i >> 5, l = i & 31;
+      const bool in = h < H && l < tl.wn;
+      if (CELL) tb.mw[i] = in ? __ldg(prm.cell_weight + cell0 + (int64_t)h * W + l) : 0.f;
+      else {
+        const int o = in ? __ldg(prm.owner + cell0 + (int64_t)h * W + l) : -1;
+        tb.moff[i] = o >= 0 ? o * C : -1;
       }
-      par ^= 1;
     }
-    // KL of the column = sum_h t_h (xs - xt) - (lse_s - lse_t): second order, so the difference is taken in double
-    if (part == 0 && col_ok) {
-      const double dl = ((double)Ms - (double)Mt) + log((double)sum_s / (double)sum_t);
-      kl_total += (double)wsum / (double)sum_s - dl;
+    if (tid == 0) { nends_s = 0; redo_s = 0u; }
+    __syncthreads();
+    // per row: lanes whose run of one owner ends here, lanes with a box at all
+    int ends_here = 0;
+    for (int h = warp; h < rows_pad; h += kKlWarps) {
+      bool on, end = false;
+      if (CELL) on = tb.mw[h * 32 + lane] != 0.f;
+      else {
+        const int o = tb.moff[h * 32 + lane];
+        const int nx = (h + 1 < rows_pad) ? tb.moff[(h + 1) * 32 + lane] : -1;
+        on = o >= 0;
+        end = on && nx != o;
+      }
+      const unsigned am = __ballot_sync(kFull, on), em = __ballot_sync(kFull, end);
+      if (lane == 0) { tb.anym[h] = am; tb.endm[h] = em; }
+      ends_here += __popc(em);
     }
-    // C: d loss / d mask rows: sum over a run of rows with one owner of T_h (p_h - t_h) = (T/mask) sum xt_h (p_h - t_h)
-    if (want_grad && part_any) {
-      const float rs = __fdividef(1.f, sum_s), rt = __fdividef(1.f, sum_t);
-      const float nms = -Ms * kLog2e, nmt = -Mt * kLog2e;
-      // s[r] holds e^(xs - local max) since sweep B: t_h = s[r] * e^(local max - max) / sum_s
-      const float cs = fast_ex2(fmaf(ml_s, kLog2e, nms)) * rs;
-      float* __restrict__ grow = prm.grad_rows + (int64_t)(omin - 1) * C + c;
-      // first every row's term T_h (p_h - t_h) * mask / T, branch-free (the exponentials of all rows overlap) ...
-      DSKD_FOR_ROWS_ON(
-        const float pt = fast_ex2(fmaf(t[r], kLog2e, nmt)) * rt;
-        s[r] = t[r] * fmaf(-s[r], cs, pt);
-      )
-      // ... then the running sum down the rows; a run of one owner ends where the owner of the next row differs
-      float acc = 0.f;
-      DSKD_FOR_ROWS_ON(
-        acc += s[r];
-        if (anyfb & (1u << r)) {  // warp-uniform: most rows end no run in any lane
-          unsigned fbv;           // (opaque copy: keeps the uniform test from being folded into the per-lane one)
-          asm volatile("mov.u32 %0, %1;" : "=r"(fbv) : "r"(fb));
-          if (fbv & (1u << r)) {
-            const unsigned off = DSKD_MOFF(r);
-            const float m = DSKD_MTAB(off);
-            // m == 0 (underflow): the run is handled below from the raw teacher feature
-            if (m != 0.f) atomicAdd(grow + (off >> 2) * (unsigned)C, __fdividef(gcoef * acc, POW2 ? m : m / Temp));
+    if (GRAD && lane == 0 && ends_here) atomicAdd(&nends_s, ends_here);
+    __syncthreads();
+    if (warp == 0) {
+      int base = 0, nadd = 0;
+      for (int b0 = 0; b0 < nblk; b0 += 32) {
+        const int b = b0 + lane;
+        bool on = false, ends = false;
+        int valid = 0;
+        if (b < nblk) {
+          valid = min(R, H - b * R);
+#pragma unroll
+          for (int r = b * R; r < b * R + R; ++r) {
+            on |= tb.anym[r] != 0u;
+            ends |= tb.endm[r] != 0u;
+          }
+        }
+        const unsigned bal = __ballot_sync(kFull, on);
+        if (on) tb.act[base + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)(b | (ends ? 0x8000 : 0));
+        base += __popc(bal);
+        // rows of skipped blocks add e^0 to both sums; rows past H inside active blocks must not
+        nadd += (b < nblk) ? (on ? valid - R : valid) : 0;
+      }
+      nadd = __reduce_add_sync(kFull, nadd);
+      if (lane == 0) { nact_s = base; nadd_s = nadd; }
+    }
+    __syncthreads();
+  }
+  const int nact = nact_s;
+  if (nact == 0) {  // no box touches this tile: every column's KL is exactly 0
+    if (tid == 0) prm.redo_mask[blockIdx.x] = 0u;
+    return;
+  }
+  const int c_begin = tl.chunk * prm.chunk, c_end = min(C, c_begin + prm.chunk);
+  // warps working side by side: each needs pool room for every run of the tile
+  int share = 1;
+  if (GRAD) {
+    const int nends = nends_s;
+    while (share < kKlWarps && nends > share * prm.pool_cap) share *= 2;
+    if (nends > share * prm.pool_cap) {  // not even one warp with every pool: the whole block is left to the redo launch
+      if (tid == 0) prm.redo_mask[blockIdx.x] = 0xffffffffu >> (32 - (c_end - c_begin));
+      return;
+    }
+  }
+  const int wstep = kKlWarps / share;  // active warps: 0 .. wstep - 1, warp w owns the pools w * share ..
+  // warp w's records: three planes (key, A, B) of share * pool_cap words each
+  const int pool_words = share * prm.pool_cap;
+  const int* pool = reinterpret_cast<const int*>(kl_smem + lay.pool) + (size_t)warp * 3 * pool_words;
+  const unsigned pool_addr = (unsigned)__cvta_generic_to_shared(pool);
+  double kl_total = 0.0;
+
+  if (warp < wstep) {
+    for (int c = c_begin + warp; c < c_end; c += wstep) {
+      KlChan ch;
+      {
+        const int64_t plane = ((int64_t)tl.img * C + c) * ((int64_t)H * W) + tl.w0 + lane;
+        ch.Sp = prm.student[lvl] + plane;
+        ch.Tp = prm.teacher[lvl] + plane;
+      }
+      ch.rowsc = CELL ? nullptr : prm.rows + c;
+      // keep the bases in registers: every address is then one IMAD.WIDE.U32 of a 32-bit element offset
+      asm volatile("" : "+l"(ch.Sp), "+l"(ch.Tp), "+l"(ch.rowsc));
+      ch.ss = ch.st = ch.ws = 0.f;
+      ch.base = 0;
+      kl_stream_pass<CELL, GRAD, R, NB>(tb, ch, W, lane, nact, prm.kscale, pool_addr, pool_words, prm.dbg);
+
+      // ---- bottom of the column: normalisers, KL, parked runs
+      const float nadd = (float)nadd_s;
+      const float ss = ch.ss + nadd, st = ch.st + nadd;
+      const bool col_ok = lane < tl.wn;
+      const bool in_range = ss > 0x1p-90f && ss < 0x1p100f && st > 0x1p-90f && st < 0x1p100f && fabsf(ch.ws) < INFINITY;
+      if (__all_sync(kFull, !col_ok || in_range)) {
+        const float rs = __fdividef(1.f, ss), rt = __fdividef(1.f, st);
+        // KL = ln2 * ws / ss - ln(ss / st): both terms are first order, their difference second order
+        if (col_ok) kl_total += (double)(kLn2 * ch.ws * rs - log1pf((ss - st) * rt));
+        if (GRAD) {
+          const float gcoef = prm.scale[lvl] * prm.temperature / (float)H;  // d loss / d pred = scale * (T/H) * (p - q)
+          float* __restrict__ growc = prm.grad_rows + c;
+          norm_s[warp][lane] = make_float2(rt, rs);
+          __syncwarp();
+          for (int j0 = 0; j0 < ch.base && !(prm.dbg & 4); j0 += 32) {
+            const int j = j0 + lane;
+            const bool have = j < ch.base;
+            const int key = have ? pool[j] : -1 - lane;  // owner * C * 32 + lane of the column
+            float g = 0.f;
+            if (have) {
+              const float2 nr = norm_s[warp][key & 31];
+              g = gcoef * (__int_as_float(pool[j + pool_words]) * nr.x - __int_as_float(pool[j + 2 * pool_words]) * nr.y);
+            }
+            // the lanes whose runs ended with one row sit next to each other and mostly belong to one box: add up
+            // neighbours with the same owner (segmented scan), one red.global per segment
+            const int own = key >> 5;
+            const int prev = __shfl_up_sync(kFull, own, 1), next = __shfl_down_sync(kFull, own, 1);
+            bool open = lane > 0 && prev == own;  // the segment continues to the left
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+              const float gv = __shfl_up_sync(kFull, g, d);
+              const bool ov = __shfl_up_sync(kFull, (int)open, d);
+              if (open && lane >= d) { g += gv; open = ov; }
+            }
+            const bool tail = lane == 31 || next != own;
+            if (have && tail && !(prm.dbg & 1)) atomicAdd(growc + own, g);
+          }
+          __syncwarp();
+        }
+      } else if (lane == 0) {
+        // exponentials out of range for the unshifted sums: this (tile, channel) is redone with exact maxima
+        atomicOr(&redo_s, 1u << (c - c_begin));
+      }
+    }
+  }
+  // loss = scale * T^2 / H * sum over columns of sum_h q (log q - log p)
+  double tot = block_sum(kl_total, red);
+  if (tid == 0) {
+    prm.redo_mask[blockIdx.x] = redo_s;
+    if (tot != 0.0)
+      atomicAdd(prm.loss, tot * (double)prm.scale[lvl] * (double)prm.temperature * (double)prm.temperature / (double)H);
+  }
+}
+
+// The redo launch: (tile, channel) pairs the streaming kernel could not finish, evaluated the way the reference does:
+// column maxima, sums against them, and a gradient sweep that issues one red.global per run.  A CTA takes one list entry
+// at a time, a warp one channel, lane = column.  Rare (logits beyond +-60 / T, or hundreds of boxes crossing one tile),
+// so plain code.
+template <bool CELL, bool GRAD>
+__global__ void __launch_bounds__(32 * kKlWarps) dsgfd_kl_redo_kernel(const __grid_constant__ KlParams prm) {
+  extern __shared__ __align__(16) unsigned char kl_smem[];
+  __shared__ double red[32];
+  int* moff = reinterpret_cast<int*>(kl_smem);
+  float* mw = reinterpret_cast<float*>(kl_smem);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float Temp = prm.temperature;
+  for (int b = blockIdx.x; b < prm.num_blocks; b += gridDim.x) {
+    const unsigned todo = prm.redo_mask[b];
+    if (todo == 0u) continue;  // uniform over the CTA
+    const KlTile tl = kl_decode_tile(prm, b);
+    const int lvl = tl.lvl;
+    const int H = prm.levels[lvl].H, C = prm.C;
+    const unsigned W = (unsigned)prm.levels[lvl].W;
+    const int64_t cell0 = (int64_t)tl.img * prm.cells_per_image + prm.levels[lvl].cell_offset + tl.w0;
+    __syncthreads();
+    for (int i = tid; i < H * 32; i += 32 * kKlWarps) {
+      const int h = i >> 5, l = i & 31;
+      const bool in = l < tl.wn;
+      if (CELL) mw[i] = in ? __ldg(prm.cell_weight + cell0 + (int64_t)h * W + l) : 0.f;
+      else {
+        const int o = in ? __ldg(prm.owner + cell0 + (int64_t)h * W + l) : -1;
+        moff[i] = o >= 0 ? o * C : -1;
+      }
+    }
+    __syncthreads();
+    const int c_begin = tl.chunk * prm.chunk;
+    const float gcoef = prm.scale[lvl] * Temp / (float)H;
+    double kl_total = 0.0;
+    // warp w takes the w-th, (w + 8)-th ... set bit of the mask
+    int nth = 0;
+    for (unsigned rest = todo; rest; rest &= rest - 1u, ++nth) {
+      if ((nth % kKlWarps) != warp) continue;
+      const int c = c_begin + (__ffs(rest) - 1);
+      const int64_t plane = ((int64_t)tl.img * C + c) * ((int64_t)H * W) + tl.w0 + lane;
+      const float* __restrict__ Sp = prm.student[lvl] + plane;
+      const float* __restrict__ Tp = prm.teacher[lvl] + plane;
+      const float* __restrict__ rowsc = CELL ? nullptr : prm.rows + c;
+      auto logits = [&](int h, float& x, float& y, float& tf, int& off) {
+        x = 0.f; y = 0.f; tf = 0.f;
+        float m = 0.f;
+        if (CELL) {
+          m = mw[h * 32 + lane];
+          off = m != 0.f ? 0 : -1;
+        } else {
+          off = moff[h * 32 + lane];
+          if (off >= 0) m = rowsc[off];
+        }
+        if (off >= 0) {
+          tf = Tp[h * W];
+          x = __fdiv_rn(Sp[h * W] * m, Temp);
+          y = __fdiv_rn(tf * m, Temp);
+        }
+      };
+      float Ms = -INFINITY, Mt = -INFINITY;
+      for (int h = 0; h < H; ++h) {
+        float x, y, tf; int off;
+        logits(h, x, y, tf, off);
+        Ms = fmaxf(Ms, x);
+        Mt = fmaxf(Mt, y);
+      }
+      float ss = 0.f, st = 0.f, ws = 0.f;
+      for (int h = 0; h < H; ++h) {
+        float x, y, tf; int off;
+        logits(h, x, y, tf, off);
+        const float ex = expf(x - Ms);
+        ss += ex;
+        st += expf(y - Mt);
+        ws = fmaf(ex, x - y, ws);
+      }
+      if (lane < tl.wn)
+        kl_total += (double)ws / (double)ss - (((double)Ms - (double)Mt) + log((double)ss / (double)st));
+      if (GRAD) {
+        float* __restrict__ growc = prm.grad_rows + c;
+        float acc = 0.f;
+        for (int h = 0; h < H; ++h) {
+          float x, y, tf; int off;
+          logits(h, x, y, tf, off);
+          if (off < 0) continue;
+          acc = fmaf(tf, expf(y - Mt) / st - expf(x - Ms) / ss, acc);
+          const int nx = (h + 1 < H) ? moff[(h + 1) * 32 + lane] : -1;
+          if (nx != off) {
+            atomicAdd(growc + off, gcoef * acc);
             acc = 0.f;
           }
         }
-      )
-      if (zero_any) {
-        // some mask value of this channel underflowed to 0: the logits of such a run are all 0, p - t is one
-        // constant, and the registers carry no trace of the teacher feature -- walk the rows again
-        const float d0 = fast_ex2(nmt) * rt - fast_ex2(nms) * rs;
-        const float* __restrict__ Tp = prm.teacher[lvl] + plane;
-        float tsum = 0.f;
-        for (int r = 0; r < nrows; ++r) {
-          const int o = col_ok ? __ldg(prm.owner + cell0 + r * uW) : -1;
-          const int nx = (col_ok && r + 1 < nrows) ? __ldg(prm.owner + cell0 + (r + 1) * uW) : -1;
-          const bool zero = o >= 0 && mtab[o - omin + 1] == 0.f;
-          if (zero) tsum += ld_stream_f1(Tp + r * uW);
-          if (nx != o) {
-            if (zero) atomicAdd(prm.grad_rows + (int64_t)o * C + c, gcoef * tsum * d0);
-            tsum = 0.f;
+      }
+    }
+    double tot = block_sum(kl_total, red);
+    if (tid == 0 && tot != 0.0)
+      atomicAdd(prm.loss, tot * (double)prm.scale[lvl] * (double)Temp * (double)Temp / (double)H);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Encoder-memory layout [S, N, C] (channel fastest; head_il.py:866-880 takes [N,C,H,W] *views* of it for sg_out /
+// fg_only): per-cell mask weights only, forward only (those masks are constants and the target is detached, so nothing
+// receives a gradient: SURVEY A3-var).  A warp owns one column (level, image, w) and 128 channels, lane = 4 consecutive
+// channels: every feature load is one aligned 512 B piece of a token row, the weight of a cell is warp-uniform, and
+// cells with weight 0 are skipped exactly (they add e^0 to both sums in closed form).
+constexpr int kSncWarps = 8;
+constexpr int kSncRows = 4;  // rows loaded ahead of the arithmetic (8 x 512 B in flight per warp)
+
+struct KlSncParams {
+  DskdLevel levels[DSKD_MAX_LEVELS];
+  float scale[DSKD_MAX_LEVELS];
+  int task_start[DSKD_MAX_LEVELS + 1];  // first warp task of each level; task = ((img * W + w) * groups + group)
+  int num_levels, N, C, groups;         // groups of 128 channels
+  float temperature, kscale;
+  int64_t cells_per_image;
+  const float* student;
+  const float* teacher;
+  const float* cell_weight;
+  double* loss;
+  unsigned* redo_mask;                  // [tasks / groups] bit g: group g of the column is left to the redo launch
+};
+
+__device__ __forceinline__ float kl_col(float ss, float st, float ws) {
+  // KL = ln2 * ws / ss - ln(ss / st): both terms are first order, their difference second order
+  return kLn2 * ws * __fdividef(1.f, ss) - log1pf((ss - st) * __fdividef(1.f, st));
+}
+__device__ __forceinline__ bool kl_in_range(float ss, float st, float ws) {
+  return ss > 0x1p-90f && ss < 0x1p100f && st > 0x1p-90f && st < 0x1p100f && fabsf(ws) < INFINITY;
+}
+
+struct KlSncTask {
+  int lvl, img, w, group;
+};
+__device__ __forceinline__ KlSncTask kl_snc_decode(const KlSncParams& prm, int task) {
+  KlSncTask t;
+  t.lvl = 0;
+#pragma unroll
+  for (int k = 1; k < DSKD_MAX_LEVELS; ++k)
+    if (k < prm.num_levels && task >= prm.task_start[k]) t.lvl = k;
+  int idx = task - prm.task_start[t.lvl];
+  t.group = idx % prm.groups;
+  idx /= prm.groups;
+  t.w = idx % prm.levels[t.lvl].W;
+  t.img = idx / prm.levels[t.lvl].W;
+  return t;
+}
+
+__global__ void __launch_bounds__(32 * kSncWarps, 4) dsgfd_kl_snc_kernel(const __grid_constant__ KlSncParams prm) {
+  __shared__ double red[32];
+  constexpr unsigned kFull = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int task = blockIdx.x * kSncWarps + (threadIdx.x >> 5);
+  double kl_total = 0.0;
+  float loss_scale = 0.f;
+  if (task < prm.task_start[prm.num_levels]) {
+    const KlSncTask tk = kl_snc_decode(prm, task);
+    const int H = prm.levels[tk.lvl].H, W = prm.levels[tk.lvl].W, C = prm.C;
+    const int c0 = tk.group * 128 + lane * 4;
+    const bool ch_ok = c0 < C;  // C % 4 == 0 (host): a lane's four channels exist together
+    const float* __restrict__ wcol = prm.cell_weight + (int64_t)tk.img * prm.cells_per_image + prm.levels[tk.lvl].cell_offset + tk.w;
+    // token (h, w) of image img: ((cell_offset + h * W + w) * N + img) * C
+    const int64_t tok0 = ((prm.levels[tk.lvl].cell_offset + tk.w) * (int64_t)prm.N + tk.img) * C + (ch_ok ? c0 : 0);
+    const int64_t pitch = (int64_t)W * prm.N * C;
+    const float* __restrict__ Sp = prm.student + tok0;
+    const float* __restrict__ Tp = prm.teacher + tok0;
+    float ss[4] = {0.f, 0.f, 0.f, 0.f}, st[4] = {0.f, 0.f, 0.f, 0.f}, ws[4] = {0.f, 0.f, 0.f, 0.f};
+    int visited = 0;
+    for (int h0 = 0; h0 < H; h0 += 32) {
+      // lane = row: the weights of 32 rows of this column, then the rows with a weight one after the other
+      const float wv = (h0 + lane < H) ? __ldg(wcol + (int64_t)(h0 + lane) * W) : 0.f;
+      unsigned todo = __ballot_sync(kFull, wv != 0.f);
+      visited += __popc(todo);
+      while (todo) {
+        float4 sv[kSncRows], tv[kSncRows];
+        float mk[kSncRows];
+        // slots past the last row of this batch compute e^0 like a cell of weight 0: counted as visited so that the
+        // closed-form term below takes them out again
+        visited += max(0, kSncRows - __popc(todo));
+#pragma unroll
+        for (int i = 0; i < kSncRows; ++i) {
+          const int r = todo ? __ffs(todo) - 1 : -1;
+          todo &= todo - 1u;  // (0 stays 0)
+          mk[i] = r >= 0 ? __shfl_sync(kFull, wv, r) * prm.kscale : 0.f;
+          if (r >= 0 && ch_ok) {
+            sv[i] = ld_stream_f4(Sp + (h0 + r) * pitch);
+            tv[i] = ld_stream_f4(Tp + (h0 + r) * pitch);
+          } else {
+            sv[i] = tv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < kSncRows; ++i) {
+          const float xs[4] = {sv[i].x * mk[i], sv[i].y * mk[i], sv[i].z * mk[i], sv[i].w * mk[i]};
+          const float ys[4] = {tv[i].x * mk[i], tv[i].y * mk[i], tv[i].z * mk[i], tv[i].w * mk[i]};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float e = fast_ex2(xs[j]), f = fast_ex2(ys[j]);
+            ss[j] += e;
+            st[j] += f;
+            ws[j] = fmaf(e, xs[j] - ys[j], ws[j]);
           }
         }
       }
     }
-  };
-
-  for (int sc = c_begin; sc < c_end; sc += chs) {
-    const int nch = min(chs, c_end - sc);
-    if (!CELL) {
-      __syncthreads();  // the readers of the previous sub-chunk are done
-      for (int cc = tid; cc < nch; cc += 32 * MAXW) {
-        rows_s[cc * nstride] = 0.f;  // cells outside boxes
-        zero_s[cc] = 0;
-      }
-      __syncthreads();
-      for (int i = tid; i < nown * nch; i += 32 * MAXW) {
-        const int o = i / nch, cc = i - o * nch;
-        float m = __ldg(prm.rows + (int64_t)(omin + o) * C + sc + cc);
-        if (POW2) m *= prm.inv_temperature;
-        rows_s[cc * nstride + o + 1] = m;
-        if (m == 0.f) zero_s[cc] = 1;
-      }
-      __syncthreads();
+    // cells never visited have logit 0: e^0 each
+    const float nadd = (float)(H - visited);
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      ss[j] += nadd;
+      st[j] += nadd;
+      ok = ok && kl_in_range(ss[j], st[j], ws[j]);
     }
-    if (active) {
-      for (int cc = group; cc < nch; cc += groups) {
-        const bool zero_any = !CELL && zero_s[cc] != 0;
-        if (nrows == kColRows) channel(std::true_type{}, sc + cc, rows_s + cc * nstride, zero_any);
-        else channel(std::false_type{}, sc + cc, rows_s + cc * nstride, zero_any);
+    if (__all_sync(kFull, !ch_ok || ok)) {
+      if (ch_ok) {
+        float k4 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) k4 += kl_col(ss[j], st[j], ws[j]);
+        kl_total = (double)k4;
       }
+    } else if (lane == 0) {
+      atomicOr(prm.redo_mask + task / prm.groups, 1u << tk.group);
     }
+    loss_scale = prm.scale[tk.lvl] * prm.temperature * prm.temperature / (float)H;
   }
-#undef DSKD_MOFF
-#undef DSKD_MTAB
-#undef DSKD_FOR_ROWS_ON
-  // loss = scale * T^2 / H * sum over columns of sum_h t (log t - log p)
-  double tot = block_sum(kl_total, red);
-  if (tid == 0 && tot != 0.0) atomicAdd(prm.loss, tot * (double)scale * (double)Temp * (double)Temp / (double)H);
+  // the warps of a CTA may sit on different levels: scale per warp before the block sum
+  double tot = block_sum(kl_total * (double)loss_scale, red);
+  if (threadIdx.x == 0 && tot != 0.0) atomicAdd(prm.loss, tot);
+}
+
+// redo launch of the [S,N,C] kernel: exact maxima, lane = channel, one warp per flagged (column, 128-channel group)
+__global__ void __launch_bounds__(32 * kSncWarps) dsgfd_kl_snc_redo_kernel(const __grid_constant__ KlSncParams prm) {
+  __shared__ double red[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int columns = prm.task_start[prm.num_levels] / prm.groups;
+  const float Temp = prm.temperature;
+  for (int col0 = blockIdx.x * kSncWarps; col0 < columns; col0 += gridDim.x * kSncWarps) {
+    const int col = col0 + warp;
+    const unsigned todo = col < columns ? prm.redo_mask[col] : 0u;
+    double kl_total = 0.0;
+    for (unsigned rest = todo; rest; rest &= rest - 1u) {
+      const int group = __ffs(rest) - 1;
+      const KlSncTask tk = kl_snc_decode(prm, col * prm.groups + group);
+      const int H = prm.levels[tk.lvl].H, W = prm.levels[tk.lvl].W, C = prm.C;
+      const float* __restrict__ wcol = prm.cell_weight + (int64_t)tk.img * prm.cells_per_image + prm.levels[tk.lvl].cell_offset + tk.w;
+      const int64_t pitch = (int64_t)W * prm.N * C;
+      double kl_group = 0.0;
+      for (int cc = lane; cc < 128; cc += 32) {
+        const int c = group * 128 + cc;
+        if (c >= C) break;
+        const int64_t tok0 = ((prm.levels[tk.lvl].cell_offset + tk.w) * (int64_t)prm.N + tk.img) * C + c;
+        const float* __restrict__ Sp = prm.student + tok0;
+        const float* __restrict__ Tp = prm.teacher + tok0;
+        auto logits = [&](int h, float& x, float& y) {
+          const float wv = wcol[(int64_t)h * W];
+          x = wv != 0.f ? __fdiv_rn(Sp[h * pitch] * wv, Temp) : 0.f;
+          y = wv != 0.f ? __fdiv_rn(Tp[h * pitch] * wv, Temp) : 0.f;
+        };
+        float Ms = -INFINITY, Mt = -INFINITY;
+        for (int h = 0; h < H; ++h) {
+          float x, y;
+          logits(h, x, y);
+          Ms = fmaxf(Ms, x);
+          Mt = fmaxf(Mt, y);
+        }
+        float ss = 0.f, st = 0.f, ws = 0.f;
+        for (int h = 0; h < H; ++h) {
+          float x, y;
+          logits(h, x, y);
+          const float ex = expf(x - Ms);
+          ss += ex;
+          st += expf(y - Mt);
+          ws = fmaf(ex, x - y, ws);
+        }
+        kl_group += (double)ws / (double)ss - (((double)Ms - (double)Mt) + log((double)ss / (double)st));
+      }
+      kl_total += kl_group * (double)prm.scale[tk.lvl] * (double)Temp * (double)Temp / (double)H;
+    }
+    double tot = block_sum(kl_total, red);
+    if (threadIdx.x == 0 && tot != 0.0) atomicAdd(prm.loss, tot);
+  }
 }
 
 }  // namespace dskd
 
 using namespace dskd;
+
+// one 32-bit channel mask per block of the streaming grid, for the smallest chunk (1 channel per block)
+extern "C" int64_t dskd_dsgfd_kl_workspace_bytes(int32_t N, int32_t num_levels, const DskdLevel* levels, int32_t C) {
+  if (N < 0 || num_levels <= 0 || num_levels > DSKD_MAX_LEVELS || levels == nullptr || C <= 0) return -1;
+  int64_t tiles = 0, columns = 0;
+  for (int l = 0; l < num_levels; ++l) {
+    tiles += (levels[l].W + 31) / 32;
+    columns += levels[l].W;
+  }
+  // NCHW: a word per block of the streaming grid; [S,N,C]: a word per (image, level, w) column
+  return std::max<int64_t>(16, 4 * std::max<int64_t>(tiles * N * (int64_t)C, columns * N));
+}
+
+static int launch_kl_snc(const DskdDsgfdKlArgs* a, cudaStream_t st) {
+  DSKD_REQUIRE(a->d_cell_weight != nullptr && a->d_grad_rows == nullptr,
+               "dsgfd_kl: the [S,N,C] layout takes per-cell masks (sg_out / fg_only), forward only");
+  DSKD_REQUIRE(a->C % 4 == 0 && a->C <= 4096 && aligned16(a->d_student[0]) && aligned16(a->d_teacher[0]),
+               "dsgfd_kl: [S,N,C] needs C %% 4 == 0, C <= 4096 and 16-byte aligned memory");
+  KlSncParams prm;
+  memset(&prm, 0, sizeof(prm));
+  prm.num_levels = a->num_levels;
+  prm.N = a->N;
+  prm.C = a->C;
+  prm.groups = (a->C + 127) / 128;
+  prm.temperature = a->temperature;
+  prm.kscale = (float)(1.4426950408889634 / (double)a->temperature);
+  prm.cells_per_image = a->cells_per_image;
+  prm.student = a->d_student[0];
+  prm.teacher = a->d_teacher[0];
+  prm.cell_weight = a->d_cell_weight;
+  prm.loss = a->d_loss;
+  prm.redo_mask = static_cast<unsigned*>(a->d_workspace);
+  int64_t tasks = 0, columns = 0;
+  for (int l = 0; l < a->num_levels; ++l) {
+    prm.levels[l] = a->levels[l];
+    prm.scale[l] = a->scale[l];
+    prm.task_start[l] = (int)tasks;
+    tasks += (int64_t)a->levels[l].W * a->N * prm.groups;
+    columns += (int64_t)a->levels[l].W * a->N;
+  }
+  DSKD_REQUIRE(tasks < (1ll << 31), "dsgfd_kl: too many columns");
+  prm.task_start[a->num_levels] = (int)tasks;
+  DSKD_CUDA_OK(cudaMemsetAsync(prm.redo_mask, 0, (size_t)columns * 4, st));
+  const int blocks = (int)ceil_div(tasks, kSncWarps);
+  dsgfd_kl_snc_kernel<<<blocks, 32 * kSncWarps, 0, st>>>(prm);
+  DSKD_LAUNCH_OK("dsgfd_kl_snc_kernel");
+  dsgfd_kl_snc_redo_kernel<<<kKlRedoCtas, 32 * kSncWarps, 0, st>>>(prm);
+  DSKD_LAUNCH_OK("dsgfd_kl_snc_redo_kernel");
+  return DSKD_OK;
+}
 
 extern "C" int dskd_dsgfd_kl_fwd_bwd(const DskdDsgfdKlArgs* a, void* stream) {
   DSKD_REQUIRE(a != nullptr, "dskd_dsgfd_kl_fwd_bwd: null args");
@@ -660,110 +762,105 @@ extern "C" int dskd_dsgfd_kl_fwd_bwd(const DskdDsgfdKlArgs* a, void* stream) {
   DSKD_REQUIRE(cell != (a->d_owner != nullptr), "dsgfd_kl: exactly one of d_owner / d_cell_weight must be set");
   DSKD_REQUIRE(a->d_loss != nullptr, "dsgfd_kl: d_loss is null");
   DSKD_REQUIRE(cell || a->num_pairs == 0 || a->d_rows != nullptr, "dsgfd_kl: d_rows is null");
+  // (owner * C) * 32 + lane is one 32-bit key of the run records
+  DSKD_REQUIRE(cell || (int64_t)a->num_pairs * a->C < (1ll << 26), "dsgfd_kl: num_pairs * C must stay below 2^26");
+  DSKD_REQUIRE(a->layout == DSKD_LAYOUT_NCHW || a->layout == DSKD_LAYOUT_SNC, "dsgfd_kl: bad layout %d", a->layout);
   if (a->N == 0) return DSKD_OK;
+  const int64_t ws_bytes = dskd_dsgfd_kl_workspace_bytes(a->N, a->num_levels, a->levels, a->C);
+  DSKD_REQUIRE(a->d_workspace != nullptr && a->workspace_bytes >= ws_bytes && (reinterpret_cast<uintptr_t>(a->d_workspace) & 15u) == 0,
+               "dsgfd_kl: workspace must be %lld bytes (dskd_dsgfd_kl_workspace_bytes), 16-byte aligned", (long long)ws_bytes);
   KlParams prm;
+  memset(&prm, 0, sizeof(prm));
   prm.num_levels = a->num_levels;
   prm.N = a->N;
   prm.C = a->C;
   prm.temperature = a->temperature;
-  prm.inv_temperature = 1.f / a->temperature;
+  prm.kscale = (float)(1.4426950408889634 / (double)a->temperature);
   prm.cells_per_image = a->cells_per_image;
   prm.owner = a->d_owner;
   prm.rows = a->d_rows;
   prm.grad_rows = a->d_grad_rows;
   prm.cell_weight = a->d_cell_weight;
   prm.loss = a->d_loss;
+  prm.redo_mask = static_cast<unsigned*>(a->d_workspace);
   int64_t cells = 0;
   int max_h = 0;
   for (int l = 0; l < a->num_levels; ++l) {
     DSKD_REQUIRE(a->levels[l].H > 0 && a->levels[l].W > 0 && a->levels[l].cell_offset == cells,
                  "dsgfd_kl: level %d is not densely packed", l);
-    DSKD_REQUIRE(a->d_student[l] && a->d_teacher[l], "dsgfd_kl: null feature pointer at level %d", l);
+    DSKD_REQUIRE(a->layout == DSKD_LAYOUT_SNC ? (l > 0 || (a->d_student[0] && a->d_teacher[0])) : (a->d_student[l] && a->d_teacher[l]),
+                 "dsgfd_kl: null feature pointer at level %d", l);
+    DSKD_REQUIRE((int64_t)a->levels[l].H * a->levels[l].W < (1ll << 31), "dsgfd_kl: level %d too large", l);
     cells += (int64_t)a->levels[l].H * a->levels[l].W;
     max_h = std::max(max_h, a->levels[l].H);
   }
   DSKD_REQUIRE(cells == a->cells_per_image, "dsgfd_kl: cells_per_image mismatch");
   cudaStream_t st = as_stream(stream);
-  int texp = 0;
-  const bool pow2 = frexpf(a->temperature, &texp) == 0.5f;  // T = 2^k: the division by T is an exact scaling
-
-  // box masks on levels of at most 16 x kColRows rows: the register-resident column kernel
-  if (max_h <= 16 * kColRows && (cell || a->num_pairs <= kColMaxPairs)) {
-    KlColParams cp;
-    cp.num_levels = a->num_levels;
-    cp.N = a->N;
-    cp.C = a->C;
-    cp.temperature = a->temperature;
-    cp.inv_temperature = 1.f / a->temperature;
-    cp.cells_per_image = a->cells_per_image;
-    cp.owner = a->d_owner;
-    cp.cell_weight = a->d_cell_weight;
-    cp.rows = a->d_rows;
-    cp.grad_rows = a->d_grad_rows;
-    cp.loss = a->d_loss;
-    cp.chunk = kColChunk;
-    const int max_parts = (max_h + kColRows - 1) / kColRows;
-    const int maxw = max_parts <= 4 ? 4 : (max_parts <= 8 ? 8 : 16);
-    const int nchunks = (a->C + cp.chunk - 1) / cp.chunk;
-    int blocks = 0;
-    for (int l = 0; l < a->num_levels; ++l) {
-      cp.levels[l] = a->levels[l];
-      cp.student[l] = a->d_student[l];
-      cp.teacher[l] = a->d_teacher[l];
-      cp.scale[l] = a->scale[l];
-      cp.wtiles[l] = (a->levels[l].W + 31) / 32;
-      cp.parts[l] = (a->levels[l].H + kColRows - 1) / kColRows;
-      cp.rpp[l] = (a->levels[l].H + cp.parts[l] - 1) / cp.parts[l];
-      cp.block_start[l] = blocks;
-      blocks += cp.wtiles[l] * nchunks * a->N;
-    }
-    cp.block_start[a->num_levels] = blocks;
-#define DSKD_COL_LAUNCH(MW)                                                                        \
-  do {                                                                                             \
-    if (cell) {                                                                                    \
-      if (pow2) dsgfd_kl_col_kernel<MW, true, true><<<blocks, 32 * MW, 0, st>>>(cp);               \
-      else dsgfd_kl_col_kernel<MW, false, true><<<blocks, 32 * MW, 0, st>>>(cp);                   \
-    } else {                                                                                       \
-      if (pow2) dsgfd_kl_col_kernel<MW, true, false><<<blocks, 32 * MW, 0, st>>>(cp);              \
-      else dsgfd_kl_col_kernel<MW, false, false><<<blocks, 32 * MW, 0, st>>>(cp);                  \
-    }                                                                                              \
-  } while (0)
-    if (maxw == 4) DSKD_COL_LAUNCH(4);
-    else if (maxw == 8) DSKD_COL_LAUNCH(8);
-    else DSKD_COL_LAUNCH(16);
-#undef DSKD_COL_LAUNCH
-    DSKD_LAUNCH_OK("dsgfd_kl_col_kernel");
-    return DSKD_OK;
-  }
+  if (a->layout == DSKD_LAYOUT_SNC) return launch_kl_snc(a, st);
   DSKD_REQUIRE(max_h <= kKlMaxH, "dsgfd_kl: H (%d) above the supported %d", max_h, kKlMaxH);
-  // shared memory: owner strip (128 B per row) + two logit strips (256 B per row) per warp
-  int warps = (int)std::min<int64_t>(kKlMaxWarps, ((int64_t)kKlSmemBudget - (int64_t)kl_header_bytes(max_h)) / (8ll * kKlCols * max_h));
-  DSKD_REQUIRE(warps >= 1, "dsgfd_kl: H (%d) does not fit the shared-memory strips", max_h);
-  warps = std::min(warps, std::max(1, a->C / kKlChan));
-  prm.warps = warps;
+  // tuning hook (tools/kl_perf.py): DSKD_KL_TUNE="rows_per_block,stages,ctas_per_sm,channels_per_cta,pool_records,dbg"
+  int blk = kKlBlk, stages = kKlStages, minb = kKlMinCtas, chunk = kKlChunk, cap = kKlPool, dbg = 0;
+  if (const char* tune = getenv("DSKD_KL_TUNE")) sscanf(tune, "%d,%d,%d,%d,%d,%d", &blk, &stages, &minb, &chunk, &cap, &dbg);
+  DSKD_REQUIRE(chunk >= 1 && chunk <= 32 && cap >= 1, "dsgfd_kl: bad DSKD_KL_TUNE");
+  prm.max_blocks = (max_h + blk - 1) / blk;
   prm.max_h = max_h;
-  const int ch_per_cta = warps * kKlChan;
-  const int nchunks = (a->C + ch_per_cta - 1) / ch_per_cta;
+  prm.chunk = std::min(a->C, chunk);
+  prm.pool_cap = cap;
+  prm.dbg = dbg;
+  const int nchunks = (a->C + prm.chunk - 1) / prm.chunk;
   int blocks = 0;
   for (int l = 0; l < a->num_levels; ++l) {
     prm.levels[l] = a->levels[l];
     prm.student[l] = a->d_student[l];
     prm.teacher[l] = a->d_teacher[l];
     prm.scale[l] = a->scale[l];
-    prm.wtiles[l] = (a->levels[l].W + kKlCols - 1) / kKlCols;
+    prm.wtiles[l] = (a->levels[l].W + 31) / 32;
+    prm.wpt[l] = (a->levels[l].W + prm.wtiles[l] - 1) / prm.wtiles[l];
     prm.block_start[l] = blocks;
     blocks += prm.wtiles[l] * nchunks * a->N;
   }
   prm.block_start[a->num_levels] = blocks;
-  const size_t smem = kl_header_bytes(max_h) + 8ull * kKlCols * max_h * warps;
-#define DSKD_KL_LAUNCH(CELLV, P2V)                                                                                  \
-  do {                                                                                                              \
-    DSKD_CUDA_OK(cudaFuncSetAttribute(dsgfd_kl_kernel<CELLV, P2V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    dsgfd_kl_kernel<CELLV, P2V><<<blocks, 32 * warps, smem, st>>>(prm);                                             \
+  prm.num_blocks = blocks;
+  const bool grad = !cell && a->d_grad_rows != nullptr;
+  const size_t smem = KlSmem(prm.max_blocks, blk, grad, cap).total;
+  DSKD_REQUIRE(smem <= 227 * 1024, "dsgfd_kl: H (%d) needs %zu bytes of shared memory", max_h, smem);
+  bool launched = false;
+#define DSKD_KL_VARIANT(CELLV, GRADV, RV, NBV, MB)                                                              \
+  if (!launched && blk == RV && stages == NBV && minb == MB) {                                                  \
+    DSKD_CUDA_OK(cudaFuncSetAttribute(dsgfd_kl_stream_kernel<CELLV, GRADV, RV, NBV, MB>,                        \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
+    dsgfd_kl_stream_kernel<CELLV, GRADV, RV, NBV, MB><<<blocks, 32 * kKlWarps, smem, st>>>(prm);                \
+    launched = true;                                                                                            \
+  }
+#define DSKD_KL_VARIANTS(CELLV, GRADV)       \
+  DSKD_KL_VARIANT(CELLV, GRADV, 5, 2, 4)     \
+  DSKD_KL_VARIANT(CELLV, GRADV, 5, 2, 3)     \
+  DSKD_KL_VARIANT(CELLV, GRADV, 5, 3, 3)     \
+  DSKD_KL_VARIANT(CELLV, GRADV, 5, 3, 4)     \
+  DSKD_KL_VARIANT(CELLV, GRADV, 4, 3, 4)     \
+  DSKD_KL_VARIANT(CELLV, GRADV, 4, 3, 3)     \
+  DSKD_KL_VARIANT(CELLV, GRADV, 8, 2, 3)     \
+  DSKD_KL_VARIANT(CELLV, GRADV, 4, 2, 5)     \
+  DSKD_KL_VARIANT(CELLV, GRADV, 5, 2, 5)
+  if (cell) { DSKD_KL_VARIANTS(true, false) }
+  else if (grad) { DSKD_KL_VARIANTS(false, true) }
+  else { DSKD_KL_VARIANTS(false, false) }
+#undef DSKD_KL_VARIANTS
+#undef DSKD_KL_VARIANT
+  DSKD_REQUIRE(launched, "dsgfd_kl: no kernel variant for DSKD_KL_TUNE=%d,%d,%d", blk, stages, minb);
+  DSKD_LAUNCH_OK("dsgfd_kl_stream_kernel");
+  // the redo launch: a few loads per CTA when no block left anything behind
+  const size_t redo_smem = (size_t)max_h * 32 * 4;
+#define DSKD_KL_REDO(CELLV, GRADV)                                                                                        \
+  do {                                                                                                                    \
+    DSKD_CUDA_OK(cudaFuncSetAttribute(dsgfd_kl_redo_kernel<CELLV, GRADV>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                      (int)redo_smem));                                                                   \
+    dsgfd_kl_redo_kernel<CELLV, GRADV><<<kKlRedoCtas, 32 * kKlWarps, redo_smem, st>>>(prm);                               \
   } while (0)
-  if (cell) { if (pow2) DSKD_KL_LAUNCH(true, true); else DSKD_KL_LAUNCH(true, false); }
-  else { if (pow2) DSKD_KL_LAUNCH(false, true); else DSKD_KL_LAUNCH(false, false); }
-#undef DSKD_KL_LAUNCH
-  DSKD_LAUNCH_OK("dsgfd_kl_kernel");
+  if (cell) DSKD_KL_REDO(true, false);
+  else if (grad) DSKD_KL_REDO(false, true);
+  else DSKD_KL_REDO(false, false);
+#undef DSKD_KL_REDO
+  DSKD_LAUNCH_OK("dsgfd_kl_redo_kernel");
   return DSKD_OK;
 }

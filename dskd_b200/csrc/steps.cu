@@ -24,22 +24,36 @@ constexpr int64_t kAlign = 256;
 inline int64_t align_up(int64_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
 
 struct Workspace {
-  int64_t cell_map, rows, energy, ids, acc, total;
-  Workspace(int32_t N, int64_t cells, int32_t P, int32_t C) {
+  int64_t cell_map, rows, energy, ids, acc, kl_redo, kl_redo_bytes, total;
+  Workspace(int32_t N, int64_t cells, int32_t P, int32_t C, int64_t kl_bytes = 0) {
     int64_t off = 0;
     cell_map = off; off += align_up((int64_t)N * cells * 4);
     rows = off;     off += align_up((int64_t)std::max(P, 1) * C * 4);
     energy = off;   off += align_up((int64_t)std::max(P, 1) * C * 4);
-    acc = off;      off += align_up(16);      // right after energy: one memset clears both; [8] = finish counter
+    acc = off;      off += align_up(16);      // right after energy: one memset clears both; [8] = finish counter, [12] = KL redo counter
     ids = off;      off += align_up((int64_t)std::max(P, 1) * 8);
+    kl_redo = off;  kl_redo_bytes = kl_bytes; off += align_up(kl_bytes);  // redo list of the KL kernels
     total = off;
   }
 };
 }  // namespace
 
+// Without the level table the KL kernels' workspace (one word per column tile, image and channel) is bounded through
+// sum_l ceil(W_l / 32) <= cells / 32 + levels; dskd_dsgfd_step_workspace_bytes_for() gives the exact figure.
 extern "C" int64_t dskd_dsgfd_step_workspace_bytes(int32_t N, int64_t cells_per_image, int32_t num_pairs, int32_t C) {
   if (N < 0 || cells_per_image < 0 || num_pairs < 0 || C <= 0) return -1;
-  return Workspace(N, cells_per_image, num_pairs, C).total;
+  const int64_t kl = std::max<int64_t>(16, 4 * (cells_per_image / 32 + DSKD_MAX_LEVELS) * N * (int64_t)C);
+  return Workspace(N, cells_per_image, num_pairs, C, kl).total;
+}
+
+extern "C" int64_t dskd_dsgfd_step_workspace_bytes_for(const DskdDsgfdStepArgs* a) {
+  if (a == nullptr || a->N < 0 || a->cells_per_image < 0 || a->num_pairs < 0 || a->C <= 0) return -1;
+  int64_t kl = 0;
+  if (a->criterion == DSKD_CRIT_KL) {
+    kl = dskd_dsgfd_kl_workspace_bytes(a->N, a->num_levels, a->levels, a->C);
+    if (kl < 0) return -1;
+  }
+  return Workspace(a->N, a->cells_per_image, a->num_pairs, a->C, kl).total;
 }
 
 extern "C" int dskd_dsgfd_step(const DskdDsgfdStepArgs* a, void* stream) {
@@ -49,8 +63,10 @@ extern "C" int dskd_dsgfd_step(const DskdDsgfdStepArgs* a, void* stream) {
   DSKD_REQUIRE(a->num_levels > 0 && a->num_levels <= DSKD_MAX_LEVELS && a->N >= 0 && a->C > 0 && a->num_pairs >= 0,
                "dskd_dsgfd_step: bad sizes");
   DSKD_REQUIRE(a->d_loss != nullptr, "dskd_dsgfd_step: d_loss is null");
-  DSKD_REQUIRE(a->criterion == DSKD_CRIT_MSE || a->layout == DSKD_LAYOUT_NCHW, "dskd_dsgfd_step: KL needs the NCHW layout");
-  const Workspace ws(a->N, a->cells_per_image, a->num_pairs, a->C);
+  DSKD_REQUIRE(a->criterion == DSKD_CRIT_MSE || a->layout == DSKD_LAYOUT_NCHW || a->mask_mode >= DSKD_MODE_SG_OUT,
+               "dskd_dsgfd_step: KL on [S,N,C] memory takes the per-cell masks (sg_out / fg_only) only");
+  const int64_t kl_ws = a->criterion == DSKD_CRIT_KL ? dskd_dsgfd_kl_workspace_bytes(a->N, a->num_levels, a->levels, a->C) : 0;
+  const Workspace ws(a->N, a->cells_per_image, a->num_pairs, a->C, kl_ws);
   DSKD_REQUIRE(a->d_workspace != nullptr && a->workspace_bytes >= ws.total &&
                    (reinterpret_cast<uintptr_t>(a->d_workspace) % kAlign) == 0,
                "dskd_dsgfd_step: workspace must be %lld bytes, 256-byte aligned", (long long)ws.total);
@@ -137,6 +153,9 @@ extern "C" int dskd_dsgfd_step(const DskdDsgfdStepArgs* a, void* stream) {
       k.scale[l] = a->scale[l];
     }
     k.d_loss = acc;
+    k.layout = a->layout;
+    k.d_workspace = base + ws.kl_redo;
+    k.workspace_bytes = ws.kl_redo_bytes;
     if (row_mode) {
       k.d_owner = static_cast<const int32_t*>(cell_map); k.d_rows = rows; k.num_pairs = P;
       k.d_grad_rows = want_hs ? energy : nullptr;

@@ -208,7 +208,7 @@ class _DsgfdFn(torch.autograd.Function):
         out = torch.empty(2, dtype=torch.float32, device=dev)          # [loss, matched count (int32 bits)]
         a.d_loss = out.data_ptr()
         a.d_matched_count = out.data_ptr() + 4
-        nbytes = lib.dskd_dsgfd_step_workspace_bytes(N, cells, P, C)
+        nbytes = lib.dskd_dsgfd_step_workspace_bytes_for(a)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         a.d_workspace, a.workspace_bytes = ws.data_ptr(), nbytes
         if profiling.enabled:
@@ -256,7 +256,7 @@ class DSGFeatureDistillLoss(nn.Module):
             `temp` (the head's unused ctor argument, head_il.py:90,124), confidences from
             `assignments['teacher_scores']` (optional).
         feature_source (str): 'neck' -- 4 x [N,C,H,W] (:678-679); 'memory' -- ([S,N,C], spatial_shapes)
-            (:866-880).  decode_* + 'kl' supports 'neck' only.
+            (:866-880).  decode_* + 'kl' takes 'neck' only, like the reference (:678-679).
         validate (bool): read the matched-query count back (one host sync) and raise IndexError like
             the reference (:705) when fewer student queries than teacher detections carry a previous label.
     """
@@ -274,9 +274,10 @@ class DSGFeatureDistillLoss(nn.Module):
         self.temp = float(temp)
         if mask_mode == 'fg_bk' and (criterion != 'mse' or feature_source != 'memory'):
             raise ValueError("mask_mode='fg_bk' is the area-mask MSE on encoder memory (_fg_bk.py:534-578)")
-        if criterion == 'kl' and feature_source != 'neck':
-            raise NotImplementedError("criterion='kl' is implemented for the [N,C,H,W] layout "
-                                      "(pass the per-level views of the memory as feature_source='neck')")
+        if criterion == 'kl' and feature_source == 'memory' and mask_mode in _ROW_MODES:
+            raise NotImplementedError("criterion='kl' on encoder memory is implemented for the per-cell masks the "
+                                      "reference applies there (sg_out / fg_only, head_il.py:865-880,916-923); the "
+                                      "decode_* masks run on the neck features (head_il.py:678-679)")
         self.loss_weight = loss_weight
         self.reduction = reduction
         self.criterion = criterion

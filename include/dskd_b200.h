@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define DSKD_ABI_VERSION 1
+#define DSKD_ABI_VERSION 2
 #define DSKD_MAX_LEVELS 8
 
 typedef enum {
@@ -150,7 +150,9 @@ int dskd_dsgfd_rows_finish(int32_t criterion, const float* d_hs_teacher, const f
  * applied to [C,H,W] so softmax runs over H; target = student*mask, detached; pred = teacher*mask).
  *   loss = sum_{l,i,c,w} scale_l * T^2/H_l * sum_h t_h (log t_h - logp_h)
  * No gradient reaches the student features; row-mask mode accumulates
- * d_grad_rows[p,c] = dLoss/d rows directly.  NCHW layout only.
+ * d_grad_rows[p,c] = dLoss/d rows directly.  Both feature layouts.
+ * One streaming pass (unshifted exponentials) plus a second tiny launch that redoes, with exact column maxima,
+ * the (tile, channel) pairs whose sums left the fp32-safe range; d_workspace holds one channel mask per tile.
  * ------------------------------------------------------------------------------------------- */
 typedef struct {
   int32_t num_levels, N, C;
@@ -166,8 +168,12 @@ typedef struct {
   int32_t num_pairs;
   const float* d_cell_weight;   /* cell-mask mode (no gradient at all)                                  */
   double* d_loss;               /* [1], caller zero-fills                                               */
+  int32_t layout;               /* DSKD_LAYOUT_NCHW (one pointer per level) or DSKD_LAYOUT_SNC ([0] only) */
+  void* d_workspace;            /* >= dskd_dsgfd_kl_workspace_bytes(...) bytes, 16-byte aligned            */
+  int64_t workspace_bytes;      /* (no initialisation needed)                                             */
 } DskdDsgfdKlArgs;
 
+int64_t dskd_dsgfd_kl_workspace_bytes(int32_t N, int32_t num_levels, const DskdLevel* levels, int32_t C);
 int dskd_dsgfd_kl_fwd_bwd(const DskdDsgfdKlArgs* args, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
@@ -211,7 +217,10 @@ typedef struct {
   void* ev_kernel_end;           /* the streaming kernel (bench.py's roofline timing); NULL = off         */
 } DskdDsgfdStepArgs;
 
+/* Workspace size: an upper bound from the sizes alone, and the exact figure for a filled-in argument struct
+ * (criterion, levels, N, C, num_pairs are read). */
 int64_t dskd_dsgfd_step_workspace_bytes(int32_t N, int64_t cells_per_image, int32_t num_pairs, int32_t C);
+int64_t dskd_dsgfd_step_workspace_bytes_for(const DskdDsgfdStepArgs* args);
 int dskd_dsgfd_step(const DskdDsgfdStepArgs* args, void* stream);
 
 /* ---------------------------------------------------------------------------------------------

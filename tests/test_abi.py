@@ -29,6 +29,7 @@ def test_library_exports_every_declared_symbol():
 def test_binding_table_matches_header():
     names = set(declared_functions())
     bound = set(_lib.SIGNATURES) | {'dskd_last_error', 'dskd_launch_count', 'dskd_dsgfd_step_workspace_bytes',
+                                   'dskd_dsgfd_step_workspace_bytes_for', 'dskd_dsgfd_kl_workspace_bytes',
                                    'dskd_qmem_workspace_bytes', 'dskd_struct_size'}
     assert names == bound, (sorted(names - bound), sorted(bound - names))
 
@@ -42,7 +43,7 @@ def test_header_cites_reference_lines():
 
 def test_abi_version_and_error_string():
     lib = _lib.load()
-    assert lib.dskd_abi_version() == 1
+    assert lib.dskd_abi_version() == 2
     rc = lib.dskd_lsap_f64(None, 3, 3, None, None)
     assert rc == _lib.EINVAL
     assert b'dskd_lsap_f64' in lib.dskd_last_error()

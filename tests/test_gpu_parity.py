@@ -246,6 +246,91 @@ def test_dsgfd_cell_masks_neck_mse_and_kl(mode):
         assert_loss(loss, ref)
 
 
+@pytest.mark.parametrize('mode', ['sg_out', 'fg_only'])
+@pytest.mark.parametrize('cfg,channels', [(SMALL, 64), (ODD, 256), (ODD, 136)], ids=['c64', 'c256', 'c136'])
+def test_dsgfd_cell_masks_kl_on_memory_layout(mode, cfg, channels):
+    """KL over H straight on encoder memory [S,N,C] (head_il.py:865-880,916-923): no [N,C,H,W] copy, same numbers."""
+    cpu = synth.make_distill_inputs(num_images=3, num_prev=40, seed=12, channels=channels, **cfg)
+    gpu = cpu.to(DEV)
+    a = cpu.assignments
+    shapes = [tuple(x) for x in a['img_shapes'].tolist()]
+    s_mem, t_mem = gpu.memory()
+    for T in (2.0, 3.0):
+        mod = dskd_b200.DSGFeatureDistillLoss(criterion='kl', T=T, mask_mode=mode, feature_source='memory', loss_weight=0.8)
+        loss = mod((s_mem, gpu.spatial_shapes), (t_mem, gpu.spatial_shapes), (gpu.hs_student, gpu.hs_teacher), gpu.assignments)
+        o_s, o_t = cpu.memory()
+        c64 = ol.KnowledgeDistillationKLDivLoss('sum', 0.8, T)
+        ref64 = (od.sg_out(o_s.double(), o_t.double(), cpu.levels, a['teacher_bboxes'], a['gt_bboxes'], shapes, c64)
+                 if mode == 'sg_out' else od.fg_only(o_s.double(), o_t.double(), cpu.levels, a['teacher_bboxes'], shapes, c64))
+        torch.testing.assert_close(loss.detach().cpu().double(), ref64, rtol=LOSS_RTOL, atol=1e-12)
+        assert not loss.requires_grad                      # constant mask, teacher pred, detached target (SURVEY A3-var)
+        neck = dskd_b200.DSGFeatureDistillLoss(criterion='kl', T=T, mask_mode=mode, feature_source='neck', loss_weight=0.8)
+        same = neck(gpu.student_feats, gpu.teacher_feats, (gpu.hs_student, gpu.hs_teacher), gpu.assignments)
+        torch.testing.assert_close(loss, same, rtol=2e-5, atol=0)
+
+
+def test_dsgfd_kl_rejects_box_masks_on_memory():
+    with pytest.raises(NotImplementedError):
+        dskd_b200.DSGFeatureDistillLoss(criterion='kl', mask_mode='decode_v1', feature_source='memory')
+
+
+@pytest.mark.parametrize('scale', [300.0, 3000.0])
+def test_dsgfd_kl_logits_beyond_the_unshifted_range(scale):
+    """Features so large that e^(feature * mask / T) leaves fp32 without the column maximum subtracted: the streaming
+    kernel hands those (tile, channel) pairs to the redo launch (exact maxima, like kd_loss.py:28-34 via torch softmax)."""
+    cpu = synth.make_distill_inputs(num_images=2, num_prev=40, seed=14, channels=16, **ODD)
+    for f in cpu.student_feats + cpu.teacher_feats:
+        f.mul_(scale)
+    gpu = cpu.to(DEV)
+    mod = dskd_b200.DSGFeatureDistillLoss(criterion='kl')
+    feats, hs = gpu.clone_student()
+    loss = mod(feats, gpu.teacher_feats, (hs, gpu.hs_teacher), gpu.assignments)
+    loss.backward()
+    o_feats, o_hs = cpu.clone_student()
+    ref = oracle_decode(cpu, crit_oracle('kl'), 1, o_feats, o_hs)
+    ref.backward()
+    assert torch.isfinite(loss).all() and torch.isfinite(hs.grad).all()
+    assert_kl_loss(loss, cpu, crit_oracle('kl'), ref)
+    _, g64 = oracle_decode_f64(cpu, crit_oracle('kl'))
+    err_ref = (o_hs.grad.double() - g64).abs().max()
+    got = hs.grad.detach().cpu().double()
+    tol = GRAD_RTOL * g64.abs() + 1e-6 * g64.abs().max() + 4 * err_ref
+    assert ((got - g64).abs() <= tol).all(), (float((got - g64).abs().max()), float(err_ref), float(g64.abs().max()))
+    # the same through the per-cell masks, both layouts (forward only)
+    a = cpu.assignments
+    shapes = [tuple(x) for x in a['img_shapes'].tolist()]
+    o_s, o_t = cpu.memory()
+    ref64 = od.fg_only(o_s.double(), o_t.double(), cpu.levels, a['teacher_bboxes'], shapes, crit_oracle('kl'))
+    s_mem, t_mem = gpu.memory()
+    for src, sf, tf in (('neck', gpu.student_feats, gpu.teacher_feats),
+                        ('memory', (s_mem, gpu.spatial_shapes), (t_mem, gpu.spatial_shapes))):
+        cell = dskd_b200.DSGFeatureDistillLoss(criterion='kl', mask_mode='fg_only', feature_source=src)
+        got = cell(sf, tf, (gpu.hs_student, gpu.hs_teacher), gpu.assignments)
+        torch.testing.assert_close(got.detach().cpu().double(), ref64, rtol=LOSS_RTOL, atol=1e-12)
+
+
+@pytest.mark.parametrize('pool', [64, 12, 2], ids=['shared_pools', 'one_warp', 'redo'])
+def test_dsgfd_kl_many_runs_per_tile(pool, monkeypatch):
+    """Crowded images: more runs of rows per column tile than one warp's record pool holds.  With a small pool
+    (DSKD_KL_TUNE) the CTA first runs fewer warps with several pools each and finally leaves the tile to the redo launch;
+    all three must give the reference's numbers."""
+    cpu = synth.make_distill_inputs(num_images=2, num_prev=40, seed=15, channels=32, num_query=100, k_range=(30, 40), **{
+        k: v for k, v in SMALL.items() if k not in ('k_range', 'num_query')})
+    gpu = cpu.to(DEV)
+    monkeypatch.setenv('DSKD_KL_TUNE', f'5,2,4,16,{pool},0')
+    mod = dskd_b200.DSGFeatureDistillLoss(criterion='kl')
+    feats, hs = gpu.clone_student()
+    loss = mod(feats, gpu.teacher_feats, (hs, gpu.hs_teacher), gpu.assignments)
+    loss.backward()
+    torch.cuda.synchronize()
+    monkeypatch.delenv('DSKD_KL_TUNE')
+    o_feats, o_hs = cpu.clone_student()
+    ref = oracle_decode(cpu, crit_oracle('kl'), 1, o_feats, o_hs)
+    ref.backward()
+    assert_kl_loss(loss, cpu, crit_oracle('kl'), ref)
+    assert_grad(hs.grad, o_hs.grad)
+
+
 @pytest.mark.parametrize('num_prev', [40, 70])
 @pytest.mark.parametrize('reduction', ['mean', 'sum'])
 def test_bcdd_vs_oracle(num_prev, reduction):
@@ -311,6 +396,7 @@ GOLDEN_CASES = [('head_decode_v1_mse.npz', 'decode_v1', 'mse', 'neck'),
                 ('head_decode_v2_mse_n1.npz', 'decode_v2', 'mse', 'neck'),
                 ('head_sg_out_mse.npz', 'sg_out', 'mse', 'memory'),
                 ('head_sg_out_kl.npz', 'sg_out', 'kl', 'neck'),
+                ('head_sg_out_kl.npz', 'sg_out', 'kl', 'memory'),     # the layout the reference views (head_il.py:879-880)
                 ('head_fg_only_mse.npz', 'fg_only', 'mse', 'memory')]
 
 

@@ -10,8 +10,17 @@ One "step" = distillation loss forward + backward for one batch of synthetic COC
 DSG-FD (decode_v1 mask, masked MSE) over 4-level 256-channel features + BCDD over the last-layer
 decoder embeddings, `images_per_gpu` 800x1333 images per rank (weak scaling; per-class prototype
 sums/counts are the only cross-rank state: one NCCL all-reduce).  Prints ONE JSON line on rank 0.
+
+Besides the headline the line carries, measured in the same run:
+  kl            the same step with the criterion every shipped config uses (KL over H, T = 2) and its kernel's roofline
+  configs       BASELINE.json configs 3-5: 70+10 at 8 images/GPU, 50+30 and 60+20 at 4 images/GPU (prototype all-reduce
+                at every N), and a trimmed token x query x batch sweep with the CPU port beside its smallest point
+  multi_rank_parity  (N > 1) the synced BCDD loss / gradient of this rank against the single-process evaluation of the
+                concatenated batch on rank 0 (SURVEY.md 8e parity definition)
+  train_step    the 40+40 incremental training step hosting the losses
 """
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -28,8 +37,11 @@ if ROOT not in sys.path:
 
 METRIC = 'distill_loss_fwd_bwd_images_per_s'
 UNIT = 'images/s'
-BYTES_PER_IMAGE_MSE = 3 * 22223 * 256 * 4      # read S + read T + write dS  (SURVEY.md section 8d): 68.27 MB
+COCO_TOKENS = 22223
 WORKLOAD = 'coco_40+40_dsgfd_mse+bcdd'
+PARITY_NOTE = ('loss rtol 1e-4 / grad rtol 1e-3 vs the fp32 oracle and the reference golden outputs (tests/); KL-over-H loss: '
+               '1e-4 vs the float64 evaluation of the reference formula, 1e-3 vs its fp32 evaluation (a second-order quantity: '
+               "the reference's own fp32 value carries 1.4e-4..3.7e-4 of noise, DESIGN.md section 2)")
 
 
 def parse_args():
@@ -49,6 +61,9 @@ def parse_args():
     ap.add_argument('--cpu-sample-images', type=int, default=2)
     ap.add_argument('--no-feeders', action='store_true', help='skip the teacher keep-id / assignment timings')
     ap.add_argument('--no-contraction', action='store_true', help='skip the tcgen05 query x memory kernel line')
+    ap.add_argument('--no-kl', action='store_true', help='skip the KL-criterion extra key')
+    ap.add_argument('--no-configs', action='store_true', help='skip BASELINE configs 3-5 (L=70/50/60, sweep)')
+    ap.add_argument('--no-train-step', action='store_true', help='skip the 40+40 training-step extra key')
     ap.add_argument('--contraction-queries', type=int, default=300,
                     help="queries contracted against every memory token (north_star: ~300 x 256 against ~20k x 256)")
     return ap.parse_args()
@@ -76,6 +91,14 @@ def recorded_traffic(kernel, images_per_gpu):
     if rec and int(rec.get('images_per_gpu', -1)) == int(images_per_gpu):
         return rec
     return None
+
+
+def algorithmic_bytes(criterion, tokens, channels, images):
+    """masked MSE fwd+bwd reads S, T and writes dS; KL fwd+bwd reads S and T (no feature gradient)."""
+    return (3 if criterion == 'mse' else 2) * tokens * channels * 4 * images
+
+
+STREAM_KERNEL = {'mse': 'dsgfd_mse_nchw_kernel', 'kl': 'dsgfd_kl_stream_kernel'}
 
 
 def time_path_feeders(args, dev, N):
@@ -116,7 +139,7 @@ def time_contraction(args, dev, N, world, dist):
     against the 22 223 x 256 memory tokens of each of this rank's N images; CUDA-graph replay, L2 flushed between
     replays, CUDA events; FLOPs = 2*K*C*S per image."""
     from dskd_b200 import qmem
-    K, S, C, Q = args.contraction_queries, 22223, 256, max(300, args.contraction_queries)
+    K, S, C, Q = args.contraction_queries, COCO_TOKENS, 256, max(300, args.contraction_queries)
     g = torch.Generator(device=dev).manual_seed(4321)
     mem = torch.randn(S, N, C, device=dev, generator=g)
     hs = torch.randn(N, Q, C, device=dev, generator=g)
@@ -148,15 +171,18 @@ def time_contraction(args, dev, N, world, dist):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
+    del graph
     flop = 2.0 * K * C * S * N
     _, bf16_peak, src = peaks()
     achieved = flop / (ms * 1e-3) / 1e12
+    traffic_rec = recorded_traffic('qmem_weight_kernel', N)
     return {'bound': 'tensor', 'kernel': 'qmem_weight_kernel (tcgen05.mma kind::tf32, TMA-fed, TMEM accumulators)',
             'achieved': achieved, 'peak': bf16_peak, 'unit': 'TFLOP/s', 'frac': achieved / bf16_peak,
             'frac_of_tf32_rate': achieved / (bf16_peak / 2),
             'peak_source': f'{src}: cuBLAS bf16 dense; kind::tf32 issues at half that rate',
             'flop_per_launch': flop, 'call_ms': ms, 'queries': K, 'tokens': S, 'channels': C, 'images': N,
-            'images_per_s': world * N / (ms * 1e-3), 'traffic': None,
+            'images_per_s': world * N / (ms * 1e-3), 'traffic': (traffic_rec or {}).get('dram_bytes_per_launch'),
+            'traffic_source': (traffic_rec or {}).get('source'),
             'timing': 'gather + contraction + combine, CUDA-graph replay, L2 flushed between replays, median'}
 
 
@@ -231,21 +257,21 @@ def cpu_reference_step(cpu_inputs, criterion):
     loss = loss + ob.bcdd_loss(hs.reshape(-1, C), a['student_labels'], cpu_inputs.hs_teacher.reshape(-1, C),
                                a['teacher_keepid'], a['teacher_labels'], a['prev_labels'], ol.MSELoss('mean', 1.0))
     loss.backward()
-    return float(loss)
+    return float(loss.detach())
 
 
-def time_cpu_reference(args, steps, warmup):
+def time_cpu_reference(criterion, num_prev, n, steps, warmup, levels=None, num_query=300):
     from dskd_b200 import synth
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    n = args.cpu_sample_images
-    cpu_inputs = synth.make_distill_inputs(num_images=n, num_prev=args.num_prev, seed=1234)
+    kw = {} if levels is None else dict(levels=levels)
+    cpu_inputs = synth.make_distill_inputs(num_images=n, num_prev=num_prev, seed=1234, num_query=num_query, **kw)
     for _ in range(warmup):
-        cpu_reference_step(cpu_inputs, args.criterion)
+        cpu_reference_step(cpu_inputs, criterion)
     times = []
     for _ in range(steps):
         t0 = time.perf_counter()
-        cpu_reference_step(cpu_inputs, args.criterion)
+        cpu_reference_step(cpu_inputs, criterion)
         times.append(time.perf_counter() - t0)
     total = sum(times)
     return dict(value=n * steps / total, unit=UNIT, cores=cores, kind='port',
@@ -258,7 +284,7 @@ def run_reference_arm(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    base, ms = time_cpu_reference(args, args.steps, args.warmup)
+    base, ms = time_cpu_reference(args.criterion, args.num_prev, args.cpu_sample_images, args.steps, args.warmup)
     line = {'metric': METRIC, 'value': base['value'], 'unit': UNIT, 'impl': 'reference', 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
@@ -272,14 +298,237 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
+class StepBench:
+    """One configuration of the distillation step on this rank: synthetic inputs, the two registry modules and the
+    step closure (BCDD on a high-priority side stream behind the HBM-bound DSG-FD kernel, joined before the sum)."""
+
+    def __init__(self, dev, rank, world, dist, images, num_prev, criterion, levels=None, num_query=300, plain_graph=False):
+        import dskd_b200
+        from dskd_b200 import synth
+        self.dev, self.rank, self.world, self.dist = dev, rank, world, dist
+        self.N, self.criterion, self.plain_graph = images, criterion, plain_graph
+        kw = {} if levels is None else dict(levels=levels)
+        self.inputs = synth.make_distill_inputs(num_images=images, num_prev=num_prev, seed=1234 + rank, device=dev,
+                                                num_query=num_query, **kw)
+        self.tokens = sum(h * w for h, w in self.inputs.levels)
+        self.channels = self.inputs.hs_student.shape[-1]
+        self.dsg = dskd_b200.build_loss(dict(type='DSGFeatureDistillLoss', criterion=criterion, reduction='sum',
+                                             loss_weight=1.0, T=2.0, mask_mode='decode_v1', feature_source='neck'))
+        self.bcdd = dskd_b200.build_loss(dict(type='BetweenClassDistanceLoss', reduction='mean', loss_weight=1.0,
+                                              sync_prototypes=world > 1))
+        self.s_feats = [f.requires_grad_(True) for f in self.inputs.student_feats]
+        self.hs_s = self.inputs.hs_student.requires_grad_(True)
+        # high priority: the latency-bound BCDD chain (and its NCCL all-reduce) must not queue behind the thousands of
+        # CTAs of the HBM-bound DSG-FD kernel -- its few CTAs take the first SM slots that free up
+        self.bcdd_stream = torch.cuda.Stream(priority=-1)
+
+    def step(self, feats, t_feats, hs, hs_t):
+        for f in feats:
+            f.grad = None
+        hs.grad = None
+        cur = torch.cuda.current_stream()
+        self.bcdd_stream.wait_stream(cur)
+        with torch.cuda.stream(self.bcdd_stream):
+            loss_corr = self.bcdd(None, None, (hs, hs_t), self.inputs.assignments)
+        loss_fg = self.dsg(feats, t_feats, (hs, hs_t), self.inputs.assignments)
+        cur.wait_stream(self.bcdd_stream)
+        loss = loss_fg + loss_corr
+        loss.backward()
+        return loss
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, *vals):
+        t = torch.tensor(list(vals), dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(x) for x in t.tolist()]
+
+    def run_eager(self, steps, warmup):
+        """(total ms, per-step streaming-kernel ms list, launches, loss): kernels issued one by one from Python."""
+        from dskd_b200 import _lib, profiling
+        lib = _lib.load()
+        inp = self.inputs
+        for _ in range(max(warmup, 3)):
+            self.step(self.s_feats, inp.teacher_feats, self.hs_s, inp.hs_teacher)
+        self.barrier()
+        launches0 = lib.dskd_launch_count()
+        profiling.start()       # C side records an event pair around the streaming kernel of every step
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        e0.record()
+        for _ in range(steps):
+            loss = self.step(self.s_feats, inp.teacher_feats, self.hs_s, inp.hs_teacher)
+        e1.record()
+        self.barrier()
+        kernel_times = profiling.stop()
+        return e0.elapsed_time(e1), kernel_times, lib.dskd_launch_count() - launches0, float(loss.detach())
+
+    def capture(self):
+        """The same step captured once in a CUDA graph: identical kernels, identical inputs, no per-launch host cost."""
+        inp = self.inputs
+        # fresh leaves: their AccumulateGrad nodes are first used on the capture stream
+        g_feats = [f.detach().clone().requires_grad_(True) for f in self.s_feats]
+        g_hs = self.hs_s.detach().clone().requires_grad_(True)
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                self.step(g_feats, inp.teacher_feats, g_hs, inp.hs_teacher)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        for f in g_feats:
+            f.grad = None
+        g_hs.grad = None
+        # keep_graph: the library instantiates the captured cudaGraph_t itself, with per-node priorities (small
+        # kernels -- mask build, BCDD, the NCCL all-reduce -- ahead of the streaming kernel's CTAs)
+        graph = torch.cuda.CUDAGraph(keep_graph=not self.plain_graph)
+        with torch.cuda.graph(graph, stream=side):
+            graph_loss = self.step(g_feats, inp.teacher_feats, g_hs, inp.hs_teacher)
+        policy = 'torch replay (stream order)'
+        runner = graph
+        if not self.plain_graph:
+            try:
+                from dskd_b200.graphs import PrioritizedGraph
+                runner = PrioritizedGraph(graph)
+                policy = f'node priorities: {runner.num_small} small kernels first, {runner.num_big} streaming'
+            except Exception as exc:            # noqa: BLE001 -- fall back to PyTorch's own instantiation, say so
+                graph.instantiate()
+                policy = f'torch replay (stream order); prioritized instantiation failed: {exc}'
+        self._keep = (g_feats, g_hs, graph)
+        return runner, graph_loss, policy
+
+    def run_graph(self, steps, warmup, flush=None):
+        """(ms per step, loss, policy).  flush: a buffer larger than L2 rewritten between replays (configurations whose
+        inputs fit the 126 MB L2); each replay is then timed on its own and the median taken."""
+        runner, graph_loss, policy = self.capture()
+        for _ in range(max(warmup, 3)):
+            runner.replay()
+        self.barrier()
+        if flush is None:
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            for _ in range(steps):
+                runner.replay()
+            g1.record()
+            self.barrier()
+            ms = g0.elapsed_time(g1) / steps
+        else:
+            ts = []
+            for _ in range(steps):
+                flush.zero_()
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                g0.record()
+                runner.replay()
+                g1.record()
+                torch.cuda.synchronize()
+                ts.append(g0.elapsed_time(g1))
+            self.barrier()
+            ms = statistics.median(ts)
+        loss = float(graph_loss.detach())
+        del runner
+        self._keep = None
+        return ms, loss, policy
+
+    def kernel_roofline(self, kernel_ms, ms_per_step):
+        peak, _, peak_src = peaks()
+        alg = algorithmic_bytes(self.criterion, self.tokens, self.channels, self.N)
+        achieved = alg / (kernel_ms * 1e-3) / 1e9
+        rec = recorded_traffic(STREAM_KERNEL[self.criterion], self.N) if self.tokens == COCO_TOKENS else None
+        return {'bound': 'hbm', 'kernel': STREAM_KERNEL[self.criterion], 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                'frac': achieved / peak, 'frac_of_nominal_8000': achieved / 8000.0, 'peak_source': peak_src,
+                'algorithmic_bytes_per_launch': alg, 'kernel_ms': kernel_ms,
+                'kernel_share_of_step': kernel_ms / ms_per_step if ms_per_step else None,
+                'traffic': (rec or {}).get('dram_bytes_per_launch'), 'traffic_source': (rec or {}).get('source')}
+
+
+def measure_config(dev, rank, world, dist, images, num_prev, criterion, steps, warmup, levels=None, num_query=300,
+                   flush=None, plain_graph=False):
+    """Short measurement of one extra configuration: eager pass (kernel events) + graph replay; max over ranks."""
+    sb = StepBench(dev, rank, world, dist, images, num_prev, criterion, levels, num_query, plain_graph)
+    eager_ms, kernel_times, _, loss = sb.run_eager(max(3, steps // 2), warmup)
+    kernel_ms = statistics.mean(kernel_times) if kernel_times else float('nan')
+    try:
+        ms, g_loss, _ = sb.run_graph(steps, warmup, flush)
+        launch = 'cuda_graph_replay'
+        if abs(g_loss - loss) > 1e-3 * abs(loss):
+            raise RuntimeError(f'graph replay loss {g_loss} != eager loss {loss}')
+    except Exception as exc:                        # noqa: BLE001 -- report, do not hide
+        ms, launch = eager_ms / max(3, steps // 2), f'eager ({type(exc).__name__}: {exc})'
+    ms, kernel_ms = sb.max_over_ranks(ms, kernel_ms)
+    roof = sb.kernel_roofline(kernel_ms, ms)
+    out = {'images_per_gpu': images, 'num_prev': num_prev, 'criterion': criterion, 'tokens': sb.tokens, 'queries': num_query,
+           'value': world * images / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms, 'launch': launch,
+           'kernel_ms': kernel_ms, 'achieved_gbs': roof['achieved'], 'frac': roof['frac'], 'loss': loss,
+           'l2': 'flushed between replays' if flush is not None else 'inputs larger than L2'}
+    del sb
+    gc.collect()
+    torch.cuda.empty_cache()
+    return out
+
+
+def multi_rank_parity(sb, dist):
+    """the W-rank result must equal the single-process evaluation of the concatenated batch.  Every rank
+    evaluates BCDD with the prototype all-reduce; rank 0 gathers all ranks' embeddings / labels / keep-ids, evaluates
+    BetweenClassDistanceLoss(sync_prototypes=False) on the concatenation and compares the loss (rtol 1e-4) and, for every
+    rank, grad_hs / world against the matching slice (rtol 1e-3, atol 1e-6 * max)."""
+    import dskd_b200
+    inp, world, rank, dev = sb.inputs, sb.world, sb.rank, sb.dev
+    a = inp.assignments
+    hs = inp.hs_student.detach().clone().requires_grad_(True)
+    loss = sb.bcdd(None, None, (hs, inp.hs_teacher), a)
+    loss.backward()
+    N, Q, C = hs.shape
+    payload = dict(hs_s=hs.detach().cpu(), hs_t=inp.hs_teacher.cpu(), labels=a['student_labels'].cpu(),
+                   keepid=a['teacher_keepid'].cpu(), tlabels=a['teacher_labels'].cpu(), grad=hs.grad.cpu(),
+                   loss=float(loss.detach()))
+    gathered = [None] * world
+    dist.all_gather_object(gathered, payload)
+    if rank != 0:
+        return None
+    cat = lambda k: torch.cat([g[k] for g in gathered]).to(dev)
+    keep = torch.cat([g['keepid'] + r * N * Q for r, g in enumerate(gathered)]).to(dev)
+    big = dict(student_labels=cat('labels'), teacher_keepid=keep, teacher_labels=cat('tlabels'),
+               prev_labels=a['prev_labels'], num_classes=a.get('num_classes', 80))
+    hs_all = cat('hs_s').requires_grad_(True)
+    single = dskd_b200.build_loss(dict(type='BetweenClassDistanceLoss', reduction='mean', loss_weight=1.0, sync_prototypes=False))
+    ref = single(None, None, (hs_all, cat('hs_t')), big)
+    ref.backward()
+    ref_loss = float(ref.detach())
+    loss_err = max(abs(g['loss'] - ref_loss) / max(abs(ref_loss), 1e-30) for g in gathered)
+    ref_grad = hs_all.grad.cpu()
+    scale = float(ref_grad.abs().max())
+    worst = 0.0
+    for r, g in enumerate(gathered):
+        got = g['grad'] / world                         # DDP's gradient mean
+        want = ref_grad[r * N:(r + 1) * N]
+        viol = ((got - want).abs() - (1e-3 * want.abs() + 1e-6 * scale)).max()
+        worst = max(worst, float((got - want).abs().max()) / max(scale, 1e-30))
+        if float(viol) > 0:
+            return {'ok': False, 'loss_rel_err': loss_err, 'grad_max_err_over_max': worst, 'failed_rank': r}
+    return {'ok': bool(loss_err <= 1e-4), 'loss_rel_err': loss_err, 'grad_max_err_over_max': worst, 'ranks': world,
+            'what': 'synced BCDD (NCCL prototype all-reduce, grad_scale = world) vs BetweenClassDistanceLoss on the '
+                    'concatenated batch; loss rtol 1e-4, grad / world rtol 1e-3'}
+
+
+def time_train_step(dev, rank, world, dist, images=4, criterion='kl', steps=3, warmup=2):
+    """The 40+40 incremental training step (chaosuan_..._40_...py:24-152,214-238) with the shipped
+    KL criterion: random-init GFL-Deformable-DETR R-50 student + frozen teacher, AdamW, the CUDA distillation path inside."""
+    from dskd_b200.harness import bench_train_step
+    return bench_train_step(dev, rank, world, dist, images_per_gpu=images, criterion=criterion, steps=steps, warmup=warmup)
+
+
 def main():
     args = parse_args()
     if args.impl == 'reference':
         run_reference_arm(args)
         return
     import torch.distributed as dist
-    import dskd_b200
-    from dskd_b200 import _lib, synth
+    from dskd_b200 import synth
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -291,122 +540,36 @@ def main():
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=dev)
-    lib = _lib.load()
 
+    # the BCDD side stream (StepBench.step) is deliberate: autograd then sees the embeddings' AccumulateGrad node and the
+    # BCDD backward on different streams and would warn about it on every step
+    torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
     N = args.images_per_gpu
-    inputs = synth.make_distill_inputs(num_images=N, num_prev=args.num_prev, seed=1234 + rank, device=dev)
-    dsg = dskd_b200.build_loss(dict(type='DSGFeatureDistillLoss', criterion=args.criterion, reduction='sum',
-                                    loss_weight=1.0, T=2.0, mask_mode='decode_v1', feature_source='neck'))
-    bcdd = dskd_b200.build_loss(dict(type='BetweenClassDistanceLoss', reduction='mean', loss_weight=1.0,
-                                     sync_prototypes=world > 1))
-    s_feats = [f.requires_grad_(True) for f in inputs.student_feats]
-    hs_s = inputs.hs_student.requires_grad_(True)
-
-    from dskd_b200 import profiling
-
-    # high priority: the latency-bound BCDD chain (and its NCCL all-reduce) must not queue behind the 3 712 CTAs of the
-    # HBM-bound DSG-FD kernel -- its few CTAs take the first SM slots that free up
-    bcdd_stream = torch.cuda.Stream(priority=-1)
-
-    def step(feats, t_feats, hs, hs_t):
-        for f in feats:
-            f.grad = None
-        hs.grad = None
-        # BCDD (latency-bound, and the only collective) runs on a side stream behind the HBM-bound DSG-FD kernel
-        cur = torch.cuda.current_stream()
-        bcdd_stream.wait_stream(cur)
-        with torch.cuda.stream(bcdd_stream):
-            loss_corr = bcdd(None, None, (hs, hs_t), inputs.assignments)
-        loss_fg = dsg(feats, t_feats, (hs, hs_t), inputs.assignments)
-        cur.wait_stream(bcdd_stream)
-        loss = loss_fg + loss_corr
-        loss.backward()
-        return loss
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    sb = StepBench(dev, rank, world, dist, N, args.num_prev, args.criterion, plain_graph=args.plain_graph)
+    inputs, s_feats, hs_s, step = sb.inputs, sb.s_feats, sb.hs_s, sb.step
 
     # ---------------- device-resident throughput, eager launches (host-issue bound for this small step)
-    for _ in range(max(args.warmup, 3)):
-        step(s_feats, inputs.teacher_feats, hs_s, inputs.hs_teacher)
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    launches0 = lib.dskd_launch_count()
-    profiling.start()       # C side records an event pair around the streaming kernel of every step
-    e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e_start.record()
-    for _ in range(args.steps):
-        loss = step(s_feats, inputs.teacher_feats, hs_s, inputs.hs_teacher)
-    e_stop.record()
-    barrier()
-    kernel_times = profiling.stop()
-    launches = lib.dskd_launch_count() - launches0
-    eager_ms = e_start.elapsed_time(e_stop)
-    loss_value = float(loss.detach())
+    eager_ms, kernel_times, launches, loss_value = sb.run_eager(args.steps, args.warmup)
 
-    # ---------------- the same step captured once in a CUDA graph and replayed (`value`): identical kernels,
-    # identical inputs, no per-launch host cost.  Falls back to the eager number if capture is not possible.
+    # ---------------- the same step captured once in a CUDA graph and replayed (`value`)
     graph_ms = None
     graph_err = None
-    graph_policy = 'torch replay (stream order)'
+    graph_policy = None
     if not args.no_graph:
         try:
-            # fresh leaves: their AccumulateGrad nodes must first be used on the capture (side) stream
-            g_feats = [f.detach().clone().requires_grad_(True) for f in s_feats]
-            g_hs = hs_s.detach().clone().requires_grad_(True)
-            torch.cuda.synchronize()
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                for _ in range(3):
-                    step(g_feats, inputs.teacher_feats, g_hs, inputs.hs_teacher)
-            torch.cuda.current_stream().wait_stream(side)
-            torch.cuda.synchronize()
-            for f in g_feats:
-                f.grad = None
-            g_hs.grad = None
-            # keep_graph: the library instantiates the captured cudaGraph_t itself, with per-node priorities (small
-            # kernels -- mask build, BCDD, the NCCL all-reduce -- ahead of the streaming kernel's 3 712 CTAs)
-            graph = torch.cuda.CUDAGraph(keep_graph=not args.plain_graph)
-            with torch.cuda.graph(graph):
-                graph_loss = step(g_feats, inputs.teacher_feats, g_hs, inputs.hs_teacher)
-            if args.plain_graph:
-                runner = graph
-            else:
-                try:
-                    from dskd_b200.graphs import PrioritizedGraph
-                    runner = PrioritizedGraph(graph)
-                    graph_policy = f'node priorities: {runner.num_small} small kernels first, {runner.num_big} streaming'
-                except Exception as exc:            # noqa: BLE001 -- fall back to PyTorch's own instantiation, say so
-                    graph.instantiate()
-                    runner = graph
-                    graph_policy = f'torch replay (stream order); prioritized instantiation failed: {exc}'
-            for _ in range(max(args.warmup, 3)):
-                runner.replay()
-            barrier()
-            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            g0.record()
-            for _ in range(args.steps):
-                runner.replay()
-            g1.record()
-            barrier()
-            graph_ms = g0.elapsed_time(g1)
-            if abs(float(graph_loss.detach()) - loss_value) > 1e-3 * abs(loss_value):
-                raise RuntimeError(f'graph replay loss {float(graph_loss.detach())} != eager loss {loss_value}')
+            ms, g_loss, graph_policy = sb.run_graph(args.steps, args.warmup)
+            graph_ms = ms * args.steps
+            if abs(g_loss - loss_value) > 1e-3 * abs(loss_value):
+                raise RuntimeError(f'graph replay loss {g_loss} != eager loss {loss_value}')
         except Exception as exc:                    # noqa: BLE001 -- report, do not hide
             graph_err = f'{type(exc).__name__}: {exc}'
             graph_ms = None
     clocks = sampler.stop() if rank == 0 else None
     elapsed_ms = graph_ms if graph_ms is not None else eager_ms
-    t = torch.tensor([elapsed_ms, eager_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms, eager_ms = float(t[0].item()), float(t[1].item())
+    elapsed_ms, eager_ms = sb.max_over_ranks(elapsed_ms, eager_ms)
     kernel_ms = statistics.mean(kernel_times) if kernel_times else float('nan')
 
     # ---------------- end-to-end through the module call with HOST buffers (`e2e`)
@@ -419,64 +582,120 @@ def main():
         host_loss = torch.empty((), pin_memory=True)
         h2d = sum(t_.numel() * 4 for t_ in host_s + host_t + [host_hs, host_ht])
 
-        def e2e_step():
-            fs = [h.to(dev, non_blocking=True).requires_grad_(True) for h in host_s]
+        def upload():
+            fs = [h.to(dev, non_blocking=True) for h in host_s]
             ft = [h.to(dev, non_blocking=True) for h in host_t]
-            hs = host_hs.to(dev, non_blocking=True).requires_grad_(True)
-            ht = host_ht.to(dev, non_blocking=True)
-            l = step(fs, ft, hs, ht)
+            return fs, ft, host_hs.to(dev, non_blocking=True), host_ht.to(dev, non_blocking=True)
+
+        def e2e_step():
+            fs, ft, hs, ht = upload()
+            l = step([f.requires_grad_(True) for f in fs], ft, hs.requires_grad_(True), ht)
             host_loss.copy_(l.detach(), non_blocking=True)
             torch.cuda.current_stream().synchronize()
             return float(host_loss)
+
+        def h2d_only():
+            upload()
+            torch.cuda.current_stream().synchronize()
+
+        def wall(fn, reps):
+            for _ in range(2):
+                fn()
+            sb.barrier()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                fn()
+            sb.barrier()
+            return sb.max_over_ranks(time.perf_counter() - t0)[0] / reps * 1e3
         e2e_steps = max(3, min(args.steps, 10))
-        for _ in range(2):
-            e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            e2e_step()
-        barrier()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {'value': world * N * e2e_steps / float(tt.item()), 'unit': UNIT, 'h2d_bytes_per_step': h2d,
-               'd2h_bytes_per_step': 4, 'steps': e2e_steps, 'ms_per_step': float(tt.item()) / e2e_steps * 1e3}
+        e2e_ms = wall(e2e_step, e2e_steps)
+        # the same host->device copies with nothing else: the PCIe / host-memory roof of this rank count
+        h2d_ms = wall(h2d_only, e2e_steps)
+        e2e = {'value': world * N / (e2e_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d,
+               'd2h_bytes_per_step': 4, 'steps': e2e_steps, 'ms_per_step': e2e_ms, 'h2d_only_ms': h2d_ms,
+               'h2d_gbs_per_rank': h2d / (h2d_ms * 1e-3) / 1e9, 'roof_frac': h2d_ms / e2e_ms,
+               'roof_note': 'roof = the same pinned-host copies with no kernel behind them, all ranks at once; e2e / roof '
+                            'shows what the step adds to the transfer'}
+        del host_s, host_t, host_hs, host_ht
 
     contraction = None
     if not args.no_contraction:
         contraction = time_contraction(args, dev, N, world, dist)
 
+    # ---------------- multi-rank parity of the only collective (outside every timed region)
+    parity = multi_rank_parity(sb, dist) if world > 1 else None
+
+    # ---------------- the shipped criterion: KL over H
+    ms_per_step = elapsed_ms / args.steps
+    extras = {}
+    kernel_ms, = sb.max_over_ranks(kernel_ms)
+    roofline = sb.kernel_roofline(kernel_ms, ms_per_step)
+    del sb, s_feats, hs_s, inputs, step
+    gc.collect()
+    torch.cuda.empty_cache()
+    if not args.no_kl and args.criterion != 'kl':
+        kl = measure_config(dev, rank, world, dist, N, args.num_prev, 'kl', args.steps, args.warmup, plain_graph=args.plain_graph)
+        peak, _, src = peaks()
+        rec = recorded_traffic(STREAM_KERNEL['kl'], N)
+        kl.update({'kernel': STREAM_KERNEL['kl'], 'peak': peak, 'peak_source': src,
+                   'algorithmic_bytes_per_launch': algorithmic_bytes('kl', COCO_TOKENS, 256, N),
+                   'traffic': (rec or {}).get('dram_bytes_per_launch'), 'traffic_source': (rec or {}).get('source'),
+                   'note': 'KnowledgeDistillationKLDivLoss(T=2, sum) over H: the criterion of all four chaosuan_* configs '
+                           '(:127); same step otherwise (decode_v1 + BCDD)'})
+        extras['kl'] = kl
+
+    # ---------------- BASELINE.json configs 3-5
+    if not args.no_configs:
+        cfg_steps = max(5, min(args.steps, 10))
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        configs = {}
+        configs['coco_70+10_8img'] = measure_config(dev, rank, world, dist, 8, 70, 'kl', cfg_steps, 3)
+        configs['coco_50+30_4img'] = measure_config(dev, rank, world, dist, 4, 50, 'kl', cfg_steps, 3)
+        configs['coco_60+20_4img'] = measure_config(dev, rank, world, dist, 4, 60, 'kl', cfg_steps, 3)
+        sweep = []
+        for tokens in (5000, COCO_TOKENS, 40000):
+            levels = synth.COCO_LEVELS if tokens == COCO_TOKENS else synth.scaled_levels(tokens)
+            for q in (100, 300, 900):
+                for n in (1, 16):
+                    fl = flush if 2 * n * tokens * 256 * 4 < (160 << 20) else None
+                    sweep.append(measure_config(dev, rank, world, dist, n, 40, 'mse', 5, 3, levels, q, fl))
+        configs['sweep_mse'] = sweep
+        if world == 1 and not args.no_cpu_baseline:
+            lv = synth.scaled_levels(5000)
+            base, _ = time_cpu_reference('mse', 40, 1, steps=3, warmup=1, levels=lv, num_query=100)
+            configs['sweep_cpu_port_smallest'] = dict(base, tokens=sum(h * w for h, w in lv), queries=100, images=1)
+        configs['note'] = ('configs 3-5 of BASELINE.json: L = 70 at samples_per_gpu = 8 (chaosuan_..._70_...py:202), L = 50 / 60 '
+                           'at 4 images per GPU, KL criterion (shipped), prototype all-reduce on at n_gpus > 1; sweep: tokens x '
+                           'queries x images per GPU, masked MSE + BCDD, graph replay (L2 flushed where the inputs fit it)')
+        extras['configs'] = configs
+        del flush
+
+    if parity is not None:
+        extras['multi_rank_parity'] = parity
+
+    # ---------------- the 40+40 training step hosting the losses
+    if not args.no_train_step:
+        try:
+            extras['train_step'] = time_train_step(dev, rank, world, dist)
+        except Exception as exc:                    # noqa: BLE001 -- report, do not hide
+            extras['train_step'] = {'error': f'{type(exc).__name__}: {exc}'}
+
     if rank != 0:
         leave(world, dist)
         return
 
-    peak, _, peak_src = peaks()
-    if args.criterion == 'mse':
-        alg_bytes = BYTES_PER_IMAGE_MSE * N
-    else:
-        alg_bytes = 2 * 22223 * 256 * 4 * N
-    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
-    kernel_name = 'dsgfd_mse_nchw_kernel' if args.criterion == 'mse' else 'dsgfd_kl_col_kernel'
-    traffic_rec = recorded_traffic(kernel_name, N)
-    ms_per_step = elapsed_ms / args.steps
     line = {
         'metric': METRIC, 'value': world * N * args.steps / (elapsed_ms * 1e-3), 'unit': UNIT, 'n_gpus': world,
         'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'images_per_gpu': N, 'global_batch': world * N, 'num_prev': args.num_prev,
+        'config': {'workload': WORKLOAD if args.criterion == 'mse' else WORKLOAD.replace('mse', 'kl'), 'images_per_gpu': N,
+                   'global_batch': world * N, 'num_prev': args.num_prev,
                    'criterion': args.criterion, 'levels': [[100, 167], [50, 84], [25, 42], [13, 21]], 'channels': 256,
                    'queries': 300, 'parallelism': f'dp{world}', 'prototype_allreduce': world > 1,
                    'launch': 'cuda_graph_replay' if graph_ms is not None else 'eager',
                    'graph_policy': graph_policy if graph_ms is not None else None,
                    'cache': f'inputs larger than L2: {2 * N * 22.76:.0f} MB of features read per step vs 126 MB L2'},
-        'roofline': {'bound': 'hbm', 'kernel': 'dsgfd_mse_nchw_kernel' if args.criterion == 'mse' else 'dsgfd_kl_col_kernel',
-                     'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                     'frac_of_nominal_8000': achieved / 8000.0, 'peak_source': peak_src,
-                     'algorithmic_bytes_per_launch': alg_bytes, 'kernel_ms': kernel_ms,
-                     'kernel_share_of_step': kernel_ms / ms_per_step,
-                     'traffic': (traffic_rec or {}).get('dram_bytes_per_launch'),
-                     'traffic_source': (traffic_rec or {}).get('source')},
+        'roofline': roofline,
         'contraction': contraction,
         'e2e': e2e,
         'gpu_launches': int(launches),
@@ -484,28 +703,38 @@ def main():
                   'note': 'same step issued kernel by kernel from Python; host-issue bound', 'graph_error': graph_err},
         'clocks': clocks,
         'loss': loss_value,
+        'parity_note': PARITY_NOTE,
     }
+    line.update(extras)
     if world == 1 and not args.no_feeders:
         line['feeders'] = time_path_feeders(args, dev, N)
     if world == 1 and not args.no_cpu_baseline:
-        base, _ = time_cpu_reference(args, steps=3, warmup=1)
+        base, _ = time_cpu_reference(args.criterion, args.num_prev, args.cpu_sample_images, steps=3, warmup=1)
         line['cpu_baseline'] = base
     print(json.dumps(line), flush=True)
     leave(world, dist)
 
 
 def leave(world, dist):
-    """End of a multi-rank run.  `destroy_process_group()` blocked for minutes on the B200 box once the step (with its
-    NCCL all-reduce) had been captured in a CUDA graph, so after a last barrier every rank flushes and exits directly;
-    torchrun sees exit code 0."""
+    """End of a multi-rank run: every CUDA graph that captured the NCCL all-reduce has been dropped by now (StepBench.
+    run_graph deletes its exec and torch graph), so the process group can be destroyed normally.  A watchdog still ends the
+    process if the teardown should block (seen in round 1 while graph execs holding NCCL kernels were alive)."""
     if world <= 1:
         return
+    gc.collect()
     torch.cuda.synchronize()
     dist.barrier()
     torch.cuda.synchronize()
     sys.stdout.flush()
     sys.stderr.flush()
-    os._exit(0)
+
+    def watchdog():
+        time.sleep(30)
+        sys.stderr.write('bench.py: destroy_process_group() did not return within 30 s; exiting\n')
+        sys.stderr.flush()
+        os._exit(0)
+    threading.Thread(target=watchdog, daemon=True).start()
+    dist.destroy_process_group()
 
 
 if __name__ == '__main__':

@@ -28,7 +28,7 @@ constexpr int kKlWarps = 8;       // warps per CTA (one channel at a time each)
 constexpr int kKlBlk = 5;         // rows per block: the unit of loading ahead and of skipping rows without boxes
 constexpr int kKlStages = 2;      // row blocks in the register ring: the loads of kKlStages - 1 blocks are in flight
 constexpr int kKlMinCtas = 4;     // CTAs per SM the register budget is cut for
-constexpr int kKlChunk = 16;      // channels per CTA
+constexpr int kKlChunk = 16;      // channels per CTA (8 for small batches: twice the CTAs to fill 148 SMs x 4)
 constexpr int kKlPool = 256;      // (owner, lane, A, B) records a warp can park per channel before the normalisers are known
 constexpr int kKlMaxH = 1600;     // rows per level (shared-memory tables: 136 B per row)
 constexpr int kKlRedoCtas = 148;  // grid of the redo launch
@@ -64,6 +64,18 @@ __device__ __forceinline__ float fast_ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// KL of one column from its three sums (units of log 2 for ws): ln2 * ws / ss - ln(ss / st).  Both terms are first
+// order, their difference second order: near ss == st the logarithm is taken as log1p of the relative difference.
+__device__ __forceinline__ float kl_col(float ss, float st, float ws) {
+  const float rs = __fdividef(1.f, ss), rt = __fdividef(1.f, st);
+  const float d = (ss - st) * rt;  // (overflows for sums that are 2^128 apart: the plain logarithms then)
+  const float lg = fabsf(d) < 0.5f ? log1pf(d) : logf(ss) - logf(st);
+  return kLn2 * ws * rs - lg;
+}
+__device__ __forceinline__ bool kl_in_range(float ss, float st, float ws) {
+  return ss > 0x1p-90f && ss < 0x1p100f && st > 0x1p-90f && st < 0x1p100f && fabsf(ws) < INFINITY;
+}
+
 // loads under a predicate (0 when off): cells outside boxes are never fetched
 __device__ __forceinline__ float ld_stream_f1_ge0(const float* p, int key) {
   float v;
@@ -367,11 +379,9 @@ __global__ void __launch_bounds__(32 * kKlWarps, MINB) dsgfd_kl_stream_kernel(co
       const float nadd = (float)nadd_s;
       const float ss = ch.ss + nadd, st = ch.st + nadd;
       const bool col_ok = lane < tl.wn;
-      const bool in_range = ss > 0x1p-90f && ss < 0x1p100f && st > 0x1p-90f && st < 0x1p100f && fabsf(ch.ws) < INFINITY;
-      if (__all_sync(kFull, !col_ok || in_range)) {
+      if (__all_sync(kFull, !col_ok || kl_in_range(ss, st, ch.ws))) {
         const float rs = __fdividef(1.f, ss), rt = __fdividef(1.f, st);
-        // KL = ln2 * ws / ss - ln(ss / st): both terms are first order, their difference second order
-        if (col_ok) kl_total += (double)(kLn2 * ch.ws * rs - log1pf((ss - st) * rt));
+        if (col_ok) kl_total += (double)kl_col(ss, st, ch.ws);
         if (GRAD) {
           const float gcoef = prm.scale[lvl] * prm.temperature / (float)H;  // d loss / d pred = scale * (T/H) * (p - q)
           float* __restrict__ growc = prm.grad_rows + c;
@@ -538,14 +548,6 @@ struct KlSncParams {
   double* loss;
   unsigned* redo_mask;                  // [tasks / groups] bit g: group g of the column is left to the redo launch
 };
-
-__device__ __forceinline__ float kl_col(float ss, float st, float ws) {
-  // KL = ln2 * ws / ss - ln(ss / st): both terms are first order, their difference second order
-  return kLn2 * ws * __fdividef(1.f, ss) - log1pf((ss - st) * __fdividef(1.f, st));
-}
-__device__ __forceinline__ bool kl_in_range(float ss, float st, float ws) {
-  return ss > 0x1p-90f && ss < 0x1p100f && st > 0x1p-90f && st < 0x1p100f && fabsf(ws) < INFINITY;
-}
 
 struct KlSncTask {
   int lvl, img, w, group;
@@ -799,7 +801,7 @@ extern "C" int dskd_dsgfd_kl_fwd_bwd(const DskdDsgfdKlArgs* a, void* stream) {
   if (a->layout == DSKD_LAYOUT_SNC) return launch_kl_snc(a, st);
   DSKD_REQUIRE(max_h <= kKlMaxH, "dsgfd_kl: H (%d) above the supported %d", max_h, kKlMaxH);
   // tuning hook (tools/kl_perf.py): DSKD_KL_TUNE="rows_per_block,stages,ctas_per_sm,channels_per_cta,pool_records,dbg"
-  int blk = kKlBlk, stages = kKlStages, minb = kKlMinCtas, chunk = kKlChunk, cap = kKlPool, dbg = 0;
+  int blk = kKlBlk, stages = kKlStages, minb = kKlMinCtas, chunk = a->N <= 4 ? kKlChunk / 2 : kKlChunk, cap = kKlPool, dbg = 0;
   if (const char* tune = getenv("DSKD_KL_TUNE")) sscanf(tune, "%d,%d,%d,%d,%d,%d", &blk, &stages, &minb, &chunk, &cap, &dbg);
   DSKD_REQUIRE(chunk >= 1 && chunk <= 32 && cap >= 1, "dsgfd_kl: bad DSKD_KL_TUNE");
   prm.max_blocks = (max_h + blk - 1) / blk;

@@ -154,3 +154,63 @@ class IncrementalTrainStep:
         self.opt.step()
         return dict(loss=total.detach(), loss_det=loss.detach(), loss_corr=loss_corr.detach(), loss_fg_feature=loss_fg.detach(),
                     num_teacher=int(tinfo['pred_keepid'].numel()))
+
+
+def synthetic_batch(device, images, height=800, width=1333, seed=1234):
+    """Synthetic 800x1333 images with 1-10 ground-truth boxes of the NEW classes (40..79) each."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    img = torch.randn(images, 3, height, width, device=device, generator=g)
+    gt_b, gt_l = [], []
+    for _ in range(images):
+        k = int(torch.randint(1, 11, (1,), device=device, generator=g))
+        x1 = torch.rand(k, device=device, generator=g) * 0.7 * width
+        y1 = torch.rand(k, device=device, generator=g) * 0.7 * height
+        bw = 8 + torch.rand(k, device=device, generator=g) * (0.3 * width - 8)
+        bh = 8 + torch.rand(k, device=device, generator=g) * (0.3 * height - 8)
+        gt_b.append(torch.stack([x1, y1, (x1 + bw).clamp(max=width), (y1 + bh).clamp(max=height)], 1))
+        gt_l.append(torch.randint(40, 80, (k,), device=device, generator=g))
+    return img, gt_b, gt_l
+
+
+def bench_train_step(device, rank, world, dist, images_per_gpu=4, criterion='kl', steps=3, warmup=2, height=800, width=1333,
+                     backbone='resnet50'):
+    """Time the 40+40 incremental training step on synthetic data (bench.py's `train_step` key, tools/train_step_bench.py):
+    CUDA events around `steps` iterations after `warmup`, max over ranks; DDP (gradient mean) + prototype all-reduce when
+    world > 1, like tools/train_increment.py:299-304."""
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    try:
+        student, teacher = make_student_teacher(device, backbone=backbone)
+        student.train()
+        if world > 1:
+            student = torch.nn.parallel.DistributedDataParallel(student, device_ids=[device.index], broadcast_buffers=False,
+                                                                find_unused_parameters=True)
+        trainer = IncrementalTrainStep(student, teacher, num_prev=40, criterion=criterion, sync_prototypes=world > 1)
+        img, gt_b, gt_l = synthetic_batch(device, images_per_gpu, height, width, seed=1234 + rank)
+        out = None
+        for _ in range(max(warmup, 1)):
+            out = trainer.step(img, gt_b, gt_l)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = trainer.step(img, gt_b, gt_l)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        return {'metric': 'incremental_train_step_images_per_s', 'value': world * images_per_gpu * steps / (ms * 1e-3),
+                'unit': 'images/s', 'n_gpus': world, 'steps': steps, 'warmup': max(warmup, 1), 'ms_per_step': ms / steps,
+                'dtype': 'f32 (tf32 matmul/conv)', 'data': 'synthetic',
+                'config': {'workload': 'coco_40+40_incremental_train_step', 'images_per_gpu': images_per_gpu,
+                           'image': [height, width], 'backbone': backbone, 'criterion': criterion, 'queries': 300,
+                           'decoder_layers': 6, 'parallelism': f'dp{world}'},
+                'losses': {k: float(v) for k, v in out.items()},
+                'peak_mem_gb': torch.cuda.max_memory_allocated(device) / 2 ** 30}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32

@@ -101,11 +101,11 @@ def main():
     has_layout = os.environ.get('DSKD_KL_SNC', '0') == '1'
     cases = [('nchw box+grad', dict()), ('nchw box fwd', dict(grad=False)), ('nchw cell', dict(cell=True))]
     if has_layout:
-        cases += [('snc box+grad', dict(layout=L.LAYOUT_SNC)), ('snc cell', dict(cell=True, layout=L.LAYOUT_SNC))]
+        cases += [('snc cell', dict(cell=True, layout=L.LAYOUT_SNC))]
     if args.one:
         sel = {'box': cases[0], 'cell': cases[2]}
         if has_layout:
-            sel.update({'snc_box': cases[3], 'snc_cell': cases[4]})
+            sel.update({'snc_cell': cases[3]})
         name, kw = sel[args.one]
         a, keep, cov, loss = build_args(inp, inp.assignments['teacher_bboxes'], **kw)
         ms = time_call(lib, a, st, args.iters)

@@ -31,7 +31,7 @@ def main():
     ap.add_argument('--backbone', default='resnet50')
     args = ap.parse_args()
     import torch.distributed as dist
-    from dskd_b200.harness import IncrementalTrainStep, make_student_teacher
+    from dskd_b200.harness import bench_train_step
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -41,61 +41,15 @@ def main():
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=dev)
-    torch.backends.cuda.matmul.allow_tf32 = True
-    torch.backends.cudnn.allow_tf32 = True
-
-    student, teacher = make_student_teacher(dev, backbone=args.backbone)
-    student.train()
-    if world > 1:
-        student = torch.nn.parallel.DistributedDataParallel(student, device_ids=[local_rank], broadcast_buffers=False,
-                                                            find_unused_parameters=True)   # train_increment.py:301-303
-    trainer = IncrementalTrainStep(student, teacher, num_prev=40, criterion=args.criterion, sync_prototypes=world > 1)
-    N, H, W = args.images_per_gpu, args.height, args.width
-    g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    img = torch.randn(N, 3, H, W, device=dev, generator=g)
-    gt_b, gt_l = [], []
-    for _ in range(N):
-        k = int(torch.randint(1, 11, (1,), device=dev, generator=g))
-        x1 = torch.rand(k, device=dev, generator=g) * 0.7 * W
-        y1 = torch.rand(k, device=dev, generator=g) * 0.7 * H
-        bw = 8 + torch.rand(k, device=dev, generator=g) * (0.3 * W - 8)
-        bh = 8 + torch.rand(k, device=dev, generator=g) * (0.3 * H - 8)
-        gt_b.append(torch.stack([x1, y1, (x1 + bw).clamp(max=W), (y1 + bh).clamp(max=H)], 1))
-        gt_l.append(torch.randint(40, 80, (k,), device=dev, generator=g))
-
-    out = None
-    for _ in range(max(args.warmup, 1)):
-        out = trainer.step(img, gt_b, gt_l)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        out = trainer.step(img, gt_b, gt_l)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    line = bench_train_step(dev, rank, world, dist, images_per_gpu=args.images_per_gpu, criterion=args.criterion,
+                            steps=args.steps, warmup=args.warmup, height=args.height, width=args.width, backbone=args.backbone)
     if rank == 0:
-        line = {'metric': 'incremental_train_step_images_per_s', 'value': world * N * args.steps / (ms * 1e-3),
-                'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 1),
-                'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'dtype': 'f32 (tf32 matmul/conv)',
-                'data': 'synthetic', 'vs_baseline': None,
-                'config': {'workload': 'coco_40+40_incremental_train_step', 'images_per_gpu': N, 'image': [H, W],
-                           'backbone': args.backbone, 'criterion': args.criterion, 'queries': 300, 'decoder_layers': 6,
-                           'parallelism': f'dp{world}'},
-                'losses': {k: float(v) for k, v in out.items()},
-                'peak_mem_gb': torch.cuda.max_memory_allocated() / 2 ** 30}
+        line.update({'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None})
         print(json.dumps(line), flush=True)
     if world > 1:
         torch.cuda.synchronize()
         dist.barrier()
-        sys.stdout.flush()
-        os._exit(0)
+        dist.destroy_process_group()
 
 
 if __name__ == '__main__':

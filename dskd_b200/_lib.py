@@ -184,6 +184,42 @@ def ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+def _first_cuda_tensor(obj, depth=0):
+    if isinstance(obj, torch.Tensor):
+        return obj if obj.is_cuda else None
+    if depth < 3 and isinstance(obj, (tuple, list)):
+        for x in obj:
+            t = _first_cuda_tensor(x, depth + 1)
+            if t is not None:
+                return t
+    return None
+
+
+def guarded(fn):
+    """Decorator of the public entry points: the ctypes calls launch on the CUDA device that is CURRENT for the calling
+    thread, so when the tensors live on another device the call runs under `torch.cuda.device(that device)` (what
+    PyTorch's own ops do with their device guard).  Costs one scan of the arguments when no switch is needed."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        t = None
+        for a in args:
+            t = _first_cuda_tensor(a)
+            if t is not None:
+                break
+        if t is None:
+            for a in kwargs.values():
+                t = _first_cuda_tensor(a)
+                if t is not None:
+                    break
+        if t is not None and t.device.index != torch.cuda.current_device():
+            with torch.cuda.device(t.device):
+                return fn(*args, **kwargs)
+        return fn(*args, **kwargs)
+    return wrapper
+
+
 def stream_of(t: torch.Tensor):
     return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
 

@@ -74,6 +74,7 @@ class GFLHungarianAssigner:
         self.solver = solver          # `assign_batch` only; the per-image `assign` always returns host-checked results
 
     # ------------------------------------------------------------------ batched path
+    @L.guarded
     def cost_matrices(self, cls_scores, bbox_preds, gt_bboxes_list, gt_labels_list, img_shapes, decoded=False):
         """cls_scores [P,Q,classes] (or [layers,N,Q,classes]); bbox_preds [...,Q,2+4*(reg_max+1)] sigmoid
         outputs (or decoded cxcywh [...,Q,4] with decoded=True).  Returns (cost [P,Q,max_gt] on the device,
@@ -126,6 +127,7 @@ class GFLHungarianAssigner:
                                              C.c_void_p(out.data_ptr()), self.num_threads), 'dskd_lsap_batch_f32')
         return out
 
+    @L.guarded
     def solve_device(self, cost: torch.Tensor, m: dict, check: bool = False) -> torch.Tensor:
         """The same matching on the device (`dskd_lsap_batch_device`): no copy of the cost matrices, no host sync.
         `check=True` reads the per-problem status back (one sync) and raises like SciPy on an infeasible matrix."""
@@ -140,6 +142,7 @@ class GFLHungarianAssigner:
             raise ValueError('cost matrix is infeasible')          # scipy.optimize.linear_sum_assignment's message
         return assigned
 
+    @L.guarded
     def assign_batch(self, cls_scores, bbox_preds, gt_bboxes_list, gt_labels_list, img_shapes,
                      prev_labels: Optional[Sequence[int]] = None) -> Dict[str, torch.Tensor]:
         """All decoder layers at once (`loss_single_split` x 6 -> `get_targets`, head_il.py:504-512,1437-1455).
@@ -170,6 +173,7 @@ class GFLHungarianAssigner:
                     bbox_targets=bt, bbox_weights=bw, teacher_only_weights=only)
 
     # ------------------------------------------------------------------ the reference's per-image signature
+    @L.guarded
     def assign(self, bbox_pred, cls_pred, gt_bboxes, gt_labels, bbox_lrtb=None, img_meta=None,
                gt_bboxes_ignore=None, eps=1e-7):
         """gfl_hungarian_assigner.py:59-160: bbox_pred [Q,4] normalised cxcywh, cls_pred [Q,classes] logits,

@@ -302,10 +302,16 @@ __global__ void __launch_bounds__(256) prepare_v1_kernel(const __grid_constant__
     }
     if (tid == (int)blockDim.x - 1) s_total = excl + c;
     __syncthreads();
-    const int id_pred = s_id;  // 0 when fewer than b+1 queries carry a previous label (the reference raises, :705)
+    // fewer than b + 1 queries carry a previous label: the reference raises IndexError at :705.  Without a host sync
+    // the failure is made loud on the device instead: the pair's mask row and the step's loss become NaN.
+    const bool unmatched = b >= s_total;
+    const int id_pred = s_id;
     if (tid == 0) {
       p.ids[b] = id_pred;
-      if (b == 0 && p.matched_count) *p.matched_count = s_total;
+      if (b == 0) {
+        reinterpret_cast<int*>(p.counter)[1] = s_total;  // read back by the epilogue of the step
+        if (p.matched_count) *p.matched_count = s_total;
+      }
     }
     // ---- mask row b = softmax_c |hs_T[keepid[b]] - hs_S[id_pred]| (head_il.py:705-706); energy row cleared
     float* a = reinterpret_cast<float*>(smem_raw);
@@ -340,7 +346,7 @@ __global__ void __launch_bounds__(256) prepare_v1_kernel(const __grid_constant__
     if (tid == 0) bcast = sum;
     __syncthreads();
     sum = bcast;
-    for (int ch = tid; ch < C; ch += blockDim.x) p.rows[(int64_t)b * C + ch] = a[ch] / sum;
+    for (int ch = tid; ch < C; ch += blockDim.x) p.rows[(int64_t)b * C + ch] = unmatched ? __int_as_float(0x7fc00000) : a[ch] / sum;
     return;
   }
   b -= p.num_pairs;
@@ -362,6 +368,7 @@ __global__ void __launch_bounds__(128) rows_finish_final_kernel(const float* __r
                                                                 const float* __restrict__ rows, const float* __restrict__ eg,
                                                                 int C, double* __restrict__ loss_acc, unsigned* __restrict__ counter,
                                                                 float* __restrict__ loss, float* __restrict__ grad_hs_s) {
+  // counter[1]: matched student queries (prepare_v1_kernel); fewer than pairs => NaN loss (see there)
   __shared__ float red[32];
   __shared__ double dred[32];
   __shared__ float bcast;
@@ -397,9 +404,16 @@ __global__ void __launch_bounds__(128) rows_finish_final_kernel(const float* __r
     __threadfence();
     if (atomicAdd(counter, 1u) == gridDim.x - 1) {  // last pair: every partial sum is in
       __threadfence();
-      loss[0] = (float)(*reinterpret_cast<volatile double*>(loss_acc));
+      const bool short_of_queries = reinterpret_cast<const volatile int*>(counter)[1] < (int)gridDim.x;
+      loss[0] = short_of_queries ? __int_as_float(0x7fc00000) : (float)(*reinterpret_cast<volatile double*>(loss_acc));
     }
   }
+}
+
+// loss[0] = (float) acc for the KL criterion of the fused decode_v1 step, NaN when pairs went unmatched
+__global__ void v1_loss_final_kernel(const double* __restrict__ acc, const int* __restrict__ matched, int num_pairs,
+                                     float* __restrict__ loss) {
+  loss[0] = *matched < num_pairs ? __int_as_float(0x7fc00000) : (float)acc[0];
 }
 
 }  // namespace dskd
@@ -542,6 +556,12 @@ int launch_rows_finish_final(const DskdDsgfdStepArgs* a, const float* rows, cons
   rows_finish_final_kernel<<<a->num_pairs, 128, 0, st>>>(a->d_hs_teacher, a->d_hs_student, a->d_teacher_keepid, ids, rows,
                                                          energy, a->C, acc, counter, a->d_loss, grad_hs);
   DSKD_LAUNCH_OK("rows_finish_final_kernel");
+  return DSKD_OK;
+}
+
+int launch_v1_loss_final(const DskdDsgfdStepArgs* a, const double* acc, const unsigned* counter, cudaStream_t st) {
+  v1_loss_final_kernel<<<1, 1, 0, st>>>(acc, reinterpret_cast<const int*>(counter) + 1, a->num_pairs, a->d_loss);
+  DSKD_LAUNCH_OK("v1_loss_final_kernel");
   return DSKD_OK;
 }
 }  // namespace dskd

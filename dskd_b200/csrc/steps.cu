@@ -9,6 +9,7 @@ int launch_prepare_v1(const DskdDsgfdStepArgs* a, int* owner, float* rows, float
                       unsigned* counter, cudaStream_t st);
 int launch_rows_finish_final(const DskdDsgfdStepArgs* a, const float* rows, const float* energy, const int64_t* ids,
                              double* acc, unsigned* counter, float* grad_hs, cudaStream_t st);
+int launch_v1_loss_final(const DskdDsgfdStepArgs* a, const double* acc, const unsigned* counter, cudaStream_t st);
 }  // namespace dskd
 
 namespace {
@@ -30,7 +31,7 @@ struct Workspace {
     cell_map = off; off += align_up((int64_t)N * cells * 4);
     rows = off;     off += align_up((int64_t)std::max(P, 1) * C * 4);
     energy = off;   off += align_up((int64_t)std::max(P, 1) * C * 4);
-    acc = off;      off += align_up(16);      // right after energy: one memset clears both; [8] = finish counter, [12] = KL redo counter
+    acc = off;      off += align_up(16);      // right after energy: one memset clears both; [8] = finish counter, [12] = matched student queries
     ids = off;      off += align_up((int64_t)std::max(P, 1) * 8);
     kl_redo = off;  kl_redo_bytes = kl_bytes; off += align_up(kl_bytes);  // redo list of the KL kernels
     total = off;
@@ -80,8 +81,11 @@ extern "C" int dskd_dsgfd_step(const DskdDsgfdStepArgs* a, void* stream) {
   const bool row_mode = a->mask_mode <= DSKD_MODE_DECODE_V2;
   const bool v1 = a->mask_mode == DSKD_MODE_DECODE_V1;
   const int P = a->num_pairs;
-  if (a->N == 0) {
+  if (a->N == 0) {  // empty batch: zero loss, zero gradients, nothing matched
     DSKD_CUDA_OK(cudaMemsetAsync(a->d_loss, 0, sizeof(float), st));
+    if (a->d_matched_count) DSKD_CUDA_OK(cudaMemsetAsync(a->d_matched_count, 0, sizeof(int32_t), st));
+    if (a->d_grad_hs_student)
+      DSKD_CUDA_OK(cudaMemsetAsync(a->d_grad_hs_student, 0, sizeof(float) * (size_t)a->num_query_rows * a->C, st));
     return DSKD_OK;
   }
   const bool want_hs = v1 && a->d_grad_hs_student != nullptr;
@@ -173,6 +177,7 @@ extern "C" int dskd_dsgfd_step(const DskdDsgfdStepArgs* a, void* stream) {
                                 a->C, acc, want_hs ? a->d_grad_hs_student : nullptr, stream);
     if (rc) return rc;
   }
+  if (fused_v1) return launch_v1_loss_final(a, acc, counter, st);  // NaN when teacher detections went unpaired
   return dskd_f64_to_f32(acc, a->d_loss, 1, 1.0f, stream);
 }
 

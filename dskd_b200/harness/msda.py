@@ -54,6 +54,7 @@ class _MsdaFn(torch.autograd.Function):
         return gv, gl, ga, None
 
 
+@L.guarded
 def ms_deform_attn(value, spatial_shapes, sampling_locations, attention_weights):
     """value [N,S,M,D]; spatial_shapes list[(H,W)]; sampling_locations [N,Lq,M,L,P,2] in [0,1] (x, y);
     attention_weights [N,Lq,M,L,P] -> [N,Lq,M*D].  Raises on CPU tensors."""

@@ -72,19 +72,45 @@ def _img_hw_list(assignments, n):
     return hw
 
 
-_meta_cache: Dict[tuple, torch.Tensor] = {}
+class _MetaCache:
+    """Small int32 tables (box prefix offsets, image sizes) on the device.
+
+    The offsets change with every training iteration, so a miss must be cheap: the table goes through a pinned staging
+    tensor and an asynchronous copy (no host sync).  Recently used tables are kept (LRU) because a step captured in a CUDA
+    graph bakes their addresses in: a table handed out while the stream is capturing is pinned in the cache for the
+    lifetime of the process and never evicted, so a replay cannot read freed memory."""
+
+    def __init__(self, capacity=64):
+        self.capacity = capacity
+        self._entries = {}            # key -> [tensor, captured]
+
+    def get(self, meta, device):
+        key = (tuple(meta), str(device))
+        capturing = torch.cuda.is_current_stream_capturing()
+        ent = self._entries.pop(key, None)
+        if ent is None:
+            if capturing:
+                raise L.DskdError('DSGFeatureDistillLoss: a new box / image-size table under CUDA-graph capture -- run the '
+                                  'step once with the same assignments before capturing it (host-to-device copies of '
+                                  'fresh host data cannot be captured)')
+            host = torch.tensor(meta, dtype=torch.int32).pin_memory()
+            ent = [host.to(device, non_blocking=True), False, host]
+        ent[1] = ent[1] or capturing
+        self._entries[key] = ent                                  # most recently used last
+        if len(self._entries) > self.capacity:
+            for k in list(self._entries):
+                if len(self._entries) <= self.capacity:
+                    break
+                if not self._entries[k][1]:
+                    del self._entries[k]
+        return ent[0]
+
+
+_meta_cache = _MetaCache()
 
 
 def _meta_tensor(meta, device):
-    """int32 table on the device; identical tables (same box counts / image sizes) are uploaded once."""
-    key = (tuple(meta), str(device))
-    t = _meta_cache.get(key)
-    if t is None:
-        if len(_meta_cache) > 256:
-            _meta_cache.clear()
-        t = torch.tensor(meta, dtype=torch.int32).to(device)
-        _meta_cache[key] = t
-    return t
+    return _meta_cache.get(meta, device)
 
 
 def _box_meta(boxes: Sequence[torch.Tensor], img_hw, device, gt_boxes=None):
@@ -290,6 +316,7 @@ class DSGFeatureDistillLoss(nn.Module):
         return (f'criterion={self.criterion}, mask_mode={self.mask_mode}, feature_source={self.feature_source}, '
                 f'reduction={self.reduction}, loss_weight={self.loss_weight}, T={self.T}')
 
+    @L.guarded
     def forward(self, student_feats, teacher_feats, queries, assignments, weight=None, avg_factor=None,
                 reduction_override=None):
         reduction = _resolve_reduction(self.reduction, reduction_override, avg_factor)
@@ -298,7 +325,7 @@ class DSGFeatureDistillLoss(nn.Module):
                                       '(the reference head would raise at head_il.py:715 as well)')
         if weight is not None:
             raise NotImplementedError('the head always calls loss_fg_feature with weight=None (head_il.py:715)')
-        hs_student, hs_teacher = queries
+        hs_student, hs_teacher = queries if queries is not None else (None, None)
         plan = _DsgfdPlan()
         plan.criterion, plan.mask_mode = self.criterion, self.mask_mode
         plan.temperature, plan.validate = self.T, self.validate
@@ -326,6 +353,8 @@ class DSGFeatureDistillLoss(nn.Module):
         dev = s_feats[0].device
         L.require_device(s_feats[0])
         plan.N, plan.C = int(N), int(C)
+        if N == 0:
+            raise L.DskdError('DSGFeatureDistillLoss: empty batch (the reference divides by N = 0 at head_il.py:716-717)')
 
         # ---- per-level scale: loss_weight, the 1/N of :716-717, the reduction and avg_factor
         base = float(self.loss_weight) / float(N)
@@ -365,10 +394,19 @@ class DSGFeatureDistillLoss(nn.Module):
             if self.mask_mode == 'decode_v1':
                 plan.labels = assignments['student_labels'].to(dev, torch.int64).contiguous()
                 plan.prev_mask = _prev_masks.get(assignments['prev_labels'], plan.num_classes, dev)
-        hs_s = L.f32c(hs_student)
-        hs_t = L.f32c(hs_teacher.detach())
-        if hs_s.shape[-1] != C:
-            raise L.DskdError(f'embedding width {hs_s.shape[-1]} != feature channels {C} (head_il.py:706 broadcasts them)')
+        # embeddings: the student's for decode_v1 only, the teacher's for decode_v1 / v2; the cell-mask modes use none
+        # (head_il.py:860-925,1082-1129 never touch hs)
+        empty = torch.empty(0, dtype=torch.float32, device=dev)
+        hs_s, hs_t = empty, empty
+        if self.mask_mode in _ROW_MODES:
+            if hs_teacher is None or (self.mask_mode == 'decode_v1' and hs_student is None):
+                raise L.DskdError(f"mask_mode='{self.mask_mode}' needs queries=(hs_student, hs_teacher)")
+            hs_t = L.f32c(hs_teacher.detach())
+            if self.mask_mode == 'decode_v1':
+                hs_s = L.f32c(hs_student)
+            for h in (hs_s, hs_t):
+                if h.numel() and h.shape[-1] != C:
+                    raise L.DskdError(f'embedding width {h.shape[-1]} != feature channels {C} (head_il.py:706 broadcasts them)')
         return _DsgfdFn.apply(plan, hs_s, hs_t, *s_feats, *t_feats)
 
 
@@ -456,6 +494,7 @@ class BetweenClassDistanceLoss(nn.Module):
     def extra_repr(self):
         return f'reduction={self.reduction}, loss_weight={self.loss_weight}, sync_prototypes={self.sync_prototypes}'
 
+    @L.guarded
     def forward(self, student_feats, teacher_feats, queries, assignments, weight=None, avg_factor=None,
                 reduction_override=None):
         reduction = _resolve_reduction(self.reduction, reduction_override, avg_factor)
@@ -547,6 +586,7 @@ class _ElementwiseFn(torch.autograd.Function):
         return None, None, out_p, out_t, None
 
 
+@L.guarded
 def _weighted_reduce(kind, T, pred, target, weight, reduction, avg_factor, loss_weight):
     """utils.py:30-59 on top of the fused elementwise kernel."""
     if pred.shape != target.shape:

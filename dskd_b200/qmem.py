@@ -16,6 +16,7 @@ import torch
 from . import _lib as L
 
 
+@L.guarded
 def qmem_cell_weights(teacher_memory: torch.Tensor, hs_teacher: torch.Tensor, teacher_keepid: torch.Tensor,
                       teacher_scores: Optional[torch.Tensor], box_start: torch.Tensor, max_per_image: int,
                       temperature: float = 0.5) -> torch.Tensor:

@@ -17,6 +17,7 @@ import torch
 from . import _lib as L
 
 
+@L.guarded
 def teacher_info_from_outputs(cls_scores: torch.Tensor, bbox_preds: torch.Tensor, img_shapes, score_thr: float = 0.3,
                               max_per_img: int = 100, reg_max: int = 16, need_logits: bool = False,
                               split: bool = True) -> Dict[str, object]:

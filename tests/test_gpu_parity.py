@@ -331,6 +331,47 @@ def test_dsgfd_kl_many_runs_per_tile(pool, monkeypatch):
     assert_grad(hs.grad, o_hs.grad)
 
 
+@pytest.mark.parametrize('crit', ['mse', 'kl'])
+def test_dsgfd_fewer_matched_queries_than_teacher_boxes_is_loud(crit):
+    """The reference raises IndexError at head_il.py:705 when fewer student queries carry a previous label than there are
+    teacher detections.  validate=True raises the same error (one host sync); validate=False (the graph-capturable default)
+    must not return a plausible number: loss and the embedding gradient are NaN."""
+    cpu = synth.make_distill_inputs(num_images=2, num_prev=40, seed=16, channels=32, **SMALL)
+    a = dict(cpu.assignments)
+    labels = a['student_labels'].clone()
+    prev_q = torch.nonzero(labels < 40).squeeze(1)
+    labels[prev_q[-3:]] = 80                       # three matched queries lose their previous label
+    a['student_labels'] = labels
+    cpu.assignments = a
+    gpu = cpu.to(DEV)
+    feats, hs = gpu.clone_student()
+    with pytest.raises(IndexError):
+        dskd_b200.DSGFeatureDistillLoss(criterion=crit, validate=True)(feats, gpu.teacher_feats, (hs, gpu.hs_teacher), gpu.assignments)
+    feats, hs = gpu.clone_student()
+    loss = dskd_b200.DSGFeatureDistillLoss(criterion=crit)(feats, gpu.teacher_feats, (hs, gpu.hs_teacher), gpu.assignments)
+    loss.backward()
+    assert torch.isnan(loss)
+    assert torch.isnan(hs.grad).any()
+
+
+def test_dsgfd_cell_masks_need_no_queries():
+    """sg_out / fg_only never touch the decoder embeddings (head_il.py:860-925,1082-1129): queries may be None."""
+    cpu = synth.make_distill_inputs(num_images=2, num_prev=40, seed=9, channels=64, **SMALL)
+    gpu = cpu.to(DEV)
+    for crit in ('mse', 'kl'):
+        mod = dskd_b200.DSGFeatureDistillLoss(criterion=crit, mask_mode='fg_only')
+        with_q = mod(gpu.student_feats, gpu.teacher_feats, (gpu.hs_student, gpu.hs_teacher), gpu.assignments)
+        without = mod(gpu.student_feats, gpu.teacher_feats, None, gpu.assignments)
+        half = mod(gpu.student_feats, gpu.teacher_feats, (None, gpu.hs_teacher), gpu.assignments)
+        assert float(with_q) == float(without) == float(half)
+    v2 = dskd_b200.DSGFeatureDistillLoss(criterion='mse', mask_mode='decode_v2')
+    a = v2(gpu.student_feats, gpu.teacher_feats, (gpu.hs_student, gpu.hs_teacher), gpu.assignments)
+    b = v2(gpu.student_feats, gpu.teacher_feats, (None, gpu.hs_teacher), gpu.assignments)
+    assert float(a) == float(b)
+    with pytest.raises(dskd_b200._lib.DskdError):
+        dskd_b200.DSGFeatureDistillLoss(criterion='mse')(gpu.student_feats, gpu.teacher_feats, None, gpu.assignments)
+
+
 @pytest.mark.parametrize('num_prev', [40, 70])
 @pytest.mark.parametrize('reduction', ['mean', 'sum'])
 def test_bcdd_vs_oracle(num_prev, reduction):

@@ -25,11 +25,15 @@
 namespace dskd {
 
 constexpr int kKlWarps = 8;       // warps per CTA (one channel at a time each)
-constexpr int kKlBlk = 5;         // rows per block: the unit of loading ahead and of skipping rows without boxes
-constexpr int kKlStages = 2;      // row blocks in the register ring: the loads of kKlStages - 1 blocks are in flight
+// Measured on B200 (tools/kl_perf.py --tune, 16 images of 800x1333): two channels per pass, 4-row blocks loaded and consumed
+// in place (no register ring), 4 CTAs x 8 warps per SM at 64 registers: 139 us; with a 2-stage ring at 127 registers
+// (2 CTAs per SM) 168 us; one channel per pass (5-row blocks, 2 stages, 4 CTAs per SM) 169 us.
+constexpr int kKlBlk = 4;         // rows per block: the unit of loading and of skipping rows without boxes (gradient kernels)
+constexpr int kKlBlkFwd = 5;      //   ... forward-only kernels
+constexpr int kKlStages = 1;      // row blocks in the register ring: the loads of kKlStages - 1 blocks are in flight ahead
 constexpr int kKlMinCtas = 4;     // CTAs per SM the register budget is cut for
 constexpr int kKlChunk = 16;      // channels per CTA (8 for small batches: twice the CTAs to fill 148 SMs x 4)
-constexpr int kKlPool = 256;      // (owner, lane, A, B) records a warp can park per channel before the normalisers are known
+constexpr int kKlPool = 192;      // (owner, lane, A, B) records a warp can park per pass before the normalisers are known
 constexpr int kKlMaxH = 1600;     // rows per level (shared-memory tables: 136 B per row)
 constexpr int kKlRedoCtas = 148;  // grid of the redo launch
 constexpr float kLn2 = 0.6931471805599453f;
@@ -117,12 +121,13 @@ struct KlTables {
 // dynamic shared memory layout of the streaming kernel (the same arithmetic on both sides)
 struct KlSmem {
   size_t endm, anym, pool, act, total;
-  __host__ __device__ KlSmem(int max_blocks, int blk, bool grad, int pool_cap) {
+  // rec_words: 32-bit words per run record: key + (A, B) per channel of the pass
+  __host__ __device__ KlSmem(int max_blocks, int blk, bool grad, int pool_cap, int rec_words) {
     const size_t rows = (size_t)max_blocks * blk;
     endm = rows * 32 * 4;
     anym = endm + rows * 4;
     pool = (anym + rows * 4 + 15) / 16 * 16;
-    act = pool + (grad ? (size_t)kKlWarps * pool_cap * 12 : 0);
+    act = pool + (grad ? (size_t)kKlWarps * pool_cap * rec_words * 4 : 0);
     total = (act + (size_t)max_blocks * 2 + 15) / 16 * 16;
   }
 };
@@ -250,6 +255,171 @@ __device__ __forceinline__ void kl_stream_pass(const KlTables& tb, KlChan& ch, c
   }
 }
 
+// The same pass over TWO neighbouring channels (c, c + 1) at once.  The owner table, the predicates, the row offsets and
+// the run-end bookkeeping are per column, not per channel, so they are paid once for both; the arithmetic runs on the
+// packed fp32x2 pipe (FMUL2 / FADD2 / FFMA2: one issue slot per pair), every value a (channel c, channel c + 1) pair.
+// The kernel is bound by instruction issue, not by DRAM (ncu: 75 % of the issue slots at 45 % of the DRAM roof with one
+// channel per pass), which is what this halves.
+struct KlChan2 {
+  const float* Sp0;    // plane c + w0 + lane
+  const float* Tp0;
+  const float* Sp1;    // plane c + 1
+  const float* Tp1;
+  const float* rowsc;  // rows + c (8-byte aligned: c even, C even)
+  float2 ss, st, ws;
+  int base;
+};
+
+__device__ __forceinline__ void ld4_stream_ge0(float2& s, float2& t, const float* s0, const float* s1, const float* t0,
+                                               const float* t1, int key) {
+  asm("{\n\t.reg .pred q;\n\tsetp.ge.s32 q, %8, 0;\n\t"
+      "mov.f32 %0, 0f00000000;\n\tmov.f32 %1, 0f00000000;\n\tmov.f32 %2, 0f00000000;\n\tmov.f32 %3, 0f00000000;\n\t"
+      "@q ld.global.nc.L1::no_allocate.f32 %0, [%4];\n\t@q ld.global.nc.L1::no_allocate.f32 %1, [%5];\n\t"
+      "@q ld.global.nc.L1::no_allocate.f32 %2, [%6];\n\t@q ld.global.nc.L1::no_allocate.f32 %3, [%7];\n\t}"
+      : "=f"(s.x), "=f"(s.y), "=f"(t.x), "=f"(t.y)
+      : "l"(s0), "l"(s1), "l"(t0), "l"(t1), "r"(key));
+}
+__device__ __forceinline__ void ld4_stream_nz(float2& s, float2& t, const float* s0, const float* s1, const float* t0,
+                                              const float* t1, float key) {
+  asm("{\n\t.reg .pred q;\n\tsetp.neu.f32 q, %8, 0f00000000;\n\t"
+      "mov.f32 %0, 0f00000000;\n\tmov.f32 %1, 0f00000000;\n\tmov.f32 %2, 0f00000000;\n\tmov.f32 %3, 0f00000000;\n\t"
+      "@q ld.global.nc.L1::no_allocate.f32 %0, [%4];\n\t@q ld.global.nc.L1::no_allocate.f32 %1, [%5];\n\t"
+      "@q ld.global.nc.L1::no_allocate.f32 %2, [%6];\n\t@q ld.global.nc.L1::no_allocate.f32 %3, [%7];\n\t}"
+      : "=f"(s.x), "=f"(s.y), "=f"(t.x), "=f"(t.y)
+      : "l"(s0), "l"(s1), "l"(t0), "l"(t1), "f"(key));
+}
+__device__ __forceinline__ float2 ld_cached_f2_ge0(const float* p, int key) {
+  float2 v;
+  asm("{\n\t.reg .pred q;\n\tsetp.ge.s32 q, %3, 0;\n\tmov.f32 %0, 0f00000000;\n\tmov.f32 %1, 0f00000000;\n\t"
+      "@q ld.global.nc.v2.f32 {%0, %1}, [%2];\n\t}"
+      : "=f"(v.x), "=f"(v.y)
+      : "l"(p), "r"(key));
+  return v;
+}
+__device__ __forceinline__ float2 ex2_2(float2 x) { return make_float2(fast_ex2(x.x), fast_ex2(x.y)); }
+
+template <bool CELL, bool GRAD, int R, int NB>
+__device__ __forceinline__ void kl_stream_pass2(const KlTables& tb, KlChan2& ch, const unsigned W, const int lane,
+                                                const int nact, const float kscale, const unsigned pool_addr,
+                                                const int pool_words, const int dbg) {
+  struct Stage { float2 s[R], t[R]; };
+  Stage stg[NB];
+  float2 A = make_float2(0.f, 0.f), B = make_float2(0.f, 0.f);
+  const float2 k2 = make_float2(kscale, kscale), neg1 = make_float2(-1.f, -1.f);
+  auto load = [&](Stage& sg, int entry) {
+    const int r0 = (entry & 0x7fff) * R;
+    unsigned o = (unsigned)r0 * W;
+#pragma unroll
+    for (int i = 0; i < R; ++i, o += W) {
+      const int key = tb.moff[(r0 + i) * 32 + lane];
+      if (CELL) ld4_stream_nz(sg.s[i], sg.t[i], ch.Sp0 + o, ch.Sp1 + o, ch.Tp0 + o, ch.Tp1 + o, __int_as_float(key));
+      else ld4_stream_ge0(sg.s[i], sg.t[i], ch.Sp0 + o, ch.Sp1 + o, ch.Tp0 + o, ch.Tp1 + o, key);
+    }
+  };
+  auto compute = [&](const Stage& sg, int entry, auto ends_tag) {
+    constexpr bool ENDS = decltype(ends_tag)::value;  // some lane's run ends inside this block
+    const int r0 = (entry & 0x7fff) * R;
+    float2 m[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const int off = tb.moff[(r0 + i) * 32 + lane];
+      if (CELL) m[i] = make_float2(__int_as_float(off), __int_as_float(off));
+      else m[i] = ld_cached_f2_ge0(ch.rowsc + (unsigned)off, off);
+      m[i] = __fmul2_rn(m[i], k2);
+    }
+    float2 pa[R], pb[R];  // ENDS: T_h e^y, T_h e^x of every row, so that the arithmetic of the block stays branch-free
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const float2 x = __fmul2_rn(sg.s[i], m[i]), y = __fmul2_rn(sg.t[i], m[i]);
+      const float2 e = ex2_2(x), f = ex2_2(y);
+      ch.ss = __fadd2_rn(ch.ss, e);
+      ch.st = __fadd2_rn(ch.st, f);
+      ch.ws = __ffma2_rn(e, __ffma2_rn(y, neg1, x), ch.ws);
+      if (GRAD && !ENDS) {
+        A = __ffma2_rn(sg.t[i], f, A);
+        B = __ffma2_rn(sg.t[i], e, B);
+      }
+      if (ENDS) {
+        pa[i] = __fmul2_rn(sg.t[i], f);
+        pb[i] = __fmul2_rn(sg.t[i], e);
+      }
+    }
+    if (ENDS) {
+      unsigned em[R];
+#pragma unroll
+      for (int i = 0; i < R; ++i) em[i] = (dbg & 8) ? 0u : tb.endm[r0 + i];
+#pragma unroll
+      for (int i = 0; i < R; ++i) {
+        A = __fadd2_rn(A, pa[i]);
+        B = __fadd2_rn(B, pb[i]);
+        if (em[i]) {  // warp-uniform: the run of some lane ends with this row
+          // the lanes whose run ends here park (owner, lane, A, B of both channels) in consecutive pool slots
+          const bool mine = (em[i] >> lane) & 1u;
+          if (mine) {  // five planes of pool_words each
+            const unsigned a0 = pool_addr + 4u * (ch.base + __popc(em[i] & ((1u << lane) - 1u)));
+            const unsigned pw = 4u * pool_words;
+            st_shared_b32(a0, tb.moff[(r0 + i) * 32 + lane] * 32 + lane);
+            st_shared_b32(a0 + pw, __float_as_int(A.x));
+            st_shared_b32(a0 + 2 * pw, __float_as_int(B.x));
+            st_shared_b32(a0 + 3 * pw, __float_as_int(A.y));
+            st_shared_b32(a0 + 4 * pw, __float_as_int(B.y));
+            A = make_float2(0.f, 0.f);
+            B = make_float2(0.f, 0.f);
+          }
+          ch.base += __popc(em[i]);
+        }
+      }
+    }
+  };
+  auto compute_any = [&](const Stage& sg, int entry) {
+    if (GRAD && (entry & 0x8000) && !(dbg & 2)) compute(sg, entry, std::true_type{});
+    else compute(sg, entry, std::false_type{});
+  };
+#pragma unroll
+  for (int j = 0; j < NB - 1; ++j)
+    if (j < nact) load(stg[j], tb.act[j]);
+  for (int k = 0; k < nact; k += NB) {
+#pragma unroll
+    for (int u = 0; u < NB; ++u) {
+      const int kk = k + u;
+      if (kk < nact) {
+        if (kk + NB - 1 < nact) load(stg[(u + NB - 1) % NB], tb.act[kk + NB - 1]);
+        compute_any(stg[u], tb.act[kk]);
+      }
+    }
+  }
+}
+
+// Bottom of a column for one channel of a pass: the runs parked in the pool (planes ia / ib hold A / B of this channel)
+// become d loss / d mask rows: neighbouring records of one owner are added up first (segmented scan over the lanes), then
+// one red.global per segment.
+__device__ __forceinline__ void kl_flush_pool(const int* pool, int pool_words, int ia, int ib, int count, int lane,
+                                              const float* norm /* [32][stride]: rt, rs of the source lane */, int stride,
+                                              int io, float gcoef, float* __restrict__ growc, bool no_red) {
+  constexpr unsigned kFull = 0xffffffffu;
+  for (int j0 = 0; j0 < count; j0 += 32) {
+    const int j = j0 + lane;
+    const bool have = j < count;
+    const int key = have ? pool[j] : -1 - lane;  // owner * C * 32 + lane of the column
+    float g = 0.f;
+    if (have) {
+      const float* nr = norm + (key & 31) * stride + io;
+      g = gcoef * (__int_as_float(pool[j + ia * pool_words]) * nr[0] - __int_as_float(pool[j + ib * pool_words]) * nr[1]);
+    }
+    const int own = key >> 5;
+    const int prev = __shfl_up_sync(kFull, own, 1), next = __shfl_down_sync(kFull, own, 1);
+    bool open = lane > 0 && prev == own;  // the segment continues to the left
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const float gv = __shfl_up_sync(kFull, g, d);
+      const bool ov = __shfl_up_sync(kFull, (int)open, d);
+      if (open && lane >= d) { g += gv; open = ov; }
+    }
+    const bool tail = lane == 31 || next != own;
+    if (have && tail && !no_red) atomicAdd(growc + own, g);
+  }
+}
+
 // Streaming kernel, [N,C,H,W] layout.  A CTA owns one column tile (level, image, <= 32 consecutive w) and a chunk of
 // channels; each warp streams one channel plane at a time down ALL rows of the tile, lane = column, so every feature
 // load is one coalesced row piece and the running sums of a column live in registers.  Once per CTA the owners of the
@@ -257,12 +427,13 @@ __device__ __forceinline__ void kl_stream_pass(const KlTables& tb, KlChan& ch, c
 // that hold a box cell in some column are visited (the others add e^0 per row in closed form).  The (owner, A, B)
 // records of finished runs wait in a per-warp pool until the bottom of the column.  The number of runs of a tile does
 // not depend on the channel, so the CTA knows up front how many warps can run side by side: with more runs than one
-// pool holds, 4 / 2 / 1 warps work with 2 / 4 / 8 pools each.
-template <bool CELL, bool GRAD, int R, int NB, int MINB>
+// pool holds, 4 / 2 / 1 warps work with 2 / 4 / 8 pools each.  NC = 2: a warp takes two neighbouring channels per pass
+// (kl_stream_pass2); NC = 1 is the scalar pass for an odd channel count.
+template <bool CELL, bool GRAD, int NC, int R, int NB, int MINB>
 __global__ void __launch_bounds__(32 * kKlWarps, MINB) dsgfd_kl_stream_kernel(const __grid_constant__ KlParams prm) {
   extern __shared__ __align__(16) unsigned char kl_smem[];
   __shared__ double red[32];
-  __shared__ float2 norm_s[kKlWarps][32];
+  __shared__ float norm_s[kKlWarps][32][2 * NC];  // per lane: (1 / sum e^y, 1 / sum e^x) of each channel of the pass
   __shared__ int nact_s, nadd_s, nends_s;
   __shared__ unsigned redo_s;
   constexpr unsigned kFull = 0xffffffffu;
@@ -273,7 +444,8 @@ __global__ void __launch_bounds__(32 * kKlWarps, MINB) dsgfd_kl_stream_kernel(co
   const unsigned W = (unsigned)prm.levels[lvl].W;
   const int nblk = (H + R - 1) / R, rows_pad = nblk * R;
 
-  const KlSmem lay(prm.max_blocks, R, GRAD, prm.pool_cap);
+  constexpr int kRec = 1 + 2 * NC;  // words per run record
+  const KlSmem lay(prm.max_blocks, R, GRAD, prm.pool_cap, kRec);
   KlTables tb;
   tb.moff = reinterpret_cast<int*>(kl_smem);
   tb.mw = reinterpret_cast<float*>(kl_smem);
@@ -354,67 +526,80 @@ __global__ void __launch_bounds__(32 * kKlWarps, MINB) dsgfd_kl_stream_kernel(co
     }
   }
   const int wstep = kKlWarps / share;  // active warps: 0 .. wstep - 1, warp w owns the pools w * share ..
-  // warp w's records: three planes (key, A, B) of share * pool_cap words each
+  // warp w's records: planes (key, A, B per channel) of share * pool_cap words each
   const int pool_words = share * prm.pool_cap;
-  const int* pool = reinterpret_cast<const int*>(kl_smem + lay.pool) + (size_t)warp * 3 * pool_words;
+  const int* pool = reinterpret_cast<const int*>(kl_smem + lay.pool) + (size_t)warp * kRec * pool_words;
   const unsigned pool_addr = (unsigned)__cvta_generic_to_shared(pool);
   double kl_total = 0.0;
 
   if (warp < wstep) {
-    for (int c = c_begin + warp; c < c_end; c += wstep) {
-      KlChan ch;
-      {
-        const int64_t plane = ((int64_t)tl.img * C + c) * ((int64_t)H * W) + tl.w0 + lane;
+    const bool col_ok = lane < tl.wn;
+    for (int c = c_begin + NC * warp; c < c_end; c += NC * wstep) {
+      const int64_t plane = ((int64_t)tl.img * C + c) * ((int64_t)H * W) + tl.w0 + lane;
+      bool ok;
+      int base;
+      float kl = 0.f;
+      if constexpr (NC == 2) {
+        KlChan2 ch;
+        ch.Sp0 = prm.student[lvl] + plane;
+        ch.Tp0 = prm.teacher[lvl] + plane;
+        ch.Sp1 = ch.Sp0 + (int64_t)H * W;
+        ch.Tp1 = ch.Tp0 + (int64_t)H * W;
+        ch.rowsc = CELL ? nullptr : prm.rows + c;
+        // keep the bases in registers: every address is then one IMAD.WIDE.U32 of a 32-bit element offset
+        asm volatile("" : "+l"(ch.Sp0), "+l"(ch.Tp0), "+l"(ch.Sp1), "+l"(ch.Tp1), "+l"(ch.rowsc));
+        ch.ss = ch.st = ch.ws = make_float2(0.f, 0.f);
+        ch.base = 0;
+        kl_stream_pass2<CELL, GRAD, R, NB>(tb, ch, W, lane, nact, prm.kscale, pool_addr, pool_words, prm.dbg);
+        const float nadd = (float)nadd_s;
+        const float ss0 = ch.ss.x + nadd, st0 = ch.st.x + nadd, ss1 = ch.ss.y + nadd, st1 = ch.st.y + nadd;
+        ok = __all_sync(kFull, !col_ok || (kl_in_range(ss0, st0, ch.ws.x) && kl_in_range(ss1, st1, ch.ws.y)));
+        base = ch.base;
+        if (ok) {
+          kl = kl_col(ss0, st0, ch.ws.x) + kl_col(ss1, st1, ch.ws.y);
+          if (GRAD) {
+            norm_s[warp][lane][0] = __fdividef(1.f, st0);
+            norm_s[warp][lane][1] = __fdividef(1.f, ss0);
+            norm_s[warp][lane][2] = __fdividef(1.f, st1);
+            norm_s[warp][lane][3] = __fdividef(1.f, ss1);
+          }
+        }
+      } else {
+        KlChan ch;
         ch.Sp = prm.student[lvl] + plane;
         ch.Tp = prm.teacher[lvl] + plane;
-      }
-      ch.rowsc = CELL ? nullptr : prm.rows + c;
-      // keep the bases in registers: every address is then one IMAD.WIDE.U32 of a 32-bit element offset
-      asm volatile("" : "+l"(ch.Sp), "+l"(ch.Tp), "+l"(ch.rowsc));
-      ch.ss = ch.st = ch.ws = 0.f;
-      ch.base = 0;
-      kl_stream_pass<CELL, GRAD, R, NB>(tb, ch, W, lane, nact, prm.kscale, pool_addr, pool_words, prm.dbg);
-
-      // ---- bottom of the column: normalisers, KL, parked runs
-      const float nadd = (float)nadd_s;
-      const float ss = ch.ss + nadd, st = ch.st + nadd;
-      const bool col_ok = lane < tl.wn;
-      if (__all_sync(kFull, !col_ok || kl_in_range(ss, st, ch.ws))) {
-        const float rs = __fdividef(1.f, ss), rt = __fdividef(1.f, st);
-        if (col_ok) kl_total += (double)kl_col(ss, st, ch.ws);
-        if (GRAD) {
-          const float gcoef = prm.scale[lvl] * prm.temperature / (float)H;  // d loss / d pred = scale * (T/H) * (p - q)
-          float* __restrict__ growc = prm.grad_rows + c;
-          norm_s[warp][lane] = make_float2(rt, rs);
-          __syncwarp();
-          for (int j0 = 0; j0 < ch.base && !(prm.dbg & 4); j0 += 32) {
-            const int j = j0 + lane;
-            const bool have = j < ch.base;
-            const int key = have ? pool[j] : -1 - lane;  // owner * C * 32 + lane of the column
-            float g = 0.f;
-            if (have) {
-              const float2 nr = norm_s[warp][key & 31];
-              g = gcoef * (__int_as_float(pool[j + pool_words]) * nr.x - __int_as_float(pool[j + 2 * pool_words]) * nr.y);
-            }
-            // the lanes whose runs ended with one row sit next to each other and mostly belong to one box: add up
-            // neighbours with the same owner (segmented scan), one red.global per segment
-            const int own = key >> 5;
-            const int prev = __shfl_up_sync(kFull, own, 1), next = __shfl_down_sync(kFull, own, 1);
-            bool open = lane > 0 && prev == own;  // the segment continues to the left
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-              const float gv = __shfl_up_sync(kFull, g, d);
-              const bool ov = __shfl_up_sync(kFull, (int)open, d);
-              if (open && lane >= d) { g += gv; open = ov; }
-            }
-            const bool tail = lane == 31 || next != own;
-            if (have && tail && !(prm.dbg & 1)) atomicAdd(growc + own, g);
+        ch.rowsc = CELL ? nullptr : prm.rows + c;
+        asm volatile("" : "+l"(ch.Sp), "+l"(ch.Tp), "+l"(ch.rowsc));
+        ch.ss = ch.st = ch.ws = 0.f;
+        ch.base = 0;
+        kl_stream_pass<CELL, GRAD, R, NB>(tb, ch, W, lane, nact, prm.kscale, pool_addr, pool_words, prm.dbg);
+        const float nadd = (float)nadd_s;
+        const float ss = ch.ss + nadd, st = ch.st + nadd;
+        ok = __all_sync(kFull, !col_ok || kl_in_range(ss, st, ch.ws));
+        base = ch.base;
+        if (ok) {
+          kl = kl_col(ss, st, ch.ws);
+          if (GRAD) {
+            norm_s[warp][lane][0] = __fdividef(1.f, st);
+            norm_s[warp][lane][1] = __fdividef(1.f, ss);
           }
+        }
+      }
+      // ---- bottom of the column: KL, parked runs
+      if (ok) {
+        if (col_ok) kl_total += (double)kl;
+        if (GRAD && !(prm.dbg & 4)) {
+          const float gcoef = prm.scale[lvl] * prm.temperature / (float)H;  // d loss / d pred = scale * (T/H) * (p - q)
+          __syncwarp();
+#pragma unroll
+          for (int k = 0; k < NC; ++k)
+            kl_flush_pool(pool, pool_words, 1 + 2 * k, 2 + 2 * k, base, lane, &norm_s[warp][0][0], 2 * NC, 2 * k, gcoef,
+                          prm.grad_rows + c + k, prm.dbg & 1);
           __syncwarp();
         }
       } else if (lane == 0) {
-        // exponentials out of range for the unshifted sums: this (tile, channel) is redone with exact maxima
-        atomicOr(&redo_s, 1u << (c - c_begin));
+        // exponentials out of range for the unshifted sums: these (tile, channel)s are redone with exact maxima
+        atomicOr(&redo_s, (NC == 2 ? 3u : 1u) << (c - c_begin));
       }
     }
   }
@@ -439,7 +624,15 @@ __global__ void __launch_bounds__(32 * kKlWarps) dsgfd_kl_redo_kernel(const __gr
   float* mw = reinterpret_cast<float*>(kl_smem);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float Temp = prm.temperature;
-  for (int b = blockIdx.x; b < prm.num_blocks; b += gridDim.x) {
+  // the CTA's share of the masks in one coalesced read: normally all zero, and the launch is over after one load
+  const int per = (prm.num_blocks + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int b_first = blockIdx.x * per, b_last = min(prm.num_blocks, b_first + per);
+  {
+    unsigned any = 0u;
+    for (int b = b_first + tid; b < b_last; b += 32 * kKlWarps) any |= prm.redo_mask[b];
+    if (!__syncthreads_or(any != 0u)) return;
+  }
+  for (int b = b_first; b < b_last; ++b) {
     const unsigned todo = prm.redo_mask[b];
     if (todo == 0u) continue;  // uniform over the CTA
     const KlTile tl = kl_decode_tile(prm, b);
@@ -800,10 +993,15 @@ extern "C" int dskd_dsgfd_kl_fwd_bwd(const DskdDsgfdKlArgs* a, void* stream) {
   cudaStream_t st = as_stream(stream);
   if (a->layout == DSKD_LAYOUT_SNC) return launch_kl_snc(a, st);
   DSKD_REQUIRE(max_h <= kKlMaxH, "dsgfd_kl: H (%d) above the supported %d", max_h, kKlMaxH);
-  // tuning hook (tools/kl_perf.py): DSKD_KL_TUNE="rows_per_block,stages,ctas_per_sm,channels_per_cta,pool_records,dbg"
-  int blk = kKlBlk, stages = kKlStages, minb = kKlMinCtas, chunk = a->N <= 4 ? kKlChunk / 2 : kKlChunk, cap = kKlPool, dbg = 0;
-  if (const char* tune = getenv("DSKD_KL_TUNE")) sscanf(tune, "%d,%d,%d,%d,%d,%d", &blk, &stages, &minb, &chunk, &cap, &dbg);
-  DSKD_REQUIRE(chunk >= 1 && chunk <= 32 && cap >= 1, "dsgfd_kl: bad DSKD_KL_TUNE");
+  // tuning hook (tools/kl_perf.py): DSKD_KL_TUNE="channels_per_pass,rows_per_block,stages,ctas_per_sm,channels_per_cta,pool_records,dbg"
+  const bool pair_ok = a->C % 2 == 0 && (cell || (reinterpret_cast<uintptr_t>(a->d_rows) & 7u) == 0);
+  const bool grad = !cell && a->d_grad_rows != nullptr;
+  int nc = pair_ok ? 2 : 1, blk = grad ? kKlBlk : kKlBlkFwd, stages = kKlStages, minb = kKlMinCtas;
+  int chunk = a->N <= 4 ? kKlChunk / 2 : kKlChunk, cap = kKlPool, dbg = 0;
+  if (const char* tune = getenv("DSKD_KL_TUNE"))
+    sscanf(tune, "%d,%d,%d,%d,%d,%d,%d", &nc, &blk, &stages, &minb, &chunk, &cap, &dbg);
+  DSKD_REQUIRE((nc == 1 || (nc == 2 && pair_ok)) && chunk >= 1 && chunk <= 32 && chunk % nc == 0 && cap >= 1,
+               "dsgfd_kl: bad DSKD_KL_TUNE");
   prm.max_blocks = (max_h + blk - 1) / blk;
   prm.max_h = max_h;
   prm.chunk = std::min(a->C, chunk);
@@ -823,33 +1021,31 @@ extern "C" int dskd_dsgfd_kl_fwd_bwd(const DskdDsgfdKlArgs* a, void* stream) {
   }
   prm.block_start[a->num_levels] = blocks;
   prm.num_blocks = blocks;
-  const bool grad = !cell && a->d_grad_rows != nullptr;
-  const size_t smem = KlSmem(prm.max_blocks, blk, grad, cap).total;
+  const size_t smem = KlSmem(prm.max_blocks, blk, grad, cap, 1 + 2 * nc).total;
   DSKD_REQUIRE(smem <= 227 * 1024, "dsgfd_kl: H (%d) needs %zu bytes of shared memory", max_h, smem);
   bool launched = false;
-#define DSKD_KL_VARIANT(CELLV, GRADV, RV, NBV, MB)                                                              \
-  if (!launched && blk == RV && stages == NBV && minb == MB) {                                                  \
-    DSKD_CUDA_OK(cudaFuncSetAttribute(dsgfd_kl_stream_kernel<CELLV, GRADV, RV, NBV, MB>,                        \
+#define DSKD_KL_VARIANT(CELLV, GRADV, NCV, RV, NBV, MB)                                                         \
+  if (!launched && nc == NCV && blk == RV && stages == NBV && minb == MB) {                                     \
+    DSKD_CUDA_OK(cudaFuncSetAttribute(dsgfd_kl_stream_kernel<CELLV, GRADV, NCV, RV, NBV, MB>,                   \
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
-    dsgfd_kl_stream_kernel<CELLV, GRADV, RV, NBV, MB><<<blocks, 32 * kKlWarps, smem, st>>>(prm);                \
+    dsgfd_kl_stream_kernel<CELLV, GRADV, NCV, RV, NBV, MB><<<blocks, 32 * kKlWarps, smem, st>>>(prm);           \
     launched = true;                                                                                            \
   }
-#define DSKD_KL_VARIANTS(CELLV, GRADV)       \
-  DSKD_KL_VARIANT(CELLV, GRADV, 5, 2, 4)     \
-  DSKD_KL_VARIANT(CELLV, GRADV, 5, 2, 3)     \
-  DSKD_KL_VARIANT(CELLV, GRADV, 5, 3, 3)     \
-  DSKD_KL_VARIANT(CELLV, GRADV, 5, 3, 4)     \
-  DSKD_KL_VARIANT(CELLV, GRADV, 4, 3, 4)     \
-  DSKD_KL_VARIANT(CELLV, GRADV, 4, 3, 3)     \
-  DSKD_KL_VARIANT(CELLV, GRADV, 8, 2, 3)     \
-  DSKD_KL_VARIANT(CELLV, GRADV, 4, 2, 5)     \
-  DSKD_KL_VARIANT(CELLV, GRADV, 5, 2, 5)
+#define DSKD_KL_VARIANTS(CELLV, GRADV)          \
+  DSKD_KL_VARIANT(CELLV, GRADV, 2, 4, 1, 4)     \
+  DSKD_KL_VARIANT(CELLV, GRADV, 2, 5, 1, 4)     \
+  DSKD_KL_VARIANT(CELLV, GRADV, 2, 5, 1, 3)     \
+  DSKD_KL_VARIANT(CELLV, GRADV, 2, 4, 2, 3)     \
+  DSKD_KL_VARIANT(CELLV, GRADV, 2, 5, 2, 2)     \
+  DSKD_KL_VARIANT(CELLV, GRADV, 1, 4, 1, 4)     \
+  DSKD_KL_VARIANT(CELLV, GRADV, 1, 5, 1, 4)     \
+  DSKD_KL_VARIANT(CELLV, GRADV, 1, 5, 2, 4)
   if (cell) { DSKD_KL_VARIANTS(true, false) }
   else if (grad) { DSKD_KL_VARIANTS(false, true) }
   else { DSKD_KL_VARIANTS(false, false) }
 #undef DSKD_KL_VARIANTS
 #undef DSKD_KL_VARIANT
-  DSKD_REQUIRE(launched, "dsgfd_kl: no kernel variant for DSKD_KL_TUNE=%d,%d,%d", blk, stages, minb);
+  DSKD_REQUIRE(launched, "dsgfd_kl: no kernel variant for DSKD_KL_TUNE=%d,%d,%d,%d", nc, blk, stages, minb);
   DSKD_LAUNCH_OK("dsgfd_kl_stream_kernel");
   // the redo launch: a few loads per CTA when no block left anything behind
   const size_t redo_smem = (size_t)max_h * 32 * 4;

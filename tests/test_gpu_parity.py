@@ -309,15 +309,16 @@ def test_dsgfd_kl_logits_beyond_the_unshifted_range(scale):
         torch.testing.assert_close(got.detach().cpu().double(), ref64, rtol=LOSS_RTOL, atol=1e-12)
 
 
+@pytest.mark.parametrize('nc', [2, 1], ids=['pairs', 'single'])
 @pytest.mark.parametrize('pool', [64, 12, 2], ids=['shared_pools', 'one_warp', 'redo'])
-def test_dsgfd_kl_many_runs_per_tile(pool, monkeypatch):
+def test_dsgfd_kl_many_runs_per_tile(pool, nc, monkeypatch):
     """Crowded images: more runs of rows per column tile than one warp's record pool holds.  With a small pool
     (DSKD_KL_TUNE) the CTA first runs fewer warps with several pools each and finally leaves the tile to the redo launch;
     all three must give the reference's numbers."""
     cpu = synth.make_distill_inputs(num_images=2, num_prev=40, seed=15, channels=32, num_query=100, k_range=(30, 40), **{
         k: v for k, v in SMALL.items() if k not in ('k_range', 'num_query')})
     gpu = cpu.to(DEV)
-    monkeypatch.setenv('DSKD_KL_TUNE', f'5,2,4,16,{pool},0')
+    monkeypatch.setenv('DSKD_KL_TUNE', f'{nc},4,1,4,16,{pool},0')   # channels per pass, ..., pool records
     mod = dskd_b200.DSGFeatureDistillLoss(criterion='kl')
     feats, hs = gpu.clone_student()
     loss = mod(feats, gpu.teacher_feats, (hs, gpu.hs_teacher), gpu.assignments)

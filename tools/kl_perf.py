@@ -1,8 +1,9 @@
 """Time the DSG-FD KL-over-H streaming kernel alone (CUDA events around `dskd_dsgfd_kl_fwd_bwd`, inputs larger than L2).
 
-    python tools/kl_perf.py [--images 16] [--iters 20] [--tune "5,2,16;5,3,16;..."]
+    python tools/kl_perf.py [--images 16] [--iters 20] [--tune "2,5,2,2,16,256,0;1,5,2,4,16,256,0;..."]
 coverage 'synth' = the bench's synthetic boxes, 'full' = one box covering each image (every byte is read).
---tune runs the box-mask case once per "rows_per_block,ctas_per_sm,channels_per_cta" setting (DSKD_KL_TUNE).
+--tune runs the box-mask case once per "channels_per_pass,rows_per_block,stages,ctas_per_sm,channels_per_cta,pool,dbg"
+setting (DSKD_KL_TUNE).
 """
 import argparse
 import os

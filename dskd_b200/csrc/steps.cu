@@ -180,15 +180,3 @@ extern "C" int dskd_dsgfd_step(const DskdDsgfdStepArgs* a, void* stream) {
   if (fused_v1) return launch_v1_loss_final(a, acc, counter, st);  // NaN when teacher detections went unpaired
   return dskd_f64_to_f32(acc, a->d_loss, 1, 1.0f, stream);
 }
-
-extern "C" int dskd_bcdd_loss_and_grad(const float* d_proto, int32_t num_classes, int32_t C, int32_t L, int32_t reduction,
-                                       float loss_weight, float grad_scale, const int64_t* d_student_labels,
-                                       int32_t num_student_rows, const uint8_t* d_prev_mask, float* d_dist, float* d_loss,
-                                       float* d_grad_proto_student, float* d_grad_hs_student, void* stream) {
-  DSKD_REQUIRE((d_grad_hs_student == nullptr) || d_grad_proto_student, "dskd_bcdd_loss_and_grad: gradient needs the prototype workspace");
-  int rc = dskd_bcdd_distance_loss(d_proto, num_classes, C, L, reduction, loss_weight, grad_scale, d_dist, d_loss,
-                                   d_grad_hs_student ? d_grad_proto_student : nullptr, stream);
-  if (rc || d_grad_hs_student == nullptr) return rc;
-  return dskd_bcdd_scatter_grad(d_grad_proto_student, d_student_labels, num_student_rows, d_prev_mask, num_classes, C,
-                                d_grad_hs_student, stream);
-}

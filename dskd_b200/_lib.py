@@ -221,7 +221,9 @@ def guarded(fn):
 
 
 def stream_of(t: torch.Tensor):
-    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+    """Raw handle of the current stream of `t`'s device (what PyTorch ops would launch on)."""
+    idx = t.device.index
+    return C.c_void_p(torch._C._cuda_getCurrentRawStream(idx if idx is not None else torch.cuda.current_device()))
 
 
 def f32c(t: torch.Tensor):
@@ -231,8 +233,21 @@ def f32c(t: torch.Tensor):
     return t if t.is_contiguous() else t.contiguous()
 
 
+_levels_cache = {}
+
+
 def levels_struct(shapes):
-    """shapes: iterable of (H, W) -> (ctypes array of Level, cells_per_image)."""
+    """shapes: iterable of (H, W) -> (ctypes array of Level, cells_per_image); cached per shape tuple (read-only use)."""
+    key = tuple((int(h), int(w)) for h, w in shapes)
+    hit = _levels_cache.get(key)
+    if hit is None:
+        if len(_levels_cache) > 256:
+            _levels_cache.clear()
+        hit = _levels_cache[key] = _levels_struct(key)
+    return hit
+
+
+def _levels_struct(shapes):
     arr = (Level * MAX_LEVELS)()
     off = 0
     shapes = [(int(h), int(w)) for h, w in shapes]

@@ -9,6 +9,11 @@
 // candidate columns scanned in descending-index-initialised order, rows > cols solved on the
 // transpose) so the returned indices are identical to SciPy's; tests/test_lsap.py checks that on
 // thousands of random, tied and degenerate matrices.
+//
+// Attribution: the operation order and variable roles (u, v, path, col4row, row4col, SR, SC, remaining) follow
+// SciPy's `rectangular_lsap` (scipy/optimize/rectangular_lsap/rectangular_lsap.cpp, BSD 3-Clause License,
+// Copyright (c) 2019, PM Larsen; SciPy Developers) -- required for index-identical results; no SciPy source is
+// included or linked.
 #include <algorithm>
 #include <atomic>
 #include <cmath>

@@ -14,6 +14,7 @@ s_mem, t_mem = inp.memory()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 CASES = [('decode_v1', 'mse', 'neck'), ('decode_v1', 'kl', 'neck'), ('decode_v1', 'mse', 'memory'), ('decode_v2', 'mse', 'neck'),
          ('sg_out', 'mse', 'memory'), ('fg_only', 'mse', 'memory'), ('fg_bk', 'mse', 'memory'), ('sg_out', 'kl', 'neck'),
+         ('sg_out', 'kl', 'memory'), ('fg_only', 'kl', 'neck'), ('fg_only', 'kl', 'memory'), ('decode_v2', 'kl', 'neck'),
          ('qmem', 'mse', 'memory')]
 for mode, crit, src in CASES:
     mod = dskd_b200.build_loss(dict(type='DSGFeatureDistillLoss', criterion=crit, mask_mode=mode, feature_source=src))

@@ -312,9 +312,20 @@ def gen_assign():
     save('assign.npz', d)
 
 
+def gen_incremental_settings():
+    """BASELINE.json configs 3-4: the 50+30 and 60+20 settings (w_cls = 2.0 like the 40+40 config,
+    chaosuan_gfl_deformable_detr_50/60_r50_8x4_1x_qoqo_il.py) through the unmodified head, KL criterion."""
+    run_head('decode_v1', 'kl', seed=25, L=50, w_cls=2.0, tag='_l50', t_shift=3.3)
+    run_head('decode_v1', 'kl', seed=26, L=60, w_cls=2.0, tag='_l60', t_shift=3.4)
+
+
 if __name__ == '__main__':
+    import sys
     torch.manual_seed(0)
     torch.set_num_threads(4)
+    if sys.argv[1:] == ['incremental']:          # only the files added in round 2 (the others stay byte-identical)
+        gen_incremental_settings()
+        sys.exit(0)
     gen_losses()
     gen_boxes()
     gen_assign()
@@ -327,3 +338,4 @@ if __name__ == '__main__':
     run_head('sg_out', 'kl')
     run_head('sg_out', 'mse')
     run_head('fg_only', 'mse')
+    gen_incremental_settings()

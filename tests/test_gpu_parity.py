@@ -373,7 +373,7 @@ def test_dsgfd_cell_masks_need_no_queries():
         dskd_b200.DSGFeatureDistillLoss(criterion='mse')(gpu.student_feats, gpu.teacher_feats, None, gpu.assignments)
 
 
-@pytest.mark.parametrize('num_prev', [40, 70])
+@pytest.mark.parametrize('num_prev', [40, 50, 60, 70])
 @pytest.mark.parametrize('reduction', ['mean', 'sum'])
 def test_bcdd_vs_oracle(num_prev, reduction):
     cpu = synth.make_distill_inputs(num_images=4, num_prev=num_prev, seed=10, **SMALL)
@@ -435,6 +435,8 @@ GOLDEN_CASES = [('head_decode_v1_mse.npz', 'decode_v1', 'mse', 'neck'),
                 ('head_decode_v1_mse_n1.npz', 'decode_v1', 'mse', 'neck'),
                 ('head_decode_v1_kl.npz', 'decode_v1', 'kl', 'neck'),
                 ('head_decode_v1_kl_l70.npz', 'decode_v1', 'kl', 'neck'),
+                ('head_decode_v1_kl_l50.npz', 'decode_v1', 'kl', 'neck'),      # 50+30 and 60+20 settings (BASELINE configs 4)
+                ('head_decode_v1_kl_l60.npz', 'decode_v1', 'kl', 'neck'),
                 ('head_decode_v2_mse_n1.npz', 'decode_v2', 'mse', 'neck'),
                 ('head_sg_out_mse.npz', 'sg_out', 'mse', 'memory'),
                 ('head_sg_out_kl.npz', 'sg_out', 'kl', 'neck'),
@@ -497,7 +499,8 @@ def test_assignment_vs_reference_outputs():
             torch.testing.assert_close(cost[0, :, :cols[0]].cpu(), ref, rtol=2e-6, atol=2e-6)
 
 
-@pytest.mark.parametrize('name', ['head_decode_v1_mse.npz', 'head_decode_v1_kl_l70.npz'])
+@pytest.mark.parametrize('name', ['head_decode_v1_mse.npz', 'head_decode_v1_kl_l70.npz', 'head_decode_v1_kl_l50.npz',
+                                  'head_decode_v1_kl_l60.npz'])
 def test_batched_assignment_all_layers_vs_reference(name):
     inp, out = load_head_case(name)
     N, Q = inp.t('s_cls').shape[1:3]

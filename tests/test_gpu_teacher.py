@@ -47,7 +47,8 @@ def test_filter_scores_and_topk_order_vs_reference():
     assert torch.equal(info['pred_keepid'].cpu(), ref[2])
 
 
-@pytest.mark.parametrize('name', ['head_decode_v1_mse.npz', 'head_decode_v1_kl_l70.npz'])
+@pytest.mark.parametrize('name', ['head_decode_v1_mse.npz', 'head_decode_v1_kl_l70.npz', 'head_decode_v1_kl_l50.npz',
+                                  'head_decode_v1_kl_l60.npz'])
 def test_batch_vs_reference_head_case(name):
     inp, out = load_head_case(name)
     N = inp.t('t_cls').shape[1]

@@ -169,6 +169,7 @@ def _head_oracle(inp, out, mode, crit):
 
 HEAD_CASES = [('head_decode_v1_mse.npz', 'decode_v1', 'mse'), ('head_decode_v1_mse_n1.npz', 'decode_v1', 'mse'),
               ('head_decode_v1_kl.npz', 'decode_v1', 'kl'), ('head_decode_v1_kl_l70.npz', 'decode_v1', 'kl'),
+              ('head_decode_v1_kl_l50.npz', 'decode_v1', 'kl'), ('head_decode_v1_kl_l60.npz', 'decode_v1', 'kl'),
               ('head_decode_v2_mse.npz', 'decode_v2', 'mse'), ('head_decode_v2_mse_n1.npz', 'decode_v2', 'mse'),
               ('head_sg_out_mse.npz', 'sg_out', 'mse'), ('head_sg_out_kl.npz', 'sg_out', 'kl'),
               ('head_fg_only_mse.npz', 'fg_only', 'mse')]

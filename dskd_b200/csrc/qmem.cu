@@ -19,8 +19,12 @@
 //            fp32 accumulators in TMEM, kAccStages accumulator stages of kMaxNB columns
 //   warps 2-9 epilogue    : two sets of 4 warps alternating over the tiles; tcgen05.ld 32 lanes x 32 columns,
 //            online softmax in registers (thread = token), one coalesced 4-byte store per token
-// More than kMaxNB matched queries per image are split into query blocks handled by neighbouring CTAs (the
-// memory tile is then read from HBM once and from L2 nblk times) and merged by qmem_combine_kernel.
+// The producer and issuer loops are run by their whole warp with the TMA / tcgen05 instructions under elect.sync, so
+// descriptors and barrier addresses live in uniform registers and the UTCHMMAs of a k-slab issue back to back (see
+// elect_one()).
+// More than kMaxNB matched queries per image go to the CTA-pair kernel below (cta_group::2, up to 320 queries per pass
+// over the memory); beyond that the queries are split into blocks handled by neighbouring CTAs or CTA pairs (the memory
+// tile is then read from HBM once and from L2 nblk times) and merged by qmem_combine_kernel.
 // Measured dead ends (tools/qmem_perf.py, profiles/r1/qmem_notes.md): an L2 prefetch ahead of the ring raised DRAM
 // traffic by 60 % and cost 30 %; TMA multicast of the tile to the query blocks of a cluster was 10-20 % slower than
 // letting each CTA fetch it (the lock-step release of a stage by every CTA outweighs the saved L2 requests).
@@ -38,6 +42,7 @@ constexpr int kMaxAStages = 12;           // memory-tile ring: as many 16 KB sta
 constexpr int kAccStages = 3;             // 3 x 160 = 480 of the 512 TMEM columns
 constexpr int kTmemCols = 512;
 constexpr int kEpiSets = 2;               // epilogue warp sets (4 warps each) alternating over the tiles
+constexpr int kPairSlots = 4;             // accumulator slots of the CTA-pair kernel (512 columns / slot width, at most 4)
 constexpr int kQmemThreads = 64 + 128 * kEpiSets;
 constexpr uint32_t kAStageBytes = kTokTile * kSlabCh * 4;  // 16 KB
 
@@ -124,6 +129,22 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// One lane of a converged warp.  The tcgen05 / TMA issue loops are run by the WHOLE warp with the instructions under this
+// predicate: descriptors and barrier addresses then stay in uniform registers.  Issued from inside an `if (lane == 0)`
+// branch instead, every UTCHMMA / UTMALDG sits in an ELECT + R2UR.BROADCAST "waterfall" loop of ~16 dependent
+// instructions, and that loop -- not the tensor pipe -- sets the time of a k-step (measured: ~250 cycles per step).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- CTA-pair (cta_group::2) variants
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -139,7 +160,7 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) 
       "{\n\t"
       ".reg .b32 rem;\n\t"
       "mapa.shared::cluster.u32 rem, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [rem];\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [rem];\n\t"
       "}" ::"r"(bar), "r"(cta)
       : "memory");
 }
@@ -176,12 +197,6 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
 // One 32-column chunk of the online softmax of a token row (thread = token): v = raw scores from TMEM, c = confidences.
 __device__ __forceinline__ void softmax_chunk(uint32_t (&v)[32], const float4* __restrict__ c4p, int nc, float scale, float& mx,
                                               float& den0, float& den1, float& num0, float& num1) {
-  float c[32];
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {  // confidences of these 32 columns: warp-uniform 128-bit loads (L1 broadcast)
-    const float4 c4 = __ldg(c4p + q);
-    c[4 * q] = c4.x; c[4 * q + 1] = c4.y; c[4 * q + 2] = c4.z; c[4 * q + 3] = c4.w;
-  }
   if (nc < 32) {  // padded query rows are zero vectors (score 0): take them out of the softmax
 #pragma unroll
     for (int j = 0; j < 32; ++j)
@@ -198,13 +213,20 @@ __device__ __forceinline__ void softmax_chunk(uint32_t (&v)[32], const float4* _
   }
   const float nmx = -mx;
 #pragma unroll
-  for (int j = 0; j < 32; j += 2) {
-    const float e0 = ex2_approx(fmaf(__uint_as_float(v[j]), scale, nmx));
-    const float e1 = ex2_approx(fmaf(__uint_as_float(v[j + 1]), scale, nmx));
+  for (int q = 0; q < 8; ++q) {  // confidences of these 32 columns: warp-uniform 128-bit loads (L1 broadcast)
+    const float4 c4 = __ldg(c4p + q);
+    const float e0 = ex2_approx(fmaf(__uint_as_float(v[4 * q]), scale, nmx));
+    const float e1 = ex2_approx(fmaf(__uint_as_float(v[4 * q + 1]), scale, nmx));
+    const float e2 = ex2_approx(fmaf(__uint_as_float(v[4 * q + 2]), scale, nmx));
+    const float e3 = ex2_approx(fmaf(__uint_as_float(v[4 * q + 3]), scale, nmx));
     den0 += e0;
     den1 += e1;
-    num0 = fmaf(c[j], e0, num0);
-    num1 = fmaf(c[j + 1], e1, num1);
+    num0 = fmaf(c4.x, e0, num0);
+    num1 = fmaf(c4.y, e1, num1);
+    den0 += e2;
+    den1 += e3;
+    num0 = fmaf(c4.z, e2, num0);
+    num1 = fmaf(c4.w, e3, num1);
   }
 }
 
@@ -231,7 +253,7 @@ qmem_weight_kernel(const __grid_constant__ CUtensorMap tmap_mem, const __grid_co
   const uint32_t bar_full = bars, bar_empty = bars + 8 * kMaxAStages, bar_qfull = bars + 16 * kMaxAStages,
                  bar_qempty = bar_qfull + 8, bar_accfull = bar_qfull + 16, bar_accempty = bar_accfull + 8 * kAccStages,
                  tmem_slot = bar_accempty + 8 * kAccStages;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // warp index, provably uniform
 
   // work of this CTA: query block b of a contiguous range of (image, token tile) pairs
   const int b = blockIdx.x % p.nblk;
@@ -254,61 +276,68 @@ qmem_weight_kernel(const __grid_constant__ CUtensorMap tmap_mem, const __grid_co
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
 
   if (warp == 0) {
     // ================================================================ TMA producer
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0, qe_phase = 0;
-      int cur_img = -1;
-      for (long long t = t_begin; t < t_end; ++t) {
-        const int img = (int)(t / p.tiles_per_image), tt = (int)(t % p.tiles_per_image);
-        if (img != cur_img) {
-          if (cur_img >= 0) { mbar_wait(bar_qempty, qe_phase); qe_phase ^= 1; }  // MMAs on the old block are done
+    uint32_t stage = 0, phase = 0, qe_phase = 0;
+    int cur_img = -1;
+    for (long long t = t_begin; t < t_end; ++t) {
+      const int img = (int)(t / p.tiles_per_image), tt = (int)(t % p.tiles_per_image);
+      if (img != cur_img) {
+        if (cur_img >= 0) { mbar_wait(bar_qempty, qe_phase); qe_phase ^= 1; }  // MMAs on the old block are done
+        if (elect_one()) {
           mbar_arrive_expect_tx(bar_qfull, (uint32_t)num_slabs * q_slab_bytes);
           for (int ks = 0; ks < num_slabs; ++ks)
             tma_load_2d(&tmap_q, bar_qfull, smem_q + ks * q_slab_bytes, ks * kSlabCh, (img * p.nblk + b) * p.NB);
-          cur_img = img;
         }
-        for (int ks = 0; ks < num_slabs; ++ks) {
-          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+        __syncwarp();
+        cur_img = img;
+      }
+      for (int ks = 0; ks < num_slabs; ++ks) {
+        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+        if (elect_one()) {
           mbar_arrive_expect_tx(bar_full + 8 * stage, kAStageBytes);
           tma_load_3d(&tmap_mem, bar_full + 8 * stage, smem_a + stage * kAStageBytes, ks * kSlabCh, img, tt * kTokTile);
-          if (++stage == num_stages) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == num_stages) { stage = 0; phase ^= 1; }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
-    // ================================================================ MMA issuer
-    if (lane == 0) {
-      // instruction descriptor: D fp32, A/B tf32, both K-major, N = NB, M = 128
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.NB >> 3) << 17) | ((uint32_t)(kTokTile >> 4) << 24);
-      uint32_t stage = 0, phase = 0, qf_phase = 0, acc = 0, acc_phase = 0;
-      int cur_img = -1;
-      for (long long t = t_begin; t < t_end; ++t) {
-        const int img = (int)(t / p.tiles_per_image);
-        if (img != cur_img) { mbar_wait(bar_qfull, qf_phase); qf_phase ^= 1; cur_img = img; }
-        mbar_wait(bar_accempty + 8 * acc, acc_phase ^ 1);  // epilogue has drained this accumulator stage
+    // ================================================================ MMA issuer (whole warp, one elected lane issues)
+    // instruction descriptor: D fp32, A/B tf32, both K-major, N = NB, M = 128
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.NB >> 3) << 17) | ((uint32_t)(kTokTile >> 4) << 24);
+    uint32_t stage = 0, phase = 0, qf_phase = 0, acc = 0, acc_phase = 0;
+    int cur_img = -1;
+    for (long long t = t_begin; t < t_end; ++t) {
+      const int img = (int)(t / p.tiles_per_image);
+      if (img != cur_img) { mbar_wait(bar_qfull, qf_phase); qf_phase ^= 1; cur_img = img; }
+      mbar_wait(bar_accempty + 8 * acc, acc_phase ^ 1);  // epilogue has drained this accumulator stage
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * kMaxNB;
+      for (int ks = 0; ks < num_slabs; ++ks) {
+        mbar_wait(bar_full + 8 * stage, phase);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * kMaxNB;
-        for (int ks = 0; ks < num_slabs; ++ks) {
-          mbar_wait(bar_full + 8 * stage, phase);
-          tc_fence_after();
-          const uint64_t da = smem_desc_sw128(smem_a + stage * kAStageBytes);
-          const uint64_t db = smem_desc_sw128(smem_q + ks * q_slab_bytes);
+        const uint64_t da = smem_desc_sw128(smem_a + stage * kAStageBytes);
+        const uint64_t db = smem_desc_sw128(smem_q + ks * q_slab_bytes);
+        if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < kSlabCh / 8; ++kk)  // 8 tf32 = 32 bytes along K per instruction: +2 in 16-byte units
             umma_tf32(tmem_d, da + 2 * kk, db + 2 * kk, idesc, (ks | kk) ? 1u : 0u);
           umma_commit(bar_empty + 8 * stage);  // frees the memory-tile stage when those MMAs retire
-          if (++stage == num_stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(bar_accfull + 8 * acc);  // accumulator ready for the epilogue
-        const bool last_of_image = (t + 1 == t_end) || ((int)((t + 1) / p.tiles_per_image) != img);
-        if (last_of_image) umma_commit(bar_qempty);  // the resident query block may be replaced
-        if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+        __syncwarp();
+        if (++stage == num_stages) { stage = 0; phase ^= 1; }
       }
+      const bool last_of_image = (t + 1 == t_end) || ((int)((t + 1) / p.tiles_per_image) != img);
+      if (elect_one()) {
+        umma_commit(bar_accfull + 8 * acc);          // accumulator ready for the epilogue
+        if (last_of_image) umma_commit(bar_qempty);  // the resident query block may be replaced
+      }
+      __syncwarp();
+      if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
     }
-    __syncwarp();
   } else {
     // ================================================================ epilogue: thread = token (TMEM lane)
     // Two sets of four warps alternate over the tiles, so each SM sub-partition always has two epilogue warps to
@@ -366,8 +395,13 @@ qmem_weight_kernel(const __grid_constant__ CUtensorMap tmap_mem, const __grid_co
 // the query block resident (<= 160 rows), so up to 320 queries are contracted per byte of memory read -- twice the
 // arithmetic intensity of the single-CTA kernel at the same shared-memory footprint.  The leader CTA issues the MMAs
 // (two per k-step when NB > 256: N = n_lo and N = n_hi); completion is multicast to the barriers of both CTAs.
-// TMEM holds one accumulator stage of NB <= 320 columns per CTA; the two epilogue warp sets split its 32-column
-// chunks between them and write per-set partials that qmem_combine_kernel merges.
+//  * full barriers live in the leader and take ONE arrival, the leader's expect_tx of the bytes of both CTAs; the
+//    peer's TMA only completes bytes on it (a peer arrival per stage cost a cluster-scope release each: -25 % time);
+//  * TMEM: NS = 512 / n_lo rotating accumulator slots, one per MMA part, so the epilogue of a tile drains its slots
+//    while the MMAs of the next tile fill others; a part is read into registers first and its slot handed back before
+//    the softmax runs;
+//  * the two epilogue warp sets split the 32-column chunks of a part and merge their (max, den, num) through shared
+//    memory, so with one query block the CTA writes final weights and no combine kernel runs.
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQmemThreads, 1)
 qmem_weight_pair_kernel(const __grid_constant__ CUtensorMap tmap_mem, const __grid_constant__ CUtensorMap tmap_q,
                         const __grid_constant__ QmemParams p) {
@@ -381,11 +415,16 @@ qmem_weight_pair_kernel(const __grid_constant__ CUtensorMap tmap_mem, const __gr
   const int num_stages = p.stages;
   const uint32_t bars = smem_a + num_stages * kAStageBytes;
   const uint32_t bar_full = bars, bar_empty = bars + 8 * kMaxAStages, bar_qfull = bars + 16 * kMaxAStages,
-                 bar_qempty = bar_qfull + 8, bar_accfull = bar_qfull + 16, bar_accempty = bar_qfull + 24,
-                 tmem_slot = bar_qfull + 32;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+                 bar_qempty = bar_qfull + 8, bar_accfull = bar_qfull + 16, bar_accempty = bar_accfull + 8 * kPairSlots,
+                 tmem_slot = bar_accempty + 8 * kPairSlots, xch = bars + 512;  // xch: 2 x 3 x 128 floats
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // warp index, provably uniform
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
+  // accumulator slots: every MMA part of a tile (one for NB <= 256, two above) takes the next of NS slots of SW columns,
+  // so the epilogue of a tile drains its slots while the MMAs of the next tile fill others
+  const int parts = p.n_hi ? 2 : 1;
+  const int SW = p.n_lo;                                   // n_hi <= n_lo
+  const int NS = min(kPairSlots, kTmemCols / SW);          // 2 (SW <= 256), 3 (SW = 160), 4 (SW <= 128)
 
   // work of this pair: query block b of a contiguous range of (image, 256-token tile) pairs
   const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
@@ -394,11 +433,14 @@ qmem_weight_pair_kernel(const __grid_constant__ CUtensorMap tmap_mem, const __gr
   const long long t_begin = g * p.total_tiles / G, t_end = (g + 1) * p.total_tiles / G;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < num_stages; ++s) { mbar_init(bar_full + 8 * s, 2); mbar_init(bar_empty + 8 * s, 1); }
-    mbar_init(bar_qfull, 2);
+    // full barriers: ONE arrival (the leader's expect_tx of the bytes of both CTAs); the peer's loads only complete_tx
+    for (int s = 0; s < num_stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    mbar_init(bar_qfull, 1);
     mbar_init(bar_qempty, 1);
-    mbar_init(bar_accfull, 1);
-    mbar_init(bar_accempty, 2 * 4 * kEpiSets);  // one arrival per epilogue warp of both CTAs
+    for (int sl = 0; sl < kPairSlots; ++sl) {
+      mbar_init(bar_accfull + 8 * sl, 1);
+      mbar_init(bar_accempty + 8 * sl, 2 * 4 * kEpiSets);  // one arrival per epilogue warp of both CTAs
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -410,101 +452,161 @@ qmem_weight_pair_kernel(const __grid_constant__ CUtensorMap tmap_mem, const __gr
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
 
   if (warp == 0) {
     // ================================================================ TMA producer (both CTAs; signals the leader's barriers)
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0, qe_phase = 0;
-      int cur_img = -1;
-      for (long long t = t_begin; t < t_end; ++t) {
-        const int img = (int)(t / p.tiles_per_image), tt = (int)(t % p.tiles_per_image);
-        if (img != cur_img) {
-          if (cur_img >= 0) { mbar_wait(bar_qempty, qe_phase); qe_phase ^= 1; }
+    uint32_t stage = 0, phase = 0, qe_phase = 0;
+    int cur_img = -1;
+    for (long long t = t_begin; t < t_end; ++t) {
+      const int img = (int)(t / p.tiles_per_image), tt = (int)(t % p.tiles_per_image);
+      if (img != cur_img) {
+        if (cur_img >= 0) { mbar_wait(bar_qempty, qe_phase); qe_phase ^= 1; }
+        if (elect_one()) {
           if (leader) mbar_arrive_expect_tx(bar_qfull, 2u * (uint32_t)num_slabs * q_slab_bytes);
-          else mbar_arrive_cluster(bar_qfull, 0);
           for (int ks = 0; ks < num_slabs; ++ks)
             tma_load_2d_pair(&tmap_q, bar_qfull, smem_q + ks * q_slab_bytes, ks * kSlabCh,
                              ((img * p.nblk + b) * 2 + (int)rank) * half);
-          cur_img = img;
         }
-        for (int ks = 0; ks < num_slabs; ++ks) {
-          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+        __syncwarp();
+        cur_img = img;
+      }
+      for (int ks = 0; ks < num_slabs; ++ks) {
+        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+        if (elect_one()) {
           if (leader) mbar_arrive_expect_tx(bar_full + 8 * stage, 2u * kAStageBytes);
-          else mbar_arrive_cluster(bar_full + 8 * stage, 0);
           tma_load_3d_pair(&tmap_mem, bar_full + 8 * stage, smem_a + stage * kAStageBytes, ks * kSlabCh, img,
                            tt * 2 * kTokTile + (int)rank * kTokTile);
-          if (++stage == num_stages) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == num_stages) { stage = 0; phase ^= 1; }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
-    // ================================================================ MMA issuer (leader CTA only)
-    if (leader && lane == 0) {
+    // ================================================================ MMA issuer (leader CTA only; whole warp, one lane issues)
+    if (leader) {
       const uint32_t idesc_base = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(2 * kTokTile >> 4) << 24);
       const uint32_t idesc_lo = idesc_base | ((uint32_t)(p.n_lo >> 3) << 17);
       const uint32_t idesc_hi = idesc_base | ((uint32_t)(p.n_hi >> 3) << 17);
       const uint32_t hi_row_bytes = (uint32_t)(p.n_lo / 2) * 128u;  // rows of the second MMA inside each resident slab
-      uint32_t stage = 0, phase = 0, qf_phase = 0, acc_phase = 0;
+      uint32_t stage = 0, phase = 0, qf_phase = 0;
+      long long n = 0;  // ordinal of the MMA part: slot = n % NS, round = n / NS
       int cur_img = -1;
-      for (long long t = t_begin; t < t_end; ++t) {
+      for (long long t = t_begin; t < t_end; ++t, n += parts) {
         const int img = (int)(t / p.tiles_per_image);
         if (img != cur_img) { mbar_wait(bar_qfull, qf_phase); qf_phase ^= 1; cur_img = img; }
-        mbar_wait(bar_accempty, acc_phase ^ 1);
-        acc_phase ^= 1;
+        const uint32_t s_lo = (uint32_t)(n % NS), s_hi = (uint32_t)((n + 1) % NS);
+        mbar_wait(bar_accempty + 8 * s_lo, (uint32_t)((n / NS) & 1) ^ 1);       // the epilogues have drained the slot
+        if (parts == 2) mbar_wait(bar_accempty + 8 * s_hi, (uint32_t)(((n + 1) / NS) & 1) ^ 1);
         tc_fence_after();
+        const uint32_t d_lo = tmem_base + s_lo * SW, d_hi = tmem_base + s_hi * SW;
         for (int ks = 0; ks < num_slabs; ++ks) {
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
           const uint64_t da = smem_desc_sw128(smem_a + stage * kAStageBytes);
           const uint64_t db = smem_desc_sw128(smem_q + ks * q_slab_bytes);
           const uint64_t dbh = smem_desc_sw128(smem_q + ks * q_slab_bytes + hi_row_bytes);
+          if (elect_one()) {
+            if (parts == 2) {
 #pragma unroll
-          for (int kk = 0; kk < kSlabCh / 8; ++kk) {
-            umma_tf32_pair(tmem_base, da + 2 * kk, db + 2 * kk, idesc_lo, (ks | kk) ? 1u : 0u);
-            if (p.n_hi) umma_tf32_pair(tmem_base + p.n_lo, da + 2 * kk, dbh + 2 * kk, idesc_hi, (ks | kk) ? 1u : 0u);
+              for (int kk = 0; kk < kSlabCh / 8; ++kk) {
+                umma_tf32_pair(d_lo, da + 2 * kk, db + 2 * kk, idesc_lo, (ks | kk) ? 1u : 0u);
+                umma_tf32_pair(d_hi, da + 2 * kk, dbh + 2 * kk, idesc_hi, (ks | kk) ? 1u : 0u);
+              }
+            } else {
+#pragma unroll
+              for (int kk = 0; kk < kSlabCh / 8; ++kk) umma_tf32_pair(d_lo, da + 2 * kk, db + 2 * kk, idesc_lo, (ks | kk) ? 1u : 0u);
+            }
+            umma_commit_pair(bar_empty + 8 * stage);
           }
-          umma_commit_pair(bar_empty + 8 * stage);
+          __syncwarp();
           if (++stage == num_stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit_pair(bar_accfull);
         const bool last_of_image = (t + 1 == t_end) || ((int)((t + 1) / p.tiles_per_image) != img);
-        if (last_of_image) umma_commit_pair(bar_qempty);
+        if (elect_one()) {
+          umma_commit_pair(bar_accfull + 8 * s_lo);
+          if (parts == 2) umma_commit_pair(bar_accfull + 8 * s_hi);
+          if (last_of_image) umma_commit_pair(bar_qempty);
+        }
+        __syncwarp();
       }
-      if (t_end > t_begin) mbar_wait(bar_accempty, acc_phase ^ 1);  // the peer's last remote arrivals have landed
+      // the peer's last remote arrivals have landed before this CTA may leave
+      for (long long m = (n > NS ? n - NS : 0); m < n; ++m)
+        mbar_wait(bar_accempty + 8 * (uint32_t)(m % NS), (uint32_t)((m / NS) & 1));
     }
-    __syncwarp();
   } else {
     // ================================================================ epilogue (both CTAs): thread = token
+    // The two warp sets split the 32-column chunks of every part between them.  A part of up to 192 columns is first
+    // drained into registers (at most three chunks per set), its slot is handed back to the MMA issuer at once, and the
+    // softmax runs on the registers while the tensor cores already fill the slot again.  The sets then merge their
+    // (max, den, num) through shared memory, so one result per token leaves the CTA.
     const int sub = warp & 3;
     const int eset = (warp - 2) >> 2;
+    const bool single = p.nblk == 1;
     const float scale = p.score_scale;
-    uint32_t acc_phase = 0;
-    for (long long t = t_begin; t < t_end; ++t) {
+    const int row = sub * 32 + lane;
+    long long n = 0;
+    for (long long t = t_begin; t < t_end; ++t, n += parts) {
       const int img = (int)(t / p.tiles_per_image), tt = (int)(t % p.tiles_per_image);
       const int K = p.box_start[img + 1] - p.box_start[img];
       const int kv = max(0, min(p.NB, K - b * p.NB));
       const float4* __restrict__ cj = reinterpret_cast<const float4*>(p.cpad + ((long long)img * p.nblk + b) * p.NB);
-      mbar_wait(bar_accfull, acc_phase);
-      acc_phase ^= 1;
-      tc_fence_after();
       float mx = -1e30f, den0 = 0.f, den1 = 0.f, num0 = 0.f, num1 = 0.f;
-      const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16);
-      for (int c0 = 32 * eset; c0 < kv; c0 += 32 * kEpiSets) {  // the warp sets interleave over the 32-column chunks
-        uint32_t v[32];
-        tmem_ld32(taddr + c0, v);
-        tmem_ld_wait();
-        softmax_chunk(v, cj + (c0 >> 2), kv - c0, scale, mx, den0, den1, num0, num1);
+      for (int part = 0; part < parts; ++part) {
+        const uint32_t sl = (uint32_t)((n + part) % NS);
+        mbar_wait(bar_accfull + 8 * sl, (uint32_t)(((n + part) / NS) & 1));
+        tc_fence_after();
+        const int q0 = part * p.n_lo;                         // first query (= cpad column) of this part
+        const int kvp = max(0, min(part ? p.n_hi : p.n_lo, kv - q0));
+        const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + sl * SW;
+        const int ca = 32 * eset, cb = ca + 32 * kEpiSets, cc = cb + 32 * kEpiSets;
+        if (kvp <= 3 * 32 * kEpiSets) {
+          uint32_t va[32], vb[32], vc[32];
+          if (ca < kvp) tmem_ld32(taddr + ca, va);
+          if (cb < kvp) tmem_ld32(taddr + cb, vb);
+          if (cc < kvp) tmem_ld32(taddr + cc, vc);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(bar_accempty + 8 * sl, 0);
+          if (ca < kvp) softmax_chunk(va, cj + ((q0 + ca) >> 2), kvp - ca, scale, mx, den0, den1, num0, num1);
+          if (cb < kvp) softmax_chunk(vb, cj + ((q0 + cb) >> 2), kvp - cb, scale, mx, den0, den1, num0, num1);
+          if (cc < kvp) softmax_chunk(vc, cj + ((q0 + cc) >> 2), kvp - cc, scale, mx, den0, den1, num0, num1);
+        } else {
+          for (int c0 = ca; c0 < kvp; c0 += 32 * kEpiSets) {
+            uint32_t v[32];
+            tmem_ld32(taddr + c0, v);
+            tmem_ld_wait();
+            softmax_chunk(v, cj + ((q0 + c0) >> 2), kvp - c0, scale, mx, den0, den1, num0, num1);
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(bar_accempty + 8 * sl, 0);
+        }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(bar_accempty, 0);
-      const int tok = tt * 2 * kTokTile + (int)rank * kTokTile + sub * 32 + lane;
-      if (tok < p.S) {
-        float* o = p.part + (((long long)img * p.nblk + b) * kEpiSets + eset) * 3 * p.S + tok;
-        o[0] = mx;
-        o[p.S] = den0 + den1;
-        o[2 * (long long)p.S] = num0 + num1;
+      // merge the two warp sets: set 1 publishes, set 0 combines and stores (double-buffered by tile parity)
+      float den = den0 + den1, num = num0 + num1;
+      float* x = reinterpret_cast<float*>(smem_raw + (xch - smem_u32(smem_raw))) + (size_t)(t & 1) * 3 * kTokTile;
+      if (eset == 1) { x[row] = mx; x[kTokTile + row] = den; x[2 * kTokTile + row] = num; }
+      asm volatile("bar.sync 1, %0;" ::"n"(128 * kEpiSets) : "memory");
+      if (eset == 0) {
+        const float mo = x[row], dn = x[kTokTile + row], nu = x[2 * kTokTile + row];
+        // with one query block the null logit 0 joins here and the weight is final; otherwise qmem_combine_kernel adds it
+        const float m = fmaxf(fmaxf(mx, mo), single ? 0.f : -1e30f);
+        const float ra = ex2_approx(mx - m), rb = ex2_approx(mo - m);
+        den = fmaf(den, ra, dn * rb) + (single ? ex2_approx(-m) : 0.f);
+        num = fmaf(num, ra, nu * rb);
+        const int tok = tt * 2 * kTokTile + (int)rank * kTokTile + row;
+        if (tok < p.S) {
+          if (single) {
+            p.weight[(long long)img * p.S + tok] = sqrtf(__fdividef(num, den));
+          } else {
+            float* o = p.part + ((long long)img * p.nblk + b) * 3 * p.S + tok;
+            o[0] = m;
+            o[p.S] = den;
+            o[2 * (long long)p.S] = num;
+          }
+        }
       }
     }
   }
@@ -522,26 +624,27 @@ qmem_weight_pair_kernel(const __grid_constant__ CUtensorMap tmap_mem, const __gr
 // row j - n/2 of CTA 1 otherwise -- the rows are laid out so that the accumulator columns are the queries in order.
 __global__ void __launch_bounds__(256) qmem_gather_kernel(const float* __restrict__ hs_teacher, const int64_t* __restrict__ keepid,
                                                           const float* __restrict__ scores, const int* __restrict__ box_start,
-                                                          int nblk, int NB, int pair, int n_lo, int n_hi, int C,
+                                                          int nblk, int NB, int pair, int n_lo, int n_hi, int C, int total_rows,
                                                           int64_t num_rows, float* __restrict__ qpad, float* __restrict__ cpad) {
-  const int r = blockIdx.x;  // (img * nblk + b) * NB + rr
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;  // warp = row (img * nblk + b) * NB + rr
+  if (r >= total_rows) return;
   const int rr = r % NB, ib = r / NB, b = ib % nblk, img = ib / nblk;
   int col = rr;
   if (pair) {
     const int half = NB / 2, cta = rr / half, lr = rr % half, hl = n_lo / 2;
     col = lr < hl ? cta * hl + lr : n_lo + cta * (n_hi / 2) + (lr - hl);
   }
-  const int q = b * NB + col, K = box_start[img + 1] - box_start[img];
+  const int first = __ldg(box_start + img), q = b * NB + col, K = __ldg(box_start + img + 1) - first;
   const bool valid = q < K;
   int64_t src = 0;
   if (valid) {
-    src = keepid[box_start[img] + q];
+    src = __ldg(keepid + first + q);
     if (src < 0 || src >= num_rows) src = 0;  // defensive: never read outside hs_teacher
   }
   const float4* s4 = reinterpret_cast<const float4*>(hs_teacher + src * C);
   float4* d4 = reinterpret_cast<float4*>(qpad + (int64_t)r * C);
-  for (int c = threadIdx.x; c < C / 4; c += blockDim.x) d4[c] = valid ? __ldg(s4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-  if (threadIdx.x == 0) cpad[(int64_t)ib * NB + col] = valid ? (scores ? scores[box_start[img] + q] : 1.f) : 0.f;
+  for (int c = lane; c < C / 4; c += 32) d4[c] = valid ? __ldg(s4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  if (lane == 0) cpad[(int64_t)ib * NB + col] = valid ? (scores ? __ldg(scores + first + q) : 1.f) : 0.f;
 }
 
 // Merge the per-block (max, den, num) partials and add the null logit once.
@@ -585,18 +688,18 @@ struct QmemPlan {
   int part_blocks;           // partial (max, den, num) planes per image; 1 = the kernel writes the weights itself
   int64_t qpad, cpad, part, total;
   QmemPlan(int N, int64_t S, int C, int kmax) {
-    const char* mode = getenv("DSKD_QMEM_MODE");  // "1" / "2": force the single-CTA / CTA-pair kernel (tests, tools)
-    // Measured on B200 (tools/qmem_perf.py, profiles/r1/qmem_sweep.txt): the pair kernel is correct but slower than two
-    // single-CTA query blocks sharing the tile through L2 -- with 152 resident rows only 4 ring stages fit, and its
-    // stage hand-off crosses the CTA pair, so it is latency-bound.  It stays opt-in.
-    pair = mode != nullptr && mode[0] == '2';
+    // More than kMaxNB queries per image: the CTA-pair kernel reads the memory once for up to 320 queries where the
+    // single-CTA kernel reads it once per 160 (B200, 16 images: 103 vs 131 us at 300 queries, 242 vs 301 us at 900;
+    // profiles/r2/qmem_sweep.txt).  DSKD_QMEM_MODE = "1" / "2" forces one kernel (tests, tools).
+    const char* mode = getenv("DSKD_QMEM_MODE");
+    pair = mode != nullptr && (mode[0] == '1' || mode[0] == '2') ? mode[0] == '2' : kmax > kMaxNB;
     const int cap = pair ? 2 * kMaxNB : kMaxNB;
     nblk = std::max(1, (kmax + cap - 1) / cap);
     const int per = (std::max(kmax, 1) + nblk - 1) / nblk;
     NB = std::max((per + 15) / 16 * 16, pair ? 32 : 16);
     n_lo = NB; n_hi = 0;
     if (pair && NB > 256) { n_lo = kMaxNB; n_hi = NB - kMaxNB; }
-    part_blocks = pair ? nblk * kEpiSets : nblk;
+    part_blocks = nblk;
     int64_t off = 0;
     auto up = [](int64_t x) { return (x + 255) / 256 * 256; };
     qpad = off; off += up((int64_t)N * nblk * NB * C * 4);
@@ -639,8 +742,9 @@ extern "C" int dskd_qmem_cell_weights(const DskdQmemArgs* a, void* stream) {
   float* cpad = reinterpret_cast<float*>(base + plan.cpad);
   float* part = plan.part_blocks > 1 ? reinterpret_cast<float*>(base + plan.part) : nullptr;
   const int rows = a->N * plan.nblk * plan.NB;
-  qmem_gather_kernel<<<rows, 64, 0, st>>>(a->d_hs_teacher, a->d_keepid, a->d_scores, a->d_box_start, plan.nblk, plan.NB, plan.pair ? 1 : 0,
-                                          plan.n_lo, plan.n_hi, a->C, a->num_query_rows, qpad, cpad);
+  qmem_gather_kernel<<<(unsigned)ceil_div(rows, 8), 256, 0, st>>>(a->d_hs_teacher, a->d_keepid, a->d_scores, a->d_box_start, plan.nblk,
+                                                                  plan.NB, plan.pair ? 1 : 0, plan.n_lo, plan.n_hi, a->C, rows,
+                                                                  a->num_query_rows, qpad, cpad);
   DSKD_LAUNCH_OK("qmem_gather_kernel");
 
   EncodeTiledFn encode = encode_tiled_fn();
@@ -690,7 +794,8 @@ extern "C" int dskd_qmem_cell_weights(const DskdQmemArgs* a, void* stream) {
   p.n_lo = plan.n_lo;
   p.n_hi = plan.n_hi;
   const int resident_rows = plan.pair ? plan.NB / 2 : plan.NB;
-  const size_t kSmemMax = 227 * 1024, fixed = 1024 + (size_t)resident_rows * a->C * 4 + 512;
+  const size_t kSmemMax = 227 * 1024;  // 1024 alignment slack, resident queries, 512 barriers (+ the pair kernel's merge buffer)
+  const size_t fixed = 1024 + (size_t)resident_rows * a->C * 4 + 512 + (plan.pair ? 2 * 3 * kTokTile * sizeof(float) : 0);
   int stages = (int)std::min<size_t>(kMaxAStages, (kSmemMax - fixed) / kAStageBytes);
   DSKD_REQUIRE(stages >= 2, "dskd_qmem_cell_weights: not enough shared memory for the memory-tile ring");
   p.stages = stages;

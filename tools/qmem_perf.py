@@ -3,7 +3,7 @@
 The call (gather + contraction + combine) is captured once in a CUDA graph and replayed, so the time is device
 time without host gaps; a 256 MB write between replays flushes the 126 MB L2.
     python tools/qmem_perf.py                 # sweep (BASELINE.json configs[4]: queries 100-900, batch 2/16)
-    python tools/qmem_perf.py one N K [mode]  # a single point; mode 1 = single-CTA kernel, 2 = CTA-pair kernel
+    python tools/qmem_perf.py one N K [mode [S]]  # a single point; mode 1 = single-CTA kernel, 2 = CTA-pair kernel
 """
 import os
 import sys
@@ -56,7 +56,8 @@ def bench(N, K, S=22223, C=256, Q=None, iters=15, mode=None):
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == 'one':
-        bench(int(sys.argv[2]), int(sys.argv[3]), mode=sys.argv[4] if len(sys.argv) > 4 else None)
+        bench(int(sys.argv[2]), int(sys.argv[3]), mode=sys.argv[4] if len(sys.argv) > 4 else None,
+              S=int(sys.argv[5]) if len(sys.argv) > 5 else 22223)
         sys.exit(0)
     for N in (2, 16):
         for K in (100, 160, 300, 600, 900):

@@ -258,7 +258,9 @@ qmem_weight_kernel(const __grid_constant__ CUtensorMap tmap_mem, const __grid_co
   // work of this CTA: query block b of a contiguous range of (image, token tile) pairs
   const int b = blockIdx.x % p.nblk;
   const long long g = blockIdx.x / p.nblk, G = gridDim.x / p.nblk;
-  const long long t_begin = g * p.total_tiles / G, t_end = (g + 1) * p.total_tiles / G;
+  const int t_begin = (int)(g * p.total_tiles / G), t_end = (int)((g + 1) * p.total_tiles / G);
+  // the loops below walk (image, tile in image) incrementally: no division on the issue paths
+  const int img_begin = t_begin / p.tiles_per_image, tt_begin = t_begin % p.tiles_per_image;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < num_stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
@@ -282,8 +284,8 @@ qmem_weight_kernel(const __grid_constant__ CUtensorMap tmap_mem, const __grid_co
     // ================================================================ TMA producer
     uint32_t stage = 0, phase = 0, qe_phase = 0;
     int cur_img = -1;
-    for (long long t = t_begin; t < t_end; ++t) {
-      const int img = (int)(t / p.tiles_per_image), tt = (int)(t % p.tiles_per_image);
+    int img = img_begin, tt = tt_begin;
+    for (int t = t_begin; t < t_end; ++t) {
       if (img != cur_img) {
         if (cur_img >= 0) { mbar_wait(bar_qempty, qe_phase); qe_phase ^= 1; }  // MMAs on the old block are done
         if (elect_one()) {
@@ -303,6 +305,7 @@ qmem_weight_kernel(const __grid_constant__ CUtensorMap tmap_mem, const __grid_co
         __syncwarp();
         if (++stage == num_stages) { stage = 0; phase ^= 1; }
       }
+      if (++tt == p.tiles_per_image) { tt = 0; ++img; }
     }
   } else if (warp == 1) {
     // ================================================================ MMA issuer (whole warp, one elected lane issues)
@@ -310,8 +313,8 @@ qmem_weight_kernel(const __grid_constant__ CUtensorMap tmap_mem, const __grid_co
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.NB >> 3) << 17) | ((uint32_t)(kTokTile >> 4) << 24);
     uint32_t stage = 0, phase = 0, qf_phase = 0, acc = 0, acc_phase = 0;
     int cur_img = -1;
-    for (long long t = t_begin; t < t_end; ++t) {
-      const int img = (int)(t / p.tiles_per_image);
+    int img = img_begin, tt = tt_begin;
+    for (int t = t_begin; t < t_end; ++t) {
       if (img != cur_img) { mbar_wait(bar_qfull, qf_phase); qf_phase ^= 1; cur_img = img; }
       mbar_wait(bar_accempty + 8 * acc, acc_phase ^ 1);  // epilogue has drained this accumulator stage
       tc_fence_after();
@@ -330,13 +333,14 @@ qmem_weight_kernel(const __grid_constant__ CUtensorMap tmap_mem, const __grid_co
         __syncwarp();
         if (++stage == num_stages) { stage = 0; phase ^= 1; }
       }
-      const bool last_of_image = (t + 1 == t_end) || ((int)((t + 1) / p.tiles_per_image) != img);
+      const bool last_of_image = (t + 1 == t_end) || (tt + 1 == p.tiles_per_image);
       if (elect_one()) {
         umma_commit(bar_accfull + 8 * acc);          // accumulator ready for the epilogue
         if (last_of_image) umma_commit(bar_qempty);  // the resident query block may be replaced
       }
       __syncwarp();
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+      if (++tt == p.tiles_per_image) { tt = 0; ++img; }
     }
   } else {
     // ================================================================ epilogue: thread = token (TMEM lane)
@@ -346,10 +350,11 @@ qmem_weight_kernel(const __grid_constant__ CUtensorMap tmap_mem, const __grid_co
     const int eset = (warp - 2) >> 2;
     const bool single = p.nblk == 1;
     const float scale = p.score_scale;
-    long long n = eset;                     // ordinal of the tile inside this CTA: fixes the accumulator stage
-    for (long long t = t_begin + eset; t < t_end; t += kEpiSets, n += kEpiSets) {
-      const uint32_t acc = (uint32_t)(n % kAccStages), acc_phase = (uint32_t)((n / kAccStages) & 1);
-      const int img = (int)(t / p.tiles_per_image), tt = (int)(t % p.tiles_per_image);
+    // this set takes every kEpiSets-th tile; (acc, acc_phase) and (img, tt) follow the tile ordinal incrementally
+    uint32_t acc = (uint32_t)eset % kAccStages, acc_phase = (uint32_t)eset / kAccStages;
+    int img = img_begin, tt = tt_begin + eset;
+    while (tt >= p.tiles_per_image) { tt -= p.tiles_per_image; ++img; }
+    for (int t = t_begin + eset; t < t_end; t += kEpiSets) {
       const int K = p.box_start[img + 1] - p.box_start[img];
       const int kv = max(0, min(p.NB, K - b * p.NB));  // valid query columns of this block
       const float4* __restrict__ cj = reinterpret_cast<const float4*>(p.cpad + ((long long)img * p.nblk + b) * p.NB);
@@ -379,6 +384,10 @@ qmem_weight_kernel(const __grid_constant__ CUtensorMap tmap_mem, const __grid_co
           o[2 * (long long)p.S] = num;
         }
       }
+      acc += kEpiSets;
+      if (acc >= kAccStages) { acc -= kAccStages; acc_phase ^= 1; }
+      tt += kEpiSets;
+      while (tt >= p.tiles_per_image) { tt -= p.tiles_per_image; ++img; }
     }
   }
   tc_fence_before();
@@ -430,7 +439,8 @@ qmem_weight_pair_kernel(const __grid_constant__ CUtensorMap tmap_mem, const __gr
   const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
   const int b = pair_id % p.nblk;
   const long long g = pair_id / p.nblk, G = num_pairs / p.nblk;
-  const long long t_begin = g * p.total_tiles / G, t_end = (g + 1) * p.total_tiles / G;
+  const int t_begin = (int)(g * p.total_tiles / G), t_end = (int)((g + 1) * p.total_tiles / G);
+  const int img_begin = t_begin / p.tiles_per_image, tt_begin = t_begin % p.tiles_per_image;
 
   if (threadIdx.x == 0) {
     // full barriers: ONE arrival (the leader's expect_tx of the bytes of both CTAs); the peer's loads only complete_tx
@@ -458,8 +468,8 @@ qmem_weight_pair_kernel(const __grid_constant__ CUtensorMap tmap_mem, const __gr
     // ================================================================ TMA producer (both CTAs; signals the leader's barriers)
     uint32_t stage = 0, phase = 0, qe_phase = 0;
     int cur_img = -1;
-    for (long long t = t_begin; t < t_end; ++t) {
-      const int img = (int)(t / p.tiles_per_image), tt = (int)(t % p.tiles_per_image);
+    int img = img_begin, tt = tt_begin;
+    for (int t = t_begin; t < t_end; ++t) {
       if (img != cur_img) {
         if (cur_img >= 0) { mbar_wait(bar_qempty, qe_phase); qe_phase ^= 1; }
         if (elect_one()) {
@@ -481,6 +491,7 @@ qmem_weight_pair_kernel(const __grid_constant__ CUtensorMap tmap_mem, const __gr
         __syncwarp();
         if (++stage == num_stages) { stage = 0; phase ^= 1; }
       }
+      if (++tt == p.tiles_per_image) { tt = 0; ++img; }
     }
   } else if (warp == 1) {
     // ================================================================ MMA issuer (leader CTA only; whole warp, one lane issues)
@@ -490,14 +501,19 @@ qmem_weight_pair_kernel(const __grid_constant__ CUtensorMap tmap_mem, const __gr
       const uint32_t idesc_hi = idesc_base | ((uint32_t)(p.n_hi >> 3) << 17);
       const uint32_t hi_row_bytes = (uint32_t)(p.n_lo / 2) * 128u;  // rows of the second MMA inside each resident slab
       uint32_t stage = 0, phase = 0, qf_phase = 0;
-      long long n = 0;  // ordinal of the MMA part: slot = n % NS, round = n / NS
-      int cur_img = -1;
-      for (long long t = t_begin; t < t_end; ++t, n += parts) {
-        const int img = (int)(t / p.tiles_per_image);
+      // MMA parts take the accumulator slots round robin: (slot, round parity) of the next part
+      uint32_t slot = 0, round = 0;
+      int cur_img = -1, img = img_begin, tt = tt_begin;
+      for (int t = t_begin; t < t_end; ++t) {
         if (img != cur_img) { mbar_wait(bar_qfull, qf_phase); qf_phase ^= 1; cur_img = img; }
-        const uint32_t s_lo = (uint32_t)(n % NS), s_hi = (uint32_t)((n + 1) % NS);
-        mbar_wait(bar_accempty + 8 * s_lo, (uint32_t)((n / NS) & 1) ^ 1);       // the epilogues have drained the slot
-        if (parts == 2) mbar_wait(bar_accempty + 8 * s_hi, (uint32_t)(((n + 1) / NS) & 1) ^ 1);
+        const uint32_t s_lo = slot;
+        mbar_wait(bar_accempty + 8 * s_lo, round ^ 1);       // the epilogues have drained the slot
+        if (++slot == (uint32_t)NS) { slot = 0; round ^= 1; }
+        const uint32_t s_hi = slot;
+        if (parts == 2) {
+          mbar_wait(bar_accempty + 8 * s_hi, round ^ 1);
+          if (++slot == (uint32_t)NS) { slot = 0; round ^= 1; }
+        }
         tc_fence_after();
         const uint32_t d_lo = tmem_base + s_lo * SW, d_hi = tmem_base + s_hi * SW;
         for (int ks = 0; ks < num_slabs; ++ks) {
@@ -522,17 +538,22 @@ qmem_weight_pair_kernel(const __grid_constant__ CUtensorMap tmap_mem, const __gr
           __syncwarp();
           if (++stage == num_stages) { stage = 0; phase ^= 1; }
         }
-        const bool last_of_image = (t + 1 == t_end) || ((int)((t + 1) / p.tiles_per_image) != img);
+        const bool last_of_image = (t + 1 == t_end) || (tt + 1 == p.tiles_per_image);
         if (elect_one()) {
           umma_commit_pair(bar_accfull + 8 * s_lo);
           if (parts == 2) umma_commit_pair(bar_accfull + 8 * s_hi);
           if (last_of_image) umma_commit_pair(bar_qempty);
         }
         __syncwarp();
+        if (++tt == p.tiles_per_image) { tt = 0; ++img; }
       }
-      // the peer's last remote arrivals have landed before this CTA may leave
-      for (long long m = (n > NS ? n - NS : 0); m < n; ++m)
-        mbar_wait(bar_accempty + 8 * (uint32_t)(m % NS), (uint32_t)((m / NS) & 1));
+      // the peer's last remote arrivals (on the last min(parts issued, NS) slots) have landed before this CTA may leave
+      const int issued = (t_end - t_begin) * parts;
+      for (int k = 0; k < min(issued, NS); ++k) {
+        if (slot == 0) { slot = (uint32_t)NS; round ^= 1; }
+        --slot;
+        mbar_wait(bar_accempty + 8 * slot, round);
+      }
     }
   } else {
     // ================================================================ epilogue (both CTAs): thread = token
@@ -545,16 +566,17 @@ qmem_weight_pair_kernel(const __grid_constant__ CUtensorMap tmap_mem, const __gr
     const bool single = p.nblk == 1;
     const float scale = p.score_scale;
     const int row = sub * 32 + lane;
-    long long n = 0;
-    for (long long t = t_begin; t < t_end; ++t, n += parts) {
-      const int img = (int)(t / p.tiles_per_image), tt = (int)(t % p.tiles_per_image);
+    uint32_t slot = 0, round = 0;  // accumulator slot and round parity of the next MMA part, as in the issuer
+    int img = img_begin, tt = tt_begin;
+    for (int t = t_begin; t < t_end; ++t) {
       const int K = p.box_start[img + 1] - p.box_start[img];
       const int kv = max(0, min(p.NB, K - b * p.NB));
       const float4* __restrict__ cj = reinterpret_cast<const float4*>(p.cpad + ((long long)img * p.nblk + b) * p.NB);
       float mx = -1e30f, den0 = 0.f, den1 = 0.f, num0 = 0.f, num1 = 0.f;
       for (int part = 0; part < parts; ++part) {
-        const uint32_t sl = (uint32_t)((n + part) % NS);
-        mbar_wait(bar_accfull + 8 * sl, (uint32_t)(((n + part) / NS) & 1));
+        const uint32_t sl = slot;
+        mbar_wait(bar_accfull + 8 * sl, round);
+        if (++slot == (uint32_t)NS) { slot = 0; round ^= 1; }
         tc_fence_after();
         const int q0 = part * p.n_lo;                         // first query (= cpad column) of this part
         const int kvp = max(0, min(part ? p.n_hi : p.n_lo, kv - q0));
@@ -608,6 +630,7 @@ qmem_weight_pair_kernel(const __grid_constant__ CUtensorMap tmap_mem, const __gr
           }
         }
       }
+      if (++tt == p.tiles_per_image) { tt = 0; ++img; }
     }
   }
   tc_fence_before();
@@ -786,6 +809,7 @@ extern "C" int dskd_qmem_cell_weights(const DskdQmemArgs* a, void* stream) {
   const int tile_tokens = plan.pair ? 2 * kTokTile : kTokTile;
   p.tiles_per_image = (int)ceil_div(a->S, tile_tokens);
   p.total_tiles = (long long)p.tiles_per_image * a->N;
+  DSKD_REQUIRE(p.total_tiles < (1ll << 31), "dskd_qmem_cell_weights: too many token tiles (%lld)", p.total_tiles);
   p.score_scale = 1.4426950408889634f / (sqrtf((float)a->C) * a->temperature);
   p.box_start = a->d_box_start;
   p.cpad = cpad;

@@ -99,6 +99,7 @@ def algorithmic_bytes(criterion, tokens, channels, images):
 
 
 STREAM_KERNEL = {'mse': 'dsgfd_mse_nchw_kernel', 'kl': 'dsgfd_kl_stream_kernel'}
+CUBLAS_TF32_TFLOPS = 720.1  # torch fp32 matmul with allow_tf32, 8192^3, B200 (profiles/r2/cublas_tf32_bf16_peak.txt)
 
 
 def time_path_feeders(args, dev, N):
@@ -175,15 +176,21 @@ def time_contraction(args, dev, N, world, dist):
     flop = 2.0 * K * C * S * N
     _, bf16_peak, src = peaks()
     achieved = flop / (ms * 1e-3) / 1e12
-    traffic_rec = recorded_traffic('qmem_weight_kernel', N)
-    return {'bound': 'tensor', 'kernel': 'qmem_weight_kernel (tcgen05.mma kind::tf32, TMA-fed, TMEM accumulators)',
+    kernel = 'qmem_weight_pair_kernel' if K > 160 else 'qmem_weight_kernel'  # QmemPlan: CTA pairs above 160 queries
+    traffic_rec = recorded_traffic(kernel, N)
+    if traffic_rec and traffic_rec.get('queries') != K:
+        traffic_rec = None
+    return {'bound': 'tensor', 'kernel': f'{kernel} (tcgen05.mma kind::tf32' + (' cta_group::2' if K > 160 else '') +
+                                         ', TMA-fed, TMEM accumulators)',
             'achieved': achieved, 'peak': bf16_peak, 'unit': 'TFLOP/s', 'frac': achieved / bf16_peak,
             'frac_of_tf32_rate': achieved / (bf16_peak / 2),
-            'peak_source': f'{src}: cuBLAS bf16 dense; kind::tf32 issues at half that rate',
+            'frac_of_cublas_tf32': achieved / CUBLAS_TF32_TFLOPS,
+            'peak_source': f'{src}: cuBLAS bf16 dense; kind::tf32 issues at half that rate; cuBLAS fp32-as-tf32 8192^3 '
+                           f'GEMM measured {CUBLAS_TF32_TFLOPS} TFLOP/s on this pool (profiles/r2/cublas_tf32_bf16_peak.txt)',
             'flop_per_launch': flop, 'call_ms': ms, 'queries': K, 'tokens': S, 'channels': C, 'images': N,
             'images_per_s': world * N / (ms * 1e-3), 'traffic': (traffic_rec or {}).get('dram_bytes_per_launch'),
             'traffic_source': (traffic_rec or {}).get('source'),
-            'timing': 'gather + contraction + combine, CUDA-graph replay, L2 flushed between replays, median'}
+            'timing': 'gather + contraction (+ combine above 320 queries), CUDA-graph replay, L2 flushed between replays, median'}
 
 
 class ClockSampler:

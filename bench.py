@@ -193,6 +193,25 @@ def time_contraction(args, dev, N, world, dist):
             'timing': 'gather + contraction (+ combine above 320 queries), CUDA-graph replay, L2 flushed between replays, median'}
 
 
+def gpu_numa_cpus(local_rank):
+    """(numa node, cpu set) of the host socket this GPU hangs off, from sysfs; (None, None) when the box does not say."""
+    try:
+        prop = torch.cuda.get_device_properties(local_rank)
+        bus = f'{prop.pci_domain_id:04x}:{prop.pci_bus_id:02x}:{prop.pci_device_id:02x}.0'
+        with open(f'/sys/bus/pci/devices/{bus}/numa_node') as f:
+            node = int(f.read())
+        if node < 0:
+            return None, None
+        cpus = set()
+        with open(f'/sys/devices/system/node/node{node}/cpulist') as f:
+            for part in f.read().strip().split(','):
+                lo, _, hi = part.partition('-')
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        return node, cpus
+    except (OSError, ValueError, AttributeError):
+        return None, None
+
+
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
 
@@ -580,18 +599,27 @@ def main():
             graph_err = f'{type(exc).__name__}: {exc}'
             graph_ms = None
     clocks = sampler.stop() if rank == 0 else None
+    # the eager figure once more without `nvidia-smi -lms` polling the driver next to the launches (it lengthens them)
+    eager_quiet_ms = sb.run_eager(args.steps, args.warmup)[0]
     elapsed_ms = graph_ms if graph_ms is not None else eager_ms
-    elapsed_ms, eager_ms = sb.max_over_ranks(elapsed_ms, eager_ms)
+    elapsed_ms, eager_ms, eager_quiet_ms = sb.max_over_ranks(elapsed_ms, eager_ms, eager_quiet_ms)
     kernel_ms = statistics.mean(kernel_times) if kernel_times else float('nan')
 
     # ---------------- end-to-end through the module call with HOST buffers (`e2e`)
     e2e = None
     if not args.no_e2e:
+        # the pinned staging buffers go on the host socket this GPU hangs off (first touch under that CPU affinity): at
+        # 4-8 ranks the copies otherwise cross the socket interconnect; the affinity is restored right after
+        affinity0 = os.sched_getaffinity(0)
+        numa_node, numa_cpus = gpu_numa_cpus(local_rank)
+        if numa_cpus and (affinity0 & numa_cpus):
+            os.sched_setaffinity(0, affinity0 & numa_cpus)
         host_s = [torch.empty(f.shape, dtype=f.dtype, pin_memory=True).copy_(f.detach()) for f in s_feats]
         host_t = [torch.empty(f.shape, dtype=f.dtype, pin_memory=True).copy_(f) for f in inputs.teacher_feats]
         host_hs = torch.empty(hs_s.shape, pin_memory=True).copy_(hs_s.detach())
         host_ht = torch.empty(hs_s.shape, pin_memory=True).copy_(inputs.hs_teacher)
         host_loss = torch.empty((), pin_memory=True)
+        os.sched_setaffinity(0, affinity0)
         h2d = sum(t_.numel() * 4 for t_ in host_s + host_t + [host_hs, host_ht])
 
         def upload():
@@ -627,7 +655,9 @@ def main():
                'd2h_bytes_per_step': 4, 'steps': e2e_steps, 'ms_per_step': e2e_ms, 'h2d_only_ms': h2d_ms,
                'h2d_gbs_per_rank': h2d / (h2d_ms * 1e-3) / 1e9, 'roof_frac': h2d_ms / e2e_ms,
                'roof_note': 'roof = the same pinned-host copies with no kernel behind them, all ranks at once; e2e / roof '
-                            'shows what the step adds to the transfer'}
+                            'shows what the step adds to the transfer',
+               'host_buffers': (f'pinned, first touched on NUMA node {numa_node} (the socket of this GPU)'
+                                if numa_cpus else 'pinned (no NUMA information on this box)')}
         del host_s, host_t, host_hs, host_ht
 
     contraction = None
@@ -711,9 +741,11 @@ def main():
         'contraction': contraction,
         'e2e': e2e,
         'gpu_launches': int(launches),
-        'eager': {'value': world * N * args.steps / (eager_ms * 1e-3), 'unit': UNIT, 'ms_per_step': eager_ms / args.steps,
+        'eager': {'value': world * N * args.steps / (eager_quiet_ms * 1e-3), 'unit': UNIT,
+                  'ms_per_step': eager_quiet_ms / args.steps, 'ms_per_step_under_clock_sampler': eager_ms / args.steps,
                   'note': 'the two module calls + backward issued from Python on one stream (no graph, no side stream); '
-                          'host-issue bound', 'graph_error': graph_err},
+                          'host-issue bound; measured again after the nvidia-smi clock sampler has stopped (its driver '
+                          'polling lengthens every launch)', 'graph_error': graph_err},
         'clocks': clocks,
         'loss': loss_value,
         'parity_note': PARITY_NOTE,

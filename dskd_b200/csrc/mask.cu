@@ -216,13 +216,14 @@ __global__ void __launch_bounds__(256) raster_kernel(const float* __restrict__ b
 // row finish -> loss conversion were eight of them.
 //
 // prepare_v1_kernel, one 1-D grid with three CTA roles:
-//   [0, raster_ctas)            owner raster of one 256-cell tile of one image (as raster_kernel<OWNER_EXCL>)
-//   [.., + num_pairs)           pair p: finds ITS matched student query -- the p-th query in ascending order whose
+//   [0, num_pairs)              pair p: finds ITS matched student query -- the p-th query in ascending order whose
 //                               label is a previous-task label (head_il.py:1453-1455, :672) -- by a block-wide rank
 //                               search over the labels, writes ids[p], the mask row softmax_c|hs_T - hs_S|, and clears
 //                               its row of the energy table
+//   [.., + raster_ctas)         owner raster of one 256-cell tile of one image (as raster_kernel<OWNER_EXCL>)
 //   [.., + zero_ctas)           clears grad_hs_student, the loss accumulator and the finish counter
 // ------------------------------------------------------------------------------------------------
+constexpr int kPrepTile = 256;   // cells per raster CTA of prepare_v1_kernel (1024 = 4 per thread measured slower: fewer warps to hide latency)
 struct PrepareV1Params {
   RasterParams raster;
   int raster_tiles, raster_ctas, num_pairs, zero_ctas;
@@ -234,15 +235,17 @@ struct PrepareV1Params {
   float* grad_hs; int64_t grad_hs_floats; double* acc; unsigned* counter;
 };
 
-__global__ void __launch_bounds__(256) prepare_v1_kernel(const __grid_constant__ PrepareV1Params p) {
+__global__ void __launch_bounds__(256, 8) prepare_v1_kernel(const __grid_constant__ PrepareV1Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ float red[32];
   __shared__ int s_scan[8];
   __shared__ int s_id, s_total;
   __shared__ float bcast;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  int b = blockIdx.x;
-  if (b < p.raster_ctas) {
+  // block order = start order: the pair CTAs carry the longest chain of dependent loads (labels -> prev_mask -> ids ->
+  // embeddings -> softmax) and go first, the short raster CTAs fill in behind them, the clears come last
+  int b = (int)blockIdx.x - p.num_pairs;
+  if (b >= 0 && b < p.raster_ctas) {
     // ---- owner raster: last box (highest pair index) whose half-open rectangle holds the cell (head_il.py:706)
     Rect* rects = reinterpret_cast<Rect*>(smem_raw);
     const int i = b / p.raster_tiles, tile = b - i * p.raster_tiles;
@@ -253,54 +256,121 @@ __global__ void __launch_bounds__(256) prepare_v1_kernel(const __grid_constant__
       rects[k] = make_rect(p.boxes + (int64_t)(b0 + j) * 4, img_h, img_w, p.raster.levels[l].H, p.raster.levels[l].W, false);
     }
     __syncthreads();
-    const int64_t cell = (int64_t)tile * blockDim.x + tid;
-    if (cell >= p.cells_per_image) return;
-    int l = 0;
+    const int cells = (int)p.cells_per_image;  // < 2^31 (checked at launch): 32-bit cell arithmetic
+    const int cell0 = tile * kPrepTile;
+    const int cell_last = min(cell0 + kPrepTile, cells) - 1;
+    auto level_of = [&](int c) {
+      int l = 0;
 #pragma unroll
-    for (int k = 1; k < DSKD_MAX_LEVELS; ++k)
-      if (k < p.raster.num_levels && cell >= p.raster.levels[k].cell_offset) l = k;
-    const int W = p.raster.levels[l].W;
-    const int local = (int)(cell - p.raster.levels[l].cell_offset);
-    const int h = local / W, w = local - h * W;
-    const Rect* R = rects + l * nb;
-    int owner = -1;
-    for (int j = nb - 1; j >= 0; --j) {
-      const Rect r = R[j];
-      if (h >= r.hmin && h < r.hmax && w >= r.wmin && w < r.wmax) { owner = b0 + j; break; }
+      for (int k = 1; k < DSKD_MAX_LEVELS; ++k)
+        if (k < p.raster.num_levels && c >= (int)p.raster.levels[k].cell_offset) l = k;
+      return l;
+    };
+    // A tile is kPrepTile consecutive cells -- a few rows of one level.  Only the boxes that reach those rows can own any
+    // of its cells: one ballot per warp keeps them as a bit mask and the per-cell search walks the set bits from the top
+    // (the kernel was issue-bound on the 40-box loop of every cell).  Tiles that straddle two levels take every box.
+    __shared__ unsigned cand[8];
+    const int l_first = level_of(cell0), l_last = level_of(cell_last);
+    {
+      bool keep = false;
+      if (tid < nb) {
+        keep = true;
+        if (l_first == l_last) {
+          const int off = (int)p.raster.levels[l_first].cell_offset;
+          const int Wl = p.raster.levels[l_first].W;
+          const int h0 = (cell0 - off) / Wl, h1 = (cell_last - off) / Wl;
+          const Rect r = rects[l_first * nb + tid];
+          keep = r.hmin <= h1 && r.hmax > h0 && r.wmin < r.wmax;
+        }
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      if (lane == 0) cand[warp] = m;
     }
-    p.owner[(int64_t)i * p.cells_per_image + cell] = owner;
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < kPrepTile / 256; ++u) {
+      const int cell = cell0 + u * 256 + tid;
+      if (cell > cell_last) break;
+      const int l = (l_first == l_last) ? l_first : level_of(cell);
+      const int W = p.raster.levels[l].W;
+      const int local = cell - (int)p.raster.levels[l].cell_offset;
+      const int h = local / W, w = local - h * W;
+      const Rect* R = rects + l * nb;
+      int owner = -1;
+      if (nb <= 256) {
+        for (int wv = (nb - 1) >> 5; wv >= 0 && owner < 0; --wv) {
+          unsigned m = cand[wv];
+          while (m) {
+            const int j = (wv << 5) + 31 - __clz(m);
+            m &= ~(1u << (j & 31));
+            const Rect r = R[j];
+            if (h >= r.hmin && h < r.hmax && w >= r.wmin && w < r.wmax) { owner = b0 + j; break; }
+          }
+        }
+      } else {
+        for (int j = nb - 1; j >= 0; --j) {
+          const Rect r = R[j];
+          if (h >= r.hmin && h < r.hmax && w >= r.wmin && w < r.wmax) { owner = b0 + j; break; }
+        }
+      }
+      p.owner[(int64_t)i * cells + cell] = owner;
+    }
     return;
   }
-  b -= p.raster_ctas;
-  if (b < p.num_pairs) {
-    // ---- pair b: rank search for the b-th previous-labelled query
+  if (b < 0) {
+    b += p.num_pairs;
+    // ---- pair b: rank search for the b-th previous-labelled query.  The labels are taken 256 at a time in query order
+    // (thread = query, coalesced); all chunks' loads are in flight together (a thread walking its own contiguous slice
+    // paid two dependent L2 round trips per label: 10 of this kernel's 15 us).  Per chunk and warp the ballot of the
+    // hits and its population go to shared memory; warp 0 then scans the counts and picks the b-th set bit.
     const int n = p.num_rows;
-    const int per = (n + (int)blockDim.x - 1) / (int)blockDim.x;
-    const int lo = min(n, tid * per), hi = min(n, lo + per);
-    auto hit = [&](int q) {
-      const int64_t lab = p.labels[q];
-      return lab >= 0 && lab < p.num_classes && p.prev_mask[lab] != 0;
-    };
-    int c = 0;
-    for (int q = lo; q < hi; ++q) c += hit(q) ? 1 : 0;
-    int incl = c;
+    const int chunks = (n + 255) >> 8;
+    int* cnt = reinterpret_cast<int*>(smem_raw + (size_t)p.C * sizeof(float));  // [chunks][8] hits per (chunk, warp)
+    unsigned* bal = reinterpret_cast<unsigned*>(cnt + chunks * 8);               // [chunks][8] their ballots
+    constexpr int kBatch = 10;  // chunks whose label loads are in flight together (registers: 2 per chunk)
+    for (int k0 = 0; k0 < chunks; k0 += kBatch) {
+      int64_t lab[kBatch];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += t;
+      for (int u = 0; u < kBatch; ++u) {
+        const int q = ((k0 + u) << 8) + tid;
+        lab[u] = (k0 + u < chunks && q < n) ? __ldg(p.labels + q) : -1;
+      }
+      unsigned hits = 0;
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u)
+        if (lab[u] >= 0 && lab[u] < p.num_classes && __ldg(p.prev_mask + lab[u]) != 0) hits |= 1u << u;
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const unsigned m = __ballot_sync(0xffffffffu, (hits >> u) & 1u);
+        if (lane == 0 && k0 + u < chunks) { cnt[(k0 + u) * 8 + warp] = __popc(m); bal[(k0 + u) * 8 + warp] = m; }
+      }
     }
-    if (lane == 31) s_scan[warp] = incl;
     if (tid == 0) s_id = 0;
     __syncthreads();
-    int before = 0;
-    for (int wv = 0; wv < warp; ++wv) before += s_scan[wv];
-    const int excl = before + incl - c;
-    if (b >= excl && b < excl + c) {
-      int need = b - excl;
-      for (int q = lo; q < hi; ++q)
-        if (hit(q) && need-- == 0) { s_id = q; break; }
+    if (warp == 0) {
+      // entries in (chunk, warp) order == query order; lane takes a contiguous run of them
+      const int entries = chunks * 8, per = (entries + 31) >> 5;
+      const int lo = min(entries, lane * per), hi = min(entries, lo + per);
+      int c = 0;
+      for (int e = lo; e < hi; ++e) c += cnt[e];
+      int incl = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      int before = incl - c;
+      if (b >= before && b < incl) {
+        for (int e = lo; e < hi; ++e) {
+          if (b < before + cnt[e]) {
+            s_id = (e << 5) + (int)__fns(bal[e], 0, b - before + 1);  // e * 32 = first query of this (chunk, warp)
+            break;
+          }
+          before += cnt[e];
+        }
+      }
+      if (lane == 31) s_total = incl;
     }
-    if (tid == (int)blockDim.x - 1) s_total = excl + c;
     __syncthreads();
     // fewer than b + 1 queries carry a previous label: the reference raises IndexError at :705.  Without a host sync
     // the failure is made loud on the device instead: the pair's mask row and the step's loss become NaN.
@@ -349,7 +419,7 @@ __global__ void __launch_bounds__(256) prepare_v1_kernel(const __grid_constant__
     for (int ch = tid; ch < C; ch += blockDim.x) p.rows[(int64_t)b * C + ch] = unmatched ? __int_as_float(0x7fc00000) : a[ch] / sum;
     return;
   }
-  b -= p.num_pairs;
+  b -= p.raster_ctas;
   // ---- clears
   if (b == 0 && tid == 0) { *p.acc = 0.0; *p.counter = 0u; }
   if (p.grad_hs != nullptr) {
@@ -528,7 +598,7 @@ int launch_prepare_v1(const DskdDsgfdStepArgs* a, int* owner, float* rows, float
   memset(&p, 0, sizeof(p));
   p.raster.num_levels = a->num_levels;
   for (int l = 0; l < a->num_levels; ++l) p.raster.levels[l] = a->levels[l];
-  p.raster_tiles = (int)ceil_div(a->cells_per_image, 256);
+  p.raster_tiles = (int)ceil_div(a->cells_per_image, kPrepTile);
   p.raster_ctas = p.raster_tiles * a->N;
   p.num_pairs = a->num_pairs;
   p.N = a->N; p.C = a->C; p.num_rows = a->num_query_rows; p.num_classes = a->num_classes;
@@ -541,8 +611,11 @@ int launch_prepare_v1(const DskdDsgfdStepArgs* a, int* owner, float* rows, float
   p.grad_hs_floats = a->d_grad_hs_student ? (int64_t)a->num_query_rows * a->C : 0;
   p.acc = acc; p.counter = counter;
   p.zero_ctas = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(p.grad_hs_floats, 256 * 16), 2 * kNumSMs));
-  const size_t smem = std::max((size_t)a->max_boxes_per_image * a->num_levels * sizeof(Rect), (size_t)a->C * sizeof(float));
-  DSKD_REQUIRE(smem <= 200 * 1024, "dskd_dsgfd_step: too many boxes per image (%d)", a->max_boxes_per_image);
+  // raster role: the image's rectangles; pair role: one mask row + the (chunk, warp) hit counts and ballots of the rank search
+  const size_t search = (size_t)ceil_div(p.num_rows, 256) * 8 * 2 * sizeof(int);
+  const size_t smem = std::max((size_t)a->max_boxes_per_image * a->num_levels * sizeof(Rect), (size_t)a->C * sizeof(float) + search);
+  DSKD_REQUIRE(smem <= 200 * 1024, "dskd_dsgfd_step: too many boxes per image (%d) or query rows (%d)", a->max_boxes_per_image, p.num_rows);
+  DSKD_REQUIRE(a->cells_per_image < (1ll << 31) - 256, "dskd_dsgfd_step: cells_per_image too large");
   DSKD_REQUIRE(a->d_grad_hs_student == nullptr || aligned16(a->d_grad_hs_student), "dskd_dsgfd_step: d_grad_hs_student must be 16-byte aligned");
   if (smem > 48 * 1024)
     DSKD_CUDA_OK(cudaFuncSetAttribute(prepare_v1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -482,10 +482,13 @@ class _BcddFn(torch.autograd.Function):
                                             L.ptr(grad_proto), L.ptr(grad_hs), st), 'dskd_bcdd_loss_and_grad')
         ctx.staged = grad_hs
         ctx.mark_non_differentiable(dist, proto)
+        ctx.set_materialize_grads(False)    # no zero-filled gradients for `dist` / `proto` on every backward
         return loss.reshape(()), dist, proto
 
     @staticmethod
     def backward(ctx, grad_out, _gd, _gp):
+        if grad_out is None:        # only the non-differentiable by-products were used downstream
+            return None, None, None
         if ctx.staged is None and ctx.needs_input_grad[1]:
             raise RuntimeError('BetweenClassDistanceLoss: staged gradients already consumed (single backward per forward)')
         grad_hs = ctx.staged

@@ -83,16 +83,22 @@ def test_temperature_and_large_scores_do_not_overflow():
     torch.testing.assert_close(w.double(), ref, rtol=0, atol=1e-4)
 
 
-def test_images_without_detections_get_zero_weight():
-    cpu, counts, sc, start = make(3, SMALL, 100, 256, 9)
+@pytest.mark.parametrize('k,mode', [(9, None), (9, '2'), (200, None), (400, '2')], ids=['k9', 'k9-pair', 'k200', 'k400-pair'])
+def test_images_without_detections_get_zero_weight(k, mode, qmem_mode):
+    qmem_mode(mode)
+    cpu, counts, sc, start = make(3, SMALL, max(100, k), 256, k)
     # drop the detections of image 1
     a = cpu.assignments
-    keep = torch.cat([a['teacher_keepid'][:9], a['teacher_keepid'][18:]])
-    sc2 = torch.cat([sc[:9], sc[18:]])
-    start2 = torch.tensor([0, 9, 9, 18], dtype=torch.int32)
+    k0, k1, k2 = counts
+    keep = torch.cat([a['teacher_keepid'][:k0], a['teacher_keepid'][k0 + k1:]])
+    sc2 = torch.cat([sc[:k0], sc[k0 + k1:]])
+    start2 = torch.tensor([0, k0, k0, k0 + k2], dtype=torch.int32)
     _, t_mem = cpu.memory()
-    w = qmem.qmem_cell_weights(t_mem.to(DEV), cpu.hs_teacher.to(DEV), keep.to(DEV), sc2.to(DEV), start2.to(DEV), 9).cpu()
+    w = qmem.qmem_cell_weights(t_mem.to(DEV), cpu.hs_teacher.to(DEV), keep.to(DEV), sc2.to(DEV), start2.to(DEV),
+                               max(k0, k2)).cpu()
     assert float(w[1].abs().max()) == 0.0 and float(w[0].max()) > 0 and float(w[2].max()) > 0
+    ref = oq.qmem_cell_weights(t_mem, cpu.hs_teacher, keep, sc2, [k0, 0, k2], 0.5, tf32='trunc', dtype=torch.float64)
+    torch.testing.assert_close(w.double(), ref, rtol=0, atol=TIGHT)
     none = qmem.qmem_cell_weights(t_mem.to(DEV), cpu.hs_teacher.to(DEV), keep[:0].to(DEV), None,
                                   torch.zeros(4, dtype=torch.int32, device=DEV), 0).cpu()
     assert float(none.abs().max()) == 0.0

@@ -184,8 +184,8 @@ def bench_train_step(device, rank, world, dist, images_per_gpu=4, criterion='kl'
         student, teacher = make_student_teacher(device, backbone=backbone)
         student.train()
         if world > 1:
-            student = torch.nn.parallel.DistributedDataParallel(student, device_ids=[device.index], broadcast_buffers=False,
-                                                                find_unused_parameters=True)
+            # every parameter of the detector receives a gradient in this step (DDP itself reports so)
+            student = torch.nn.parallel.DistributedDataParallel(student, device_ids=[device.index], broadcast_buffers=False)
         trainer = IncrementalTrainStep(student, teacher, num_prev=40, criterion=criterion, sync_prototypes=world > 1)
         img, gt_b, gt_l = synthetic_batch(device, images_per_gpu, height, width, seed=1234 + rank)
         out = None

@@ -24,15 +24,16 @@
 
 namespace dskd {
 
-constexpr int kKlWarps = 8;       // warps per CTA (one channel at a time each)
+constexpr int kKlWarps = 8;       // warps per CTA of the redo kernel, and of the streaming kernel for large batches
+constexpr int kKlMaxWarps = 16;   // streaming kernel: (channels per CTA / channels per pass) x row parts, at most
+constexpr int kKlMaxSplit = 4;    // row parts of a column at most
 // Measured on B200 (tools/kl_perf.py --tune, 16 images of 800x1333): two channels per pass, 4-row blocks loaded and consumed
 // in place (no register ring), 4 CTAs x 8 warps per SM at 64 registers: 139 us; with a 2-stage ring at 127 registers
 // (2 CTAs per SM) 168 us; one channel per pass (5-row blocks, 2 stages, 4 CTAs per SM) 169 us.
 constexpr int kKlBlk = 4;         // rows per block: the unit of loading and of skipping rows without boxes (gradient kernels)
 constexpr int kKlBlkFwd = 5;      //   ... forward-only kernels
-constexpr int kKlStages = 1;      // row blocks in the register ring: the loads of kKlStages - 1 blocks are in flight ahead
-constexpr int kKlMinCtas = 4;     // CTAs per SM the register budget is cut for
-constexpr int kKlChunk = 16;      // channels per CTA (8 for small batches: twice the CTAs to fill 148 SMs x 4)
+constexpr int kKlChunk = 16;      // channels per CTA
+constexpr int kKlSmallBatch = 4;  // images up to which the gradient kernel runs two row parts per column
 constexpr int kKlPool = 192;      // (owner, lane, A, B) records a warp can park per pass before the normalisers are known
 constexpr int kKlMaxH = 1600;     // rows per level (shared-memory tables: 136 B per row)
 constexpr int kKlRedoCtas = 148;  // grid of the redo launch
@@ -51,6 +52,7 @@ struct KlParams {
   int max_blocks;                // row blocks of the tallest level (sizes the shared-memory tables)
   int max_h;
   int pool_cap;                  // (owner, lane, A, B) records a warp can park per channel
+  int rsplit;                    // warps sharing one column (row parts)
   int dbg;                       // tuning experiments only (DSKD_KL_TUNE): 1 = no red.global at the bottom, 2 = no run ends
   float temperature, kscale;     // kscale = log2(e) / T: logits are kept in units of log 2
   int64_t cells_per_image;
@@ -105,6 +107,12 @@ __device__ __forceinline__ float ld_stream_f1_nz(const float* p, float key) {
       : "l"(p), "f"(key));
   return v;
 }
+// barrier of the warps that share channel slot `slot` (< 8); immediate ids, so that the CTA reserves 9 barriers, not 16
+__device__ __forceinline__ void kl_slot_barrier(int slot, int threads) {
+#define DSKD_BAR(ID) case ID - 1: asm volatile("bar.sync " #ID ", %0;" ::"r"(threads) : "memory"); break;
+  switch (slot) { DSKD_BAR(1) DSKD_BAR(2) DSKD_BAR(3) DSKD_BAR(4) DSKD_BAR(5) DSKD_BAR(6) DSKD_BAR(7) DSKD_BAR(8) }
+#undef DSKD_BAR
+}
 __device__ __forceinline__ void st_shared_b32(unsigned addr, int v) {
   asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
@@ -120,14 +128,16 @@ struct KlTables {
 
 // dynamic shared memory layout of the streaming kernel (the same arithmetic on both sides)
 struct KlSmem {
-  size_t endm, anym, pool, act, total;
-  // rec_words: 32-bit words per run record: key + (A, B) per channel of the pass
-  __host__ __device__ KlSmem(int max_blocks, int blk, bool grad, int pool_cap, int rec_words) {
+  size_t endm, anym, pool, part, act, total;
+  // rec_words: 32-bit words per run record: key + (A, B) per channel of the pass; nwarps: warps of the CTA;
+  // part_words: partial sums per lane that the row parts of a column exchange (0: one warp per column)
+  __host__ __device__ KlSmem(int max_blocks, int blk, bool grad, int pool_cap, int rec_words, int nwarps, int part_words) {
     const size_t rows = (size_t)max_blocks * blk;
     endm = rows * 32 * 4;
     anym = endm + rows * 4;
     pool = (anym + rows * 4 + 15) / 16 * 16;
-    act = pool + (grad ? (size_t)kKlWarps * pool_cap * rec_words * 4 : 0);
+    part = (pool + (grad ? (size_t)nwarps * pool_cap * rec_words * 4 : 0) + 15) / 16 * 16;
+    act = part + (size_t)nwarps * 32 * part_words * 4;
     total = (act + (size_t)max_blocks * 2 + 15) / 16 * 16;
   }
 };
@@ -390,33 +400,54 @@ __device__ __forceinline__ void kl_stream_pass2(const KlTables& tb, KlChan2& ch,
   }
 }
 
-// Bottom of a column for one channel of a pass: the runs parked in the pool (planes ia / ib hold A / B of this channel)
-// become d loss / d mask rows: neighbouring records of one owner are added up first (segmented scan over the lanes), then
-// one red.global per segment.
-__device__ __forceinline__ void kl_flush_pool(const int* pool, int pool_words, int ia, int ib, int count, int lane,
-                                              const float* norm /* [32][stride]: rt, rs of the source lane */, int stride,
-                                              int io, float gcoef, float* __restrict__ growc, bool no_red) {
+// Bottom of a column for the NC channels of a pass: the runs parked in the pool (plane 0: key, planes 1 + 2k / 2 + 2k:
+// A / B of channel k) become d loss / d mask rows: neighbouring records of one owner are added up first (one segmented scan
+// over the lanes for all channels: the segments are the same), then one red.global per segment and channel.
+template <int NC>
+__device__ __forceinline__ void kl_flush_pool(const int* pool, int pool_words, int count, int lane,
+                                              const float (&rt)[NC] /* 1 / sum e^y of this lane's column */,
+                                              const float (&rs)[NC] /* 1 / sum e^x */, float gcoef,
+                                              float* __restrict__ growc, bool no_red) {
   constexpr unsigned kFull = 0xffffffffu;
   for (int j0 = 0; j0 < count; j0 += 32) {
     const int j = j0 + lane;
     const bool have = j < count;
     const int key = have ? pool[j] : -1 - lane;  // owner * C * 32 + lane of the column
-    float g = 0.f;
-    if (have) {
-      const float* nr = norm + (key & 31) * stride + io;
-      g = gcoef * (__int_as_float(pool[j + ia * pool_words]) * nr[0] - __int_as_float(pool[j + ib * pool_words]) * nr[1]);
+    float g[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      // the normalisers of the record's column sit in the registers of its lane
+      const float nt = __shfl_sync(kFull, rt[k], key & 31), ns = __shfl_sync(kFull, rs[k], key & 31);
+      g[k] = 0.f;
+      if (have)
+        g[k] = gcoef * (__int_as_float(pool[j + (1 + 2 * k) * pool_words]) * nt -
+                        __int_as_float(pool[j + (2 + 2 * k) * pool_words]) * ns);
     }
     const int own = key >> 5;
     const int prev = __shfl_up_sync(kFull, own, 1), next = __shfl_down_sync(kFull, own, 1);
     bool open = lane > 0 && prev == own;  // the segment continues to the left
+    if (__any_sync(kFull, open)) {
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const float gv = __shfl_up_sync(kFull, g, d);
-      const bool ov = __shfl_up_sync(kFull, (int)open, d);
-      if (open && lane >= d) { g += gv; open = ov; }
+      for (int d = 1; d < 32; d <<= 1) {
+        float gv[NC];
+#pragma unroll
+        for (int k = 0; k < NC; ++k) gv[k] = __shfl_up_sync(kFull, g[k], d);
+        const bool ov = __shfl_up_sync(kFull, (int)open, d);
+        if (open && lane >= d) {
+#pragma unroll
+          for (int k = 0; k < NC; ++k) g[k] += gv[k];
+          open = ov;
+        }
+      }
     }
     const bool tail = lane == 31 || next != own;
-    if (have && tail && !no_red) atomicAdd(growc + own, g);
+    if (have && tail && !no_red) {
+      if constexpr (NC == 2) {  // (owner * C + c) is even and the rows are 8-byte aligned (pair_ok): one vector red
+        asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(growc + own), "f"(g[0]), "f"(g[1]) : "memory");
+      } else {
+        atomicAdd(growc + own, g[0]);
+      }
+    }
   }
 }
 
@@ -429,15 +460,18 @@ __device__ __forceinline__ void kl_flush_pool(const int* pool, int pool_words, i
 // not depend on the channel, so the CTA knows up front how many warps can run side by side: with more runs than one
 // pool holds, 4 / 2 / 1 warps work with 2 / 4 / 8 pools each.  NC = 2: a warp takes two neighbouring channels per pass
 // (kl_stream_pass2); NC = 1 is the scalar pass for an odd channel count.
-template <bool CELL, bool GRAD, int NC, int R, int NB, int MINB>
-__global__ void __launch_bounds__(32 * kKlWarps, MINB) dsgfd_kl_stream_kernel(const __grid_constant__ KlParams prm) {
+template <bool CELL, bool GRAD, int NC, int R>
+__global__ void __launch_bounds__(32 * kKlMaxWarps, 2) dsgfd_kl_stream_kernel(const __grid_constant__ KlParams prm) {
   extern __shared__ __align__(16) unsigned char kl_smem[];
   __shared__ double red[32];
-  __shared__ float norm_s[kKlWarps][32][2 * NC];  // per lane: (1 / sum e^y, 1 / sum e^x) of each channel of the pass
-  __shared__ int nact_s, nadd_s, nends_s;
+  __shared__ int nact_s, nadd_s, need_s;
+  __shared__ int part_ends[kKlMaxSplit];
   __shared__ unsigned redo_s;
   constexpr unsigned kFull = 0xffffffffu;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nwarps = (int)blockDim.x >> 5;
+  const int rsplit = prm.rsplit;     // warps sharing one column: each takes a contiguous part of the active row blocks
+  const int cw = nwarps / rsplit;    // channel slots: warps working on different channels side by side
   const KlTile tl = kl_decode_tile(prm, blockIdx.x);
   const int lvl = tl.lvl;
   const int H = prm.levels[lvl].H, C = prm.C;
@@ -445,44 +479,55 @@ __global__ void __launch_bounds__(32 * kKlWarps, MINB) dsgfd_kl_stream_kernel(co
   const int nblk = (H + R - 1) / R, rows_pad = nblk * R;
 
   constexpr int kRec = 1 + 2 * NC;  // words per run record
-  const KlSmem lay(prm.max_blocks, R, GRAD, prm.pool_cap, kRec);
+  constexpr int kSums = 3 * NC;     // partial sums a row part hands over per lane
+  const KlSmem lay(prm.max_blocks, R, GRAD, prm.pool_cap, kRec, nwarps, rsplit > 1 ? kSums : 0);
   KlTables tb;
   tb.moff = reinterpret_cast<int*>(kl_smem);
   tb.mw = reinterpret_cast<float*>(kl_smem);
   tb.endm = reinterpret_cast<unsigned*>(kl_smem + lay.endm);
   tb.anym = reinterpret_cast<unsigned*>(kl_smem + lay.anym);
   tb.act = reinterpret_cast<unsigned short*>(kl_smem + lay.act);
+  float* part_sums = reinterpret_cast<float*>(kl_smem + lay.part);  // [nwarps][kSums][32]
 
-  // ---- once per CTA: owner table, run ends, list of active row blocks
+  // ---- once per CTA: owner table, run ends, list of active row blocks, the row parts
   {
-    const int64_t cell0 = (int64_t)tl.img * prm.cells_per_image + prm.levels[lvl].cell_offset + tl.w0;
-    for (int i = tid; i < rows_pad * 32; i += 32 * kKlWarps) {
-      const int h = i >> 5, l = i & 31;
-      const bool in = h < H && l < tl.wn;
-      if (CELL) tb.mw[i] = in ? __ldg(prm.cell_weight + cell0 + (int64_t)h * W + l) : 0.f;
-      else {
-        const int o = in ? __ldg(prm.owner + cell0 + (int64_t)h * W + l) : -1;
-        tb.moff[i] = o >= 0 ? o * C : -1;
+    const int64_t cell0 = (int64_t)tl.img * prm.cells_per_image + prm.levels[lvl].cell_offset + tl.w0 + lane;
+    if (tid < kKlMaxSplit) part_ends[tid] = 0;
+    if (tid == 0) redo_s = 0u;
+    // A warp takes consecutive rows, lane = column: the owner table (owner * C per cell), and per row the lanes with a box
+    // at all and the lanes whose run of one owner ends with this row.  Every row is fetched once: the next row's owners
+    // are carried over (four rows in flight at a time).
+    const int rpw = (rows_pad + nwarps - 1) / nwarps;
+    const int h0 = warp * rpw, h1 = min(rows_pad, h0 + rpw);
+    const bool col_in = lane < tl.wn;
+    auto fetch = [&](int h) -> int {
+      if (!(col_in && h < H)) return CELL ? 0 : -1;
+      if (CELL) return __float_as_int(__ldg(prm.cell_weight + cell0 + (int64_t)h * W));
+      return __ldg(prm.owner + cell0 + (int64_t)h * W);
+    };
+    int o = h0 < h1 ? fetch(h0) : -1;
+    for (int h = h0; h < h1; h += 4) {
+      int nx[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) nx[u] = fetch(h + u + 1);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (h + u < h1) {
+          bool on, end = false;
+          if (CELL) {
+            on = __int_as_float(o) != 0.f;
+            tb.moff[(h + u) * 32 + lane] = o;
+          } else {
+            on = o >= 0;
+            end = on && nx[u] != o;
+            tb.moff[(h + u) * 32 + lane] = on ? o * C : -1;
+          }
+          const unsigned am = __ballot_sync(kFull, on), em = __ballot_sync(kFull, end);
+          if (lane == 0) { tb.anym[h + u] = am; tb.endm[h + u] = em; }
+        }
+        o = nx[u];
       }
     }
-    if (tid == 0) { nends_s = 0; redo_s = 0u; }
-    __syncthreads();
-    // per row: lanes whose run of one owner ends here, lanes with a box at all
-    int ends_here = 0;
-    for (int h = warp; h < rows_pad; h += kKlWarps) {
-      bool on, end = false;
-      if (CELL) on = tb.mw[h * 32 + lane] != 0.f;
-      else {
-        const int o = tb.moff[h * 32 + lane];
-        const int nx = (h + 1 < rows_pad) ? tb.moff[(h + 1) * 32 + lane] : -1;
-        on = o >= 0;
-        end = on && nx != o;
-      }
-      const unsigned am = __ballot_sync(kFull, on), em = __ballot_sync(kFull, end);
-      if (lane == 0) { tb.anym[h] = am; tb.endm[h] = em; }
-      ends_here += __popc(em);
-    }
-    if (GRAD && lane == 0 && ends_here) atomicAdd(&nends_s, ends_here);
     __syncthreads();
     if (warp == 0) {
       int base = 0, nadd = 0;
@@ -506,6 +551,33 @@ __global__ void __launch_bounds__(32 * kKlWarps, MINB) dsgfd_kl_stream_kernel(co
       }
       nadd = __reduce_add_sync(kFull, nadd);
       if (lane == 0) { nact_s = base; nadd_s = nadd; }
+      if (GRAD) {
+        // Row parts: part p streams the active blocks [p * q, (p + 1) * q).  A run that crosses into the next part is cut
+        // at the part's last row (both pieces become records of the same owner and column: their sum is the run's).
+        __syncwarp();
+        const int q = (base + rsplit - 1) / rsplit;
+        if (rsplit > 1 && lane >= 1 && lane < rsplit && lane * q < base) {
+          const int k = lane * q - 1;  // last block of part lane - 1
+          const int blk = tb.act[k] & 0x7fff, r = blk * R + R - 1;
+          if (tb.anym[r] != 0u) {
+            tb.endm[r] = tb.anym[r];
+            tb.act[k] = (unsigned short)(blk | 0x8000);
+          }
+        }
+        __syncwarp();
+        for (int k = lane; k < base; k += 32) {  // records every part must be able to park
+          const int r0 = (tb.act[k] & 0x7fff) * R;
+          int e = 0;
+#pragma unroll
+          for (int r = r0; r < r0 + R; ++r) e += __popc(tb.endm[r]);
+          if (e) atomicAdd(&part_ends[rsplit > 1 ? k / q : 0], e);
+        }
+        __syncwarp();
+        int need = lane < kKlMaxSplit ? part_ends[lane] : 0;
+#pragma unroll
+        for (int d = 1; d < kKlMaxSplit; d <<= 1) need = max(need, __shfl_xor_sync(kFull, need, d));
+        if (lane == 0) need_s = need;
+      }
     }
     __syncthreads();
   }
@@ -515,30 +587,37 @@ __global__ void __launch_bounds__(32 * kKlWarps, MINB) dsgfd_kl_stream_kernel(co
     return;
   }
   const int c_begin = tl.chunk * prm.chunk, c_end = min(C, c_begin + prm.chunk);
-  // warps working side by side: each needs pool room for every run of the tile
+  // channel slots working side by side: each warp needs pool room for every run of its row part
   int share = 1;
   if (GRAD) {
-    const int nends = nends_s;
-    while (share < kKlWarps && nends > share * prm.pool_cap) share *= 2;
-    if (nends > share * prm.pool_cap) {  // not even one warp with every pool: the whole block is left to the redo launch
+    const int need = need_s;
+    while (share < cw && need > share * prm.pool_cap) share *= 2;
+    if (need > share * prm.pool_cap) {  // not even one slot with every pool: the whole block is left to the redo launch
       if (tid == 0) prm.redo_mask[blockIdx.x] = 0xffffffffu >> (32 - (c_end - c_begin));
       return;
     }
   }
-  const int wstep = kKlWarps / share;  // active warps: 0 .. wstep - 1, warp w owns the pools w * share ..
-  // warp w's records: planes (key, A, B per channel) of share * pool_cap words each
+  const int part = warp / cw, cslot = warp - part * cw;
+  const int wstep = cw / share;  // active channel slots: 0 .. wstep - 1; slot s of part p owns the pools p * cw + s * share ..
+  // this warp's records: planes (key, A, B per channel) of share * pool_cap words each
   const int pool_words = share * prm.pool_cap;
-  const int* pool = reinterpret_cast<const int*>(kl_smem + lay.pool) + (size_t)warp * kRec * pool_words;
+  const int* pool = reinterpret_cast<const int*>(kl_smem + lay.pool) + (size_t)(part * cw + cslot * share) * kRec * prm.pool_cap;
   const unsigned pool_addr = (unsigned)__cvta_generic_to_shared(pool);
   double kl_total = 0.0;
 
-  if (warp < wstep) {
+  if (cslot < wstep) {
     const bool col_ok = lane < tl.wn;
-    for (int c = c_begin + NC * warp; c < c_end; c += NC * wstep) {
+    // this warp's part of the active blocks
+    const int q = (nact + rsplit - 1) / rsplit;
+    const int k0 = min(nact, part * q), k1 = min(nact, k0 + q);
+    KlTables tbp = tb;
+    tbp.act = tb.act + k0;
+    const int nmine = k1 - k0;
+    const float nadd = (float)nadd_s;
+    for (int c = c_begin + NC * cslot; c < c_end; c += NC * wstep) {
       const int64_t plane = ((int64_t)tl.img * C + c) * ((int64_t)H * W) + tl.w0 + lane;
-      bool ok;
+      float sums[kSums];  // per channel: sum e^x, sum e^y, sum e^x (x - y)
       int base;
-      float kl = 0.f;
       if constexpr (NC == 2) {
         KlChan2 ch;
         ch.Sp0 = prm.student[lvl] + plane;
@@ -550,20 +629,10 @@ __global__ void __launch_bounds__(32 * kKlWarps, MINB) dsgfd_kl_stream_kernel(co
         asm volatile("" : "+l"(ch.Sp0), "+l"(ch.Tp0), "+l"(ch.Sp1), "+l"(ch.Tp1), "+l"(ch.rowsc));
         ch.ss = ch.st = ch.ws = make_float2(0.f, 0.f);
         ch.base = 0;
-        kl_stream_pass2<CELL, GRAD, R, NB>(tb, ch, W, lane, nact, prm.kscale, pool_addr, pool_words, prm.dbg);
-        const float nadd = (float)nadd_s;
-        const float ss0 = ch.ss.x + nadd, st0 = ch.st.x + nadd, ss1 = ch.ss.y + nadd, st1 = ch.st.y + nadd;
-        ok = __all_sync(kFull, !col_ok || (kl_in_range(ss0, st0, ch.ws.x) && kl_in_range(ss1, st1, ch.ws.y)));
+        kl_stream_pass2<CELL, GRAD, R, 1>(tbp, ch, W, lane, nmine, prm.kscale, pool_addr, pool_words, prm.dbg);
+        sums[0] = ch.ss.x; sums[1] = ch.st.x; sums[2] = ch.ws.x;
+        sums[3] = ch.ss.y; sums[4] = ch.st.y; sums[5] = ch.ws.y;
         base = ch.base;
-        if (ok) {
-          kl = kl_col(ss0, st0, ch.ws.x) + kl_col(ss1, st1, ch.ws.y);
-          if (GRAD) {
-            norm_s[warp][lane][0] = __fdividef(1.f, st0);
-            norm_s[warp][lane][1] = __fdividef(1.f, ss0);
-            norm_s[warp][lane][2] = __fdividef(1.f, st1);
-            norm_s[warp][lane][3] = __fdividef(1.f, ss1);
-          }
-        }
       } else {
         KlChan ch;
         ch.Sp = prm.student[lvl] + plane;
@@ -572,32 +641,46 @@ __global__ void __launch_bounds__(32 * kKlWarps, MINB) dsgfd_kl_stream_kernel(co
         asm volatile("" : "+l"(ch.Sp), "+l"(ch.Tp), "+l"(ch.rowsc));
         ch.ss = ch.st = ch.ws = 0.f;
         ch.base = 0;
-        kl_stream_pass<CELL, GRAD, R, NB>(tb, ch, W, lane, nact, prm.kscale, pool_addr, pool_words, prm.dbg);
-        const float nadd = (float)nadd_s;
-        const float ss = ch.ss + nadd, st = ch.st + nadd;
-        ok = __all_sync(kFull, !col_ok || kl_in_range(ss, st, ch.ws));
+        kl_stream_pass<CELL, GRAD, R, 1>(tbp, ch, W, lane, nmine, prm.kscale, pool_addr, pool_words, prm.dbg);
+        sums[0] = ch.ss; sums[1] = ch.st; sums[2] = ch.ws;
         base = ch.base;
-        if (ok) {
-          kl = kl_col(ss, st, ch.ws);
-          if (GRAD) {
-            norm_s[warp][lane][0] = __fdividef(1.f, st);
-            norm_s[warp][lane][1] = __fdividef(1.f, ss);
-          }
+      }
+      if (rsplit > 1) {
+        // the row parts of this column meet: every part adds the partial sums up in the same order (identical totals)
+        float* mine = part_sums + (size_t)warp * kSums * 32 + lane;
+#pragma unroll
+        for (int k = 0; k < kSums; ++k) mine[k * 32] = sums[k];
+        kl_slot_barrier(cslot, 32 * rsplit);
+#pragma unroll
+        for (int k = 0; k < kSums; ++k) sums[k] = 0.f;
+        for (int p = 0; p < rsplit; ++p) {
+          const float* theirs = part_sums + (size_t)(p * cw + cslot) * kSums * 32 + lane;
+#pragma unroll
+          for (int k = 0; k < kSums; ++k) sums[k] += theirs[k * 32];
         }
+        kl_slot_barrier(cslot, 32 * rsplit);  // the partial sums may be overwritten by the next pass
       }
       // ---- bottom of the column: KL, parked runs
+      bool in_range = true;
+      float kl = 0.f, rt[NC], rs[NC];
+#pragma unroll
+      for (int k = 0; k < NC; ++k) {
+        const float ss = sums[3 * k] + nadd, st = sums[3 * k + 1] + nadd, ws = sums[3 * k + 2];
+        in_range = in_range && kl_in_range(ss, st, ws);
+        kl += kl_col(ss, st, ws);
+        rt[k] = __fdividef(1.f, st);
+        rs[k] = __fdividef(1.f, ss);
+      }
+      const bool ok = __all_sync(kFull, !col_ok || in_range);
       if (ok) {
-        if (col_ok) kl_total += (double)kl;
+        if (col_ok && part == 0) kl_total += (double)kl;
         if (GRAD && !(prm.dbg & 4)) {
           const float gcoef = prm.scale[lvl] * prm.temperature / (float)H;  // d loss / d pred = scale * (T/H) * (p - q)
           __syncwarp();
-#pragma unroll
-          for (int k = 0; k < NC; ++k)
-            kl_flush_pool(pool, pool_words, 1 + 2 * k, 2 + 2 * k, base, lane, &norm_s[warp][0][0], 2 * NC, 2 * k, gcoef,
-                          prm.grad_rows + c + k, prm.dbg & 1);
+          kl_flush_pool<NC>(pool, pool_words, base, lane, rt, rs, gcoef, prm.grad_rows + c, prm.dbg & 1);
           __syncwarp();
         }
-      } else if (lane == 0) {
+      } else if (lane == 0 && part == 0) {
         // exponentials out of range for the unshifted sums: these (tile, channel)s are redone with exact maxima
         atomicOr(&redo_s, (NC == 2 ? 3u : 1u) << (c - c_begin));
       }
@@ -993,19 +1076,28 @@ extern "C" int dskd_dsgfd_kl_fwd_bwd(const DskdDsgfdKlArgs* a, void* stream) {
   cudaStream_t st = as_stream(stream);
   if (a->layout == DSKD_LAYOUT_SNC) return launch_kl_snc(a, st);
   DSKD_REQUIRE(max_h <= kKlMaxH, "dsgfd_kl: H (%d) above the supported %d", max_h, kKlMaxH);
-  // tuning hook (tools/kl_perf.py): DSKD_KL_TUNE="channels_per_pass,rows_per_block,stages,ctas_per_sm,channels_per_cta,pool_records,dbg"
-  const bool pair_ok = a->C % 2 == 0 && (cell || (reinterpret_cast<uintptr_t>(a->d_rows) & 7u) == 0);
+  // tuning hook (tools/kl_perf.py): DSKD_KL_TUNE="channels_per_pass,rows_per_block,channels_per_cta,pool_records,dbg,warps,row_parts"
+  const bool pair_ok = a->C % 2 == 0 && (cell || ((reinterpret_cast<uintptr_t>(a->d_rows) & 7u) == 0 &&
+                                                  (reinterpret_cast<uintptr_t>(a->d_grad_rows) & 7u) == 0));
   const bool grad = !cell && a->d_grad_rows != nullptr;
-  int nc = pair_ok ? 2 : 1, blk = grad ? kKlBlk : kKlBlkFwd, stages = kKlStages, minb = kKlMinCtas;
-  int chunk = a->N <= 4 ? kKlChunk / 2 : kKlChunk, cap = kKlPool, dbg = 0;
+  int nc = pair_ok ? 2 : 1, blk = grad ? kKlBlk : kKlBlkFwd;
+  // Small batches of the gradient kernel: a tile's CTA lasts as long as its column is tall and there are too few CTAs to
+  // hide that, so two warps share a column (row parts) in 16-warp CTAs (measured at 4 images, tools/kl_perf.py --tune).
+  int chunk = kKlChunk, cap = kKlPool, dbg = 0, nwarps = 0;
+  int rsplit = grad && a->N <= kKlSmallBatch ? 2 : 1;
   if (const char* tune = getenv("DSKD_KL_TUNE"))
-    sscanf(tune, "%d,%d,%d,%d,%d,%d,%d", &nc, &blk, &stages, &minb, &chunk, &cap, &dbg);
-  DSKD_REQUIRE((nc == 1 || (nc == 2 && pair_ok)) && chunk >= 1 && chunk <= 32 && chunk % nc == 0 && cap >= 1,
+    sscanf(tune, "%d,%d,%d,%d,%d,%d,%d", &nc, &blk, &chunk, &cap, &dbg, &nwarps, &rsplit);
+  // one warp per `nc` channels of the chunk and row part
+  if (nwarps == 0) nwarps = std::max(rsplit, std::min(kKlMaxWarps, std::min(a->C, chunk) / nc * rsplit));
+  DSKD_REQUIRE((nc == 1 || (nc == 2 && pair_ok)) && chunk >= 1 && chunk <= 32 && chunk % nc == 0 && cap >= 1 &&
+                   (blk == kKlBlk || blk == kKlBlkFwd) && rsplit >= 1 && rsplit <= kKlMaxSplit && nwarps >= rsplit &&
+                   nwarps <= kKlMaxWarps && nwarps % rsplit == 0 && ((nwarps / rsplit) & (nwarps / rsplit - 1)) == 0,
                "dsgfd_kl: bad DSKD_KL_TUNE");
   prm.max_blocks = (max_h + blk - 1) / blk;
   prm.max_h = max_h;
   prm.chunk = std::min(a->C, chunk);
   prm.pool_cap = cap;
+  prm.rsplit = rsplit;
   prm.dbg = dbg;
   const int nchunks = (a->C + prm.chunk - 1) / prm.chunk;
   int blocks = 0;
@@ -1021,31 +1113,27 @@ extern "C" int dskd_dsgfd_kl_fwd_bwd(const DskdDsgfdKlArgs* a, void* stream) {
   }
   prm.block_start[a->num_levels] = blocks;
   prm.num_blocks = blocks;
-  const size_t smem = KlSmem(prm.max_blocks, blk, grad, cap, 1 + 2 * nc).total;
+  const size_t smem = KlSmem(prm.max_blocks, blk, grad, cap, 1 + 2 * nc, nwarps, rsplit > 1 ? 3 * nc : 0).total;
   DSKD_REQUIRE(smem <= 227 * 1024, "dsgfd_kl: H (%d) needs %zu bytes of shared memory", max_h, smem);
   bool launched = false;
-#define DSKD_KL_VARIANT(CELLV, GRADV, NCV, RV, NBV, MB)                                                         \
-  if (!launched && nc == NCV && blk == RV && stages == NBV && minb == MB) {                                     \
-    DSKD_CUDA_OK(cudaFuncSetAttribute(dsgfd_kl_stream_kernel<CELLV, GRADV, NCV, RV, NBV, MB>,                   \
+#define DSKD_KL_VARIANT(CELLV, GRADV, NCV, RV)                                                                  \
+  if (!launched && nc == NCV && blk == RV) {                                                                    \
+    DSKD_CUDA_OK(cudaFuncSetAttribute(dsgfd_kl_stream_kernel<CELLV, GRADV, NCV, RV>,                            \
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
-    dsgfd_kl_stream_kernel<CELLV, GRADV, NCV, RV, NBV, MB><<<blocks, 32 * kKlWarps, smem, st>>>(prm);           \
+    dsgfd_kl_stream_kernel<CELLV, GRADV, NCV, RV><<<blocks, 32 * nwarps, smem, st>>>(prm);                      \
     launched = true;                                                                                            \
   }
-#define DSKD_KL_VARIANTS(CELLV, GRADV)          \
-  DSKD_KL_VARIANT(CELLV, GRADV, 2, 4, 1, 4)     \
-  DSKD_KL_VARIANT(CELLV, GRADV, 2, 5, 1, 4)     \
-  DSKD_KL_VARIANT(CELLV, GRADV, 2, 5, 1, 3)     \
-  DSKD_KL_VARIANT(CELLV, GRADV, 2, 4, 2, 3)     \
-  DSKD_KL_VARIANT(CELLV, GRADV, 2, 5, 2, 2)     \
-  DSKD_KL_VARIANT(CELLV, GRADV, 1, 4, 1, 4)     \
-  DSKD_KL_VARIANT(CELLV, GRADV, 1, 5, 1, 4)     \
-  DSKD_KL_VARIANT(CELLV, GRADV, 1, 5, 2, 4)
+#define DSKD_KL_VARIANTS(CELLV, GRADV)               \
+  DSKD_KL_VARIANT(CELLV, GRADV, 2, kKlBlk)           \
+  DSKD_KL_VARIANT(CELLV, GRADV, 2, kKlBlkFwd)        \
+  DSKD_KL_VARIANT(CELLV, GRADV, 1, kKlBlk)           \
+  DSKD_KL_VARIANT(CELLV, GRADV, 1, kKlBlkFwd)
   if (cell) { DSKD_KL_VARIANTS(true, false) }
   else if (grad) { DSKD_KL_VARIANTS(false, true) }
   else { DSKD_KL_VARIANTS(false, false) }
 #undef DSKD_KL_VARIANTS
 #undef DSKD_KL_VARIANT
-  DSKD_REQUIRE(launched, "dsgfd_kl: no kernel variant for DSKD_KL_TUNE=%d,%d,%d,%d", nc, blk, stages, minb);
+  DSKD_REQUIRE(launched, "dsgfd_kl: no kernel variant for DSKD_KL_TUNE=%d,%d", nc, blk);
   DSKD_LAUNCH_OK("dsgfd_kl_stream_kernel");
   // the redo launch: a few loads per CTA when no block left anything behind
   const size_t redo_smem = (size_t)max_h * 32 * 4;

@@ -127,8 +127,7 @@ def test_dsgfd_decode_v1_kl(cfg, reduction):
     assert all(f.grad is None for f in feats) and all(f.grad is None for f in o_feats)
 
 
-# Level heights that reach every KL kernel configuration: 3 row parts with a short last part (4-warp CTAs), 6 and 10
-# parts (8- and 16-warp CTAs), and a level above 16 x 25 rows (the shared-memory strip kernel).
+# Tall and narrow levels: 15 to 105 row blocks per column tile, column tiles narrower than a warp.
 KL_TALL = {
     'parts3': dict(levels=((60, 40), (31, 20), (15, 10), (8, 5)), img_hw=(480, 320)),
     'parts6': dict(levels=((130, 36), (65, 18), (33, 9), (17, 5)), img_hw=(1040, 288)),
@@ -309,16 +308,47 @@ def test_dsgfd_kl_logits_beyond_the_unshifted_range(scale):
         torch.testing.assert_close(got.detach().cpu().double(), ref64, rtol=LOSS_RTOL, atol=1e-12)
 
 
+@pytest.mark.parametrize('layout', ['0,1', '8,1', '8,2', '16,2', '16,4', '4,4', '2,2', '1,1'])
+@pytest.mark.parametrize('shape', ['small', 'odd', 'parts6'])
+def test_dsgfd_kl_cta_layouts(shape, layout, monkeypatch):
+    """Every way the streaming kernel can lay a column tile out over a CTA (DSKD_KL_TUNE: warps, row parts per column):
+    the production choices are 8 warps x 1 part (large batches) and 8 warps x 2 parts on half-size channel chunks (up to
+    4 images); a run of rows that crosses a part boundary is cut into two records there."""
+    cfg = dict(small=SMALL, odd=ODD, parts6=dict(num_query=60, k_range=(3, 8), **KL_TALL['parts6']))[shape]
+    cpu = synth.make_distill_inputs(num_images=2, num_prev=40, seed=21, channels=64, **cfg)
+    gpu = cpu.to(DEV)
+    chunk = 16 if layout != '1,1' else 2
+    monkeypatch.setenv('DSKD_KL_TUNE', f'2,4,{chunk},192,0,{layout}')
+    mod = dskd_b200.DSGFeatureDistillLoss(criterion='kl')
+    feats, hs = gpu.clone_student()
+    loss = mod(feats, gpu.teacher_feats, (hs, gpu.hs_teacher), gpu.assignments)
+    loss.backward()
+    # forward-only kernels (5-row blocks) split their rows the same way
+    monkeypatch.setenv('DSKD_KL_TUNE', f'2,5,{chunk},192,0,{layout}')
+    v2 = dskd_b200.DSGFeatureDistillLoss(criterion='kl', mask_mode='decode_v2')
+    loss_v2 = v2(gpu.student_feats, gpu.teacher_feats, (gpu.hs_student, gpu.hs_teacher), gpu.assignments)
+    torch.cuda.synchronize()
+    monkeypatch.delenv('DSKD_KL_TUNE')
+    loss_v2_default = v2(gpu.student_feats, gpu.teacher_feats, (gpu.hs_student, gpu.hs_teacher), gpu.assignments)
+    o_feats, o_hs = cpu.clone_student()
+    ref = oracle_decode(cpu, crit_oracle('kl'), 1, o_feats, o_hs)
+    ref.backward()
+    assert_kl_loss(loss, cpu, crit_oracle('kl'), ref)
+    assert_grad(hs.grad, o_hs.grad)
+    torch.testing.assert_close(loss_v2, loss_v2_default, rtol=2e-4, atol=0)   # both within 1e-4 of the exact value
+
+
 @pytest.mark.parametrize('nc', [2, 1], ids=['pairs', 'single'])
+@pytest.mark.parametrize('parts', [1, 2], ids=['whole_columns', 'row_parts'])
 @pytest.mark.parametrize('pool', [64, 12, 2], ids=['shared_pools', 'one_warp', 'redo'])
-def test_dsgfd_kl_many_runs_per_tile(pool, nc, monkeypatch):
+def test_dsgfd_kl_many_runs_per_tile(pool, parts, nc, monkeypatch):
     """Crowded images: more runs of rows per column tile than one warp's record pool holds.  With a small pool
     (DSKD_KL_TUNE) the CTA first runs fewer warps with several pools each and finally leaves the tile to the redo launch;
     all three must give the reference's numbers."""
     cpu = synth.make_distill_inputs(num_images=2, num_prev=40, seed=15, channels=32, num_query=100, k_range=(30, 40), **{
         k: v for k, v in SMALL.items() if k not in ('k_range', 'num_query')})
     gpu = cpu.to(DEV)
-    monkeypatch.setenv('DSKD_KL_TUNE', f'{nc},4,1,4,16,{pool},0')   # channels per pass, ..., pool records
+    monkeypatch.setenv('DSKD_KL_TUNE', f'{nc},4,16,{pool},0,0,{parts}')   # channels per pass, ..., pool records, ..., row parts
     mod = dskd_b200.DSGFeatureDistillLoss(criterion='kl')
     feats, hs = gpu.clone_student()
     loss = mod(feats, gpu.teacher_feats, (hs, gpu.hs_teacher), gpu.assignments)

@@ -1,9 +1,10 @@
 """Time the DSG-FD KL-over-H streaming kernel alone (CUDA events around `dskd_dsgfd_kl_fwd_bwd`, inputs larger than L2).
 
-    python tools/kl_perf.py [--images 16] [--iters 20] [--tune "2,5,2,2,16,256,0;1,5,2,4,16,256,0;..."]
+    python tools/kl_perf.py [--images 16] [--iters 20] [--tune "2,4,16,192,0,8,1;2,4,8,192,0,8,2;..."]
 coverage 'synth' = the bench's synthetic boxes, 'full' = one box covering each image (every byte is read).
---tune runs the box-mask case once per "channels_per_pass,rows_per_block,stages,ctas_per_sm,channels_per_cta,pool,dbg"
-setting (DSKD_KL_TUNE).
+--tune runs the box-mask case once per "channels_per_pass,rows_per_block,channels_per_cta,pool,dbg,warps,row_parts"
+setting (DSKD_KL_TUNE; rows_per_block is 4 for the gradient kernel and 5 for the forward-only one: the forward timing of
+a setting uses 5).
 """
 import argparse
 import os
@@ -124,8 +125,10 @@ def main():
         for setting in args.tune.split(';'):
             os.environ['DSKD_KL_TUNE'] = setting
             ms = time_call(lib, a, st, args.iters)
+            f = setting.split(',')
+            os.environ['DSKD_KL_TUNE'] = ','.join([f[0], '5'] + f[2:])
             msf = time_call(lib, af, st, args.iters)
-            print(f'tune {setting:18s}: grad {ms * 1e3:8.1f} us {alg / ms / 1e6:7.0f} GB/s   fwd {msf * 1e3:8.1f} us '
+            print(f'tune {setting:20s}: grad {ms * 1e3:8.1f} us {alg / ms / 1e6:7.0f} GB/s   fwd {msf * 1e3:8.1f} us '
                   f'{alg / msf / 1e6:7.0f} GB/s', flush=True)
         os.environ.pop('DSKD_KL_TUNE', None)
 

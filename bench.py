@@ -378,8 +378,10 @@ class StepBench:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return [float(x) for x in t.tolist()]
 
-    def run_eager(self, steps, warmup):
-        """(total ms, per-step streaming-kernel ms list, launches, loss): kernels issued one by one from Python."""
+    def run_eager(self, steps, warmup, kernel_events=True):
+        """(total ms, per-step streaming-kernel ms list, launches, loss): kernels issued one by one from Python.
+        kernel_events: the C side brackets the streaming kernel of every step with a CUDA event pair (the roofline's live
+        timing); off for the plain eager figure, which should not pay for event creation and four extra records per step."""
         from dskd_b200 import _lib, profiling
         lib = _lib.load()
         inp = self.inputs
@@ -387,7 +389,8 @@ class StepBench:
             self.step(self.s_feats, inp.teacher_feats, self.hs_s, inp.hs_teacher, overlap=False)
         self.barrier()
         launches0 = lib.dskd_launch_count()
-        profiling.start()       # C side records an event pair around the streaming kernel of every step
+        if kernel_events:
+            profiling.start()       # C side records an event pair around the streaming kernel of every step
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         self.barrier()
         e0.record()
@@ -395,7 +398,7 @@ class StepBench:
             loss = self.step(self.s_feats, inp.teacher_feats, self.hs_s, inp.hs_teacher, overlap=False)
         e1.record()
         self.barrier()
-        kernel_times = profiling.stop()
+        kernel_times = profiling.stop() if kernel_events else []
         return e0.elapsed_time(e1), kernel_times, lib.dskd_launch_count() - launches0, float(loss.detach())
 
     def capture(self):
@@ -600,7 +603,7 @@ def main():
             graph_ms = None
     clocks = sampler.stop() if rank == 0 else None
     # the eager figure once more without `nvidia-smi -lms` polling the driver next to the launches (it lengthens them)
-    eager_quiet_ms = sb.run_eager(args.steps, args.warmup)[0]
+    eager_quiet_ms = sb.run_eager(args.steps, args.warmup, kernel_events=False)[0]
     elapsed_ms = graph_ms if graph_ms is not None else eager_ms
     elapsed_ms, eager_ms, eager_quiet_ms = sb.max_over_ranks(elapsed_ms, eager_ms, eager_quiet_ms)
     kernel_ms = statistics.mean(kernel_times) if kernel_times else float('nan')
@@ -745,7 +748,8 @@ def main():
                   'ms_per_step': eager_quiet_ms / args.steps, 'ms_per_step_under_clock_sampler': eager_ms / args.steps,
                   'note': 'the two module calls + backward issued from Python on one stream (no graph, no side stream); '
                           'host-issue bound; measured again after the nvidia-smi clock sampler has stopped (its driver '
-                          'polling lengthens every launch)', 'graph_error': graph_err},
+                          'polling lengthens every launch) and without the per-step CUDA event pair that times the '
+                          'streaming kernel for `roofline`', 'graph_error': graph_err},
         'clocks': clocks,
         'loss': loss_value,
         'parity_note': PARITY_NOTE,

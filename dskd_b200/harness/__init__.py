@@ -3,4 +3,5 @@ distillation hot path in a 40+40 incremental training step.  The detector itself
 random init, no parity claim -- the reference's transformer needs mmcv's CUDA op, which is absent); what is under test
 is the drop-in path: teacher keep-ids -> pseudo labels -> batched Hungarian assignment -> BCDD + DSG-FD modules."""
 from .model import GFLDeformableDETR  # noqa: F401
-from .train_step import IncrementalTrainStep, bench_train_step, make_student_teacher, synthetic_batch  # noqa: F401
+from .train_step import (DetectorTrunk, GraphedTeacher, IncrementalTrainStep, bench_train_step,  # noqa: F401
+                         graph_detectors, make_student_teacher, synthetic_batch)

@@ -99,8 +99,74 @@ def make_student_teacher(device, detections_per_image=30, num_prev=40, seed=0, *
     return student, teacher
 
 
+_TRUNK_KEYS = ('cls', 'box', 'hs')
+
+
+class DetectorTrunk(nn.Module):
+    """The detector as a tensors-in / tensors-out module (what `torch.cuda.make_graphed_callables` can capture): returns
+    (neck level 0..3, cls, box, hs); `as_outputs` turns that back into the dict the step consumes."""
+
+    def __init__(self, model):
+        super().__init__()
+        self.model = model
+
+    def forward(self, img):
+        o = self.model(img)
+        return (*o['neck_feats'], *(o[k] for k in _TRUNK_KEYS))
+
+    @staticmethod
+    def as_outputs(flat):
+        nl = len(flat) - len(_TRUNK_KEYS)
+        out = dict(zip(_TRUNK_KEYS, flat[nl:]))
+        out['neck_feats'] = tuple(flat[:nl])
+        return out
+
+
+class GraphedTeacher:
+    """The frozen teacher's forward as ONE CUDA-graph replay: static shapes, no gradient, identical every iteration.  The
+    outputs are static tensors that the next replay overwrites (the step consumes them before it calls again)."""
+
+    def __init__(self, teacher, sample_img):
+        self.teacher = teacher      # the graph bakes the parameters' addresses in: the module must outlive it
+        self.static_img = sample_img.detach().clone()
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.no_grad(), torch.cuda.stream(side):
+            for _ in range(2):      # lazy tables (sampling-offset normalisers, cuDNN plans) are built outside the capture
+                teacher(self.static_img)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            self.out = teacher(self.static_img)
+
+    def __call__(self, img):
+        if img.shape != self.static_img.shape:
+            raise ValueError(f'the teacher graph was captured for images of shape {tuple(self.static_img.shape)}')
+        self.static_img.copy_(img)
+        self.graph.replay()
+        return self.out
+
+
+def graph_detectors(student, teacher, sample_img):
+    """CUDA graphs for the static-shape parts of the step: the teacher forward (one graph) and the student detector's
+    forward and backward (`torch.cuda.make_graphed_callables`: one graph each, parameters stay ordinary autograd leaves, so
+    DDP and the optimizer see nothing new).  The heads' losses stay eager: the number of teacher detections changes the
+    shapes there every iteration.  Returns (student trunk, teacher callable); wrap the trunk in DDP AFTER this call."""
+    # the parameters' AccumulateGrad nodes are first touched on the capture side stream; later backward passes run on the
+    # caller's stream, which is intended (the replay is ordered on that stream)
+    if hasattr(torch.autograd.graph, 'set_warn_on_accumulate_grad_stream_mismatch'):
+        torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+    g_teacher = GraphedTeacher(teacher, sample_img)
+    trunk = torch.cuda.make_graphed_callables(DetectorTrunk(student), (sample_img.detach().clone(),))
+    return trunk, g_teacher
+
+
 class IncrementalTrainStep:
-    """student / teacher + the drop-in distillation path + AdamW: `step(img, gt_bboxes, gt_labels)` runs one iteration."""
+    """student / teacher + the drop-in distillation path + AdamW: `step(img, gt_bboxes, gt_labels)` runs one iteration.
+    `student` is a GFLDeformableDETR or a (graphed) DetectorTrunk of one, bare or wrapped in DDP; `teacher` any callable
+    returning the detector's output dict."""
 
     def __init__(self, student, teacher, num_prev=40, criterion='kl', lr=4e-4, sync_prototypes=False):
         self.student, self.teacher = student, teacher
@@ -116,7 +182,12 @@ class IncrementalTrainStep:
 
     @property
     def module(self):
-        return self.student.module if hasattr(self.student, 'module') else self.student
+        m = self.student.module if hasattr(self.student, 'module') else self.student      # DDP
+        return m.model if isinstance(m, DetectorTrunk) else m
+
+    def _student_forward(self, img):
+        out = self.student(img)
+        return out if isinstance(out, dict) else DetectorTrunk.as_outputs(out)
 
     def step(self, img, gt_bboxes, gt_labels):
         N, _, H, W = img.shape
@@ -124,7 +195,7 @@ class IncrementalTrainStep:
         img_shapes = [(H, W)] * N
         with torch.no_grad():
             t = self.teacher(img)
-        s = self.student(img)      # queued behind the teacher before the keep-ids' one host sync drains the stream
+        s = self._student_forward(img)      # queued behind the teacher before the keep-ids' one host sync drains the stream
         with torch.no_grad():
             tinfo = teacher_info_from_outputs(t['cls'][-1], t['box'][-1], img_shapes, score_thr=0.3, max_per_img=100)
         # hard + teacher-first pseudo labels (head_il.py:462-465)
@@ -173,21 +244,29 @@ def synthetic_batch(device, images, height=800, width=1333, seed=1234):
 
 
 def bench_train_step(device, rank, world, dist, images_per_gpu=4, criterion='kl', steps=3, warmup=2, height=800, width=1333,
-                     backbone='resnet50'):
+                     backbone='resnet50', graphs=True):
     """Time the 40+40 incremental training step on synthetic data (bench.py's `train_step` key, tools/train_step_bench.py):
     CUDA events around `steps` iterations after `warmup`, max over ranks; DDP (gradient mean) + prototype all-reduce when
-    world > 1, like tools/train_increment.py:299-304."""
+    world > 1, like tools/train_increment.py:299-304.  graphs: teacher forward and student detector forward / backward as
+    CUDA graphs (`graph_detectors`); if the capture fails the step runs eagerly and the error is reported."""
     tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
     torch.backends.cuda.matmul.allow_tf32 = True
     torch.backends.cudnn.allow_tf32 = True
     try:
         student, teacher = make_student_teacher(device, backbone=backbone)
         student.train()
+        img, gt_b, gt_l = synthetic_batch(device, images_per_gpu, height, width, seed=1234 + rank)
+        launch = 'eager'
+        if graphs:
+            try:
+                student, teacher = graph_detectors(student, teacher, img)
+                launch = 'cuda graphs: teacher forward, student detector forward + backward; heads / losses / optimizer eager'
+            except Exception as exc:        # noqa: BLE001 -- report, fall back to eager launches
+                launch = f'eager (graph capture failed: {type(exc).__name__}: {str(exc)[:200]})'
         if world > 1:
             # every parameter of the detector receives a gradient in this step (DDP itself reports so)
             student = torch.nn.parallel.DistributedDataParallel(student, device_ids=[device.index], broadcast_buffers=False)
         trainer = IncrementalTrainStep(student, teacher, num_prev=40, criterion=criterion, sync_prototypes=world > 1)
-        img, gt_b, gt_l = synthetic_batch(device, images_per_gpu, height, width, seed=1234 + rank)
         out = None
         for _ in range(max(warmup, 1)):
             out = trainer.step(img, gt_b, gt_l)
@@ -209,7 +288,7 @@ def bench_train_step(device, rank, world, dist, images_per_gpu=4, criterion='kl'
                 'dtype': 'f32 (tf32 matmul/conv)', 'data': 'synthetic',
                 'config': {'workload': 'coco_40+40_incremental_train_step', 'images_per_gpu': images_per_gpu,
                            'image': [height, width], 'backbone': backbone, 'criterion': criterion, 'queries': 300,
-                           'decoder_layers': 6, 'parallelism': f'dp{world}'},
+                           'decoder_layers': 6, 'parallelism': f'dp{world}', 'launch': launch},
                 'losses': {k: float(v) for k, v in out.items()},
                 'peak_mem_gb': torch.cuda.max_memory_allocated(device) / 2 ** 30}
     finally:

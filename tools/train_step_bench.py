@@ -29,6 +29,7 @@ def main():
     ap.add_argument('--height', type=int, default=800)
     ap.add_argument('--width', type=int, default=1333)
     ap.add_argument('--backbone', default='resnet50')
+    ap.add_argument('--no-graphs', action='store_true', help='eager launches for the detectors too')
     args = ap.parse_args()
     import torch.distributed as dist
     from dskd_b200.harness import bench_train_step
@@ -42,7 +43,8 @@ def main():
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=dev)
     line = bench_train_step(dev, rank, world, dist, images_per_gpu=args.images_per_gpu, criterion=args.criterion,
-                            steps=args.steps, warmup=args.warmup, height=args.height, width=args.width, backbone=args.backbone)
+                            steps=args.steps, warmup=args.warmup, height=args.height, width=args.width, backbone=args.backbone,
+                            graphs=not args.no_graphs)
     if rank == 0:
         line.update({'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None})
         print(json.dumps(line), flush=True)

@@ -181,7 +181,8 @@ def require_device(t: torch.Tensor):
 
 
 def ptr(t):
-    return None if t is None else C.c_void_p(t.data_ptr())
+    """Device address for a `void*` argument (ctypes converts the int; None is NULL)."""
+    return None if t is None else t.data_ptr()
 
 
 def _first_cuda_tensor(obj, depth=0):

@@ -1113,7 +1113,12 @@ extern "C" int dskd_dsgfd_kl_fwd_bwd(const DskdDsgfdKlArgs* a, void* stream) {
   }
   prm.block_start[a->num_levels] = blocks;
   prm.num_blocks = blocks;
-  const size_t smem = KlSmem(prm.max_blocks, blk, grad, cap, 1 + 2 * nc, nwarps, rsplit > 1 ? 3 * nc : 0).total;
+  size_t smem = KlSmem(prm.max_blocks, blk, grad, cap, 1 + 2 * nc, nwarps, rsplit > 1 ? 3 * nc : 0).total;
+  if (smem > 227 * 1024 && nwarps > kKlWarps) {  // very tall levels: the 8-warp layout needs half the record pools
+    nwarps = kKlWarps;
+    prm.rsplit = rsplit = 1;
+    smem = KlSmem(prm.max_blocks, blk, grad, cap, 1 + 2 * nc, nwarps, 0).total;
+  }
   DSKD_REQUIRE(smem <= 227 * 1024, "dsgfd_kl: H (%d) needs %zu bytes of shared memory", max_h, smem);
   bool launched = false;
 #define DSKD_KL_VARIANT(CELLV, GRADV, NCV, RV)                                                                  \

@@ -133,6 +133,14 @@ class GFLDeformableDETR(nn.Module):
         nn.init.constant_(self.reg_branch[-1].bias, 0.)
         nn.init.constant_(self.reg_branch[-1].bias.data[2:], -2.0)
         self.dim, self.num_query, self.num_classes, self.reg_max = dim, num_query, num_classes, reg_max
+        self.channels_last = False
+
+    def use_channels_last(self):
+        """NHWC convolutions for backbone and neck (cuDNN's tensor-core layout: no internal transposes); the neck outputs
+        keep NCHW shapes with NHWC strides, the loss modules make them contiguous where they need to."""
+        self.to(memory_format=torch.channels_last)
+        self.channels_last = True
+        return self
 
     def train(self, mode=True):
         super().train(mode)
@@ -142,6 +150,8 @@ class GFLDeformableDETR(nn.Module):
         return self
 
     def extract_feat(self, img):
+        if self.channels_last:
+            img = img.contiguous(memory_format=torch.channels_last)
         x = self.layer1(self.stem(img))
         c3 = self.layer2(x)
         c4 = self.layer3(c3)

@@ -244,7 +244,7 @@ def synthetic_batch(device, images, height=800, width=1333, seed=1234):
 
 
 def bench_train_step(device, rank, world, dist, images_per_gpu=4, criterion='kl', steps=3, warmup=2, height=800, width=1333,
-                     backbone='resnet50', graphs=True):
+                     backbone='resnet50', graphs=True, channels_last=False):
     """Time the 40+40 incremental training step on synthetic data (bench.py's `train_step` key, tools/train_step_bench.py):
     CUDA events around `steps` iterations after `warmup`, max over ranks; DDP (gradient mean) + prototype all-reduce when
     world > 1, like tools/train_increment.py:299-304.  graphs: teacher forward and student detector forward / backward as
@@ -255,6 +255,9 @@ def bench_train_step(device, rank, world, dist, images_per_gpu=4, criterion='kl'
     try:
         student, teacher = make_student_teacher(device, backbone=backbone)
         student.train()
+        if channels_last:
+            student.use_channels_last()
+            teacher.use_channels_last()
         img, gt_b, gt_l = synthetic_batch(device, images_per_gpu, height, width, seed=1234 + rank)
         launch = 'eager'
         if graphs:
@@ -288,7 +291,8 @@ def bench_train_step(device, rank, world, dist, images_per_gpu=4, criterion='kl'
                 'dtype': 'f32 (tf32 matmul/conv)', 'data': 'synthetic',
                 'config': {'workload': 'coco_40+40_incremental_train_step', 'images_per_gpu': images_per_gpu,
                            'image': [height, width], 'backbone': backbone, 'criterion': criterion, 'queries': 300,
-                           'decoder_layers': 6, 'parallelism': f'dp{world}', 'launch': launch},
+                           'decoder_layers': 6, 'parallelism': f'dp{world}', 'launch': launch,
+                           'conv_layout': 'channels_last' if channels_last else 'nchw'},
                 'losses': {k: float(v) for k, v in out.items()},
                 'peak_mem_gb': torch.cuda.max_memory_allocated(device) / 2 ** 30}
     finally:

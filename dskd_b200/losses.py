@@ -169,6 +169,8 @@ def _scale_by_grad_output(buf: Optional[torch.Tensor], grad_out: torch.Tensor):
 
 
 def _as_scalar_grad(grad_out: torch.Tensor):
+    if grad_out.dtype is torch.float32 and grad_out.dim() == 0:      # the usual case: d(loss) of a scalar fp32 loss
+        return grad_out
     g = grad_out.detach()
     if g.dtype != torch.float32:
         g = g.float()

@@ -133,6 +133,8 @@ KL_TALL = {
     'parts6': dict(levels=((130, 36), (65, 18), (33, 9), (17, 5)), img_hw=(1040, 288)),
     'parts10': dict(levels=((230, 33), (115, 17), (58, 9), (29, 5)), img_hw=(1840, 264)),
     'strips': dict(levels=((420, 9), (210, 5), (105, 3), (53, 2)), img_hw=(3360, 72)),
+    # 177 KB of owner table: the 16-warp small-batch layout does not fit beside it, the launcher falls back to 8 warps
+    'very_tall': dict(levels=((1300, 3), (650, 2), (325, 1), (163, 1)), img_hw=(10400, 24)),
 }
 
 

@@ -29,6 +29,7 @@ def main():
     ap.add_argument('--height', type=int, default=800)
     ap.add_argument('--width', type=int, default=1333)
     ap.add_argument('--backbone', default='resnet50')
+    ap.add_argument('--channels-last', action='store_true', help='NHWC convolutions in backbone and neck')
     ap.add_argument('--no-graphs', action='store_true', help='eager launches for the detectors too')
     args = ap.parse_args()
     import torch.distributed as dist
@@ -44,7 +45,7 @@ def main():
         dist.init_process_group('nccl', device_id=dev)
     line = bench_train_step(dev, rank, world, dist, images_per_gpu=args.images_per_gpu, criterion=args.criterion,
                             steps=args.steps, warmup=args.warmup, height=args.height, width=args.width, backbone=args.backbone,
-                            graphs=not args.no_graphs)
+                            graphs=not args.no_graphs, channels_last=args.channels_last)
     if rank == 0:
         line.update({'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None})
         print(json.dumps(line), flush=True)

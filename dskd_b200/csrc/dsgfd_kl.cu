@@ -27,6 +27,7 @@ namespace dskd {
 constexpr int kKlWarps = 8;       // warps per CTA of the redo kernel, and of the streaming kernel for large batches
 constexpr int kKlMaxWarps = 16;   // streaming kernel: (channels per CTA / channels per pass) x row parts, at most
 constexpr int kKlMaxSplit = 4;    // row parts of a column at most
+constexpr int kKlPre = 16;        // owner rows a lane fetches at once in the prologue
 // Measured on B200 (tools/kl_perf.py --tune, 16 images of 800x1333): two channels per pass, 4-row blocks loaded and consumed
 // in place (no register ring), 4 CTAs x 8 warps per SM at 64 registers: 139 us; with a 2-stage ring at 127 registers
 // (2 CTAs per SM) 168 us; one channel per pass (5-row blocks, 2 stages, 4 CTAs per SM) 169 us.
@@ -505,13 +506,14 @@ __global__ void __launch_bounds__(32 * kKlMaxWarps, 2) dsgfd_kl_stream_kernel(co
       if (CELL) return __float_as_int(__ldg(prm.cell_weight + cell0 + (int64_t)h * W));
       return __ldg(prm.owner + cell0 + (int64_t)h * W);
     };
+    // kKlPre rows in flight per lane: at 100 rows and 8 warps the whole share of a warp is one batch, one L2 latency
     int o = h0 < h1 ? fetch(h0) : -1;
-    for (int h = h0; h < h1; h += 4) {
-      int nx[4];
+    for (int h = h0; h < h1; h += kKlPre) {
+      int nx[kKlPre];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) nx[u] = fetch(h + u + 1);
+      for (int u = 0; u < kKlPre; ++u) nx[u] = (h + u < h1) ? fetch(h + u + 1) : -1;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < kKlPre; ++u) {
         if (h + u < h1) {
           bool on, end = false;
           if (CELL) {

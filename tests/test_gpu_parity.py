@@ -54,10 +54,10 @@ def oracle_decode_f64(cpu, crit_mod):
 KL_RTOL_VS_FP32 = 1e-3
 
 
-def assert_kl_loss(got, cpu, crit_mod, ref32):
+def assert_kl_loss(got, cpu, crit_mod, ref32, rtol32=KL_RTOL_VS_FP32):
     ref64, _ = oracle_decode_f64(cpu, crit_mod)
     torch.testing.assert_close(got.detach().cpu().double(), ref64, rtol=LOSS_RTOL, atol=1e-12)
-    torch.testing.assert_close(got.detach().cpu().double(), ref32.detach().double(), rtol=KL_RTOL_VS_FP32, atol=1e-12)
+    torch.testing.assert_close(got.detach().cpu().double(), ref32.detach().double(), rtol=rtol32, atol=1e-12)
 
 
 def oracle_decode(cpu, crit_mod, version=1, feats=None, hs=None):
@@ -151,7 +151,9 @@ def test_dsgfd_kl_tall_levels_and_temperatures(shape, T):
     o_feats, o_hs = cpu.clone_student()
     ref = oracle_decode(cpu, crit_oracle('kl', 'sum', 1.0, T), 1, o_feats, o_hs)
     ref.backward()
-    assert_kl_loss(loss, cpu, crit_oracle('kl', 'sum', 1.0, T), ref)
+    # the fp32 evaluation of the reference formula loses accuracy with the column height (softmax over H rows): at
+    # H = 1300 it is 1.2e-3 off the float64 value, which the kernel matches to 1e-4
+    assert_kl_loss(loss, cpu, crit_oracle('kl', 'sum', 1.0, T), ref, rtol32=5e-3 if shape == 'very_tall' else KL_RTOL_VS_FP32)
     assert_grad(hs.grad, o_hs.grad)
 
 

@@ -736,7 +736,7 @@ def main():
         'config': {'workload': WORKLOAD if args.criterion == 'mse' else WORKLOAD.replace('mse', 'kl'), 'images_per_gpu': N,
                    'global_batch': world * N, 'num_prev': args.num_prev,
                    'criterion': args.criterion, 'levels': [[100, 167], [50, 84], [25, 42], [13, 21]], 'channels': 256,
-                   'queries': 300, 'parallelism': f'dp{world}', 'prototype_allreduce': world > 1,
+                   'queries': 300, 'parallelism': f'dp{world}', 'prototype_allreduce': prototype_transport(world),
                    'launch': 'cuda_graph_replay' if graph_ms is not None else 'eager',
                    'graph_policy': graph_policy if graph_ms is not None else None,
                    'cache': f'inputs larger than L2: {2 * N * 22.76:.0f} MB of features read per step vs 126 MB L2'},
@@ -764,6 +764,15 @@ def main():
     leave(world, dist)
 
 
+def prototype_transport(world):
+    """How the BCDD prototype tables were summed over the ranks in this run."""
+    if world <= 1:
+        return False
+    from dskd_b200 import peer
+    return ('one kernel over NVLink peer memory (dskd_peer_allreduce)' if peer._exchanges
+            else 'NCCL all-reduce (peer memory unavailable or DSKD_PROTO_TRANSPORT=nccl)')
+
+
 def leave(world, dist):
     """End of a multi-rank run: every CUDA graph that captured the NCCL all-reduce has been dropped by now (StepBench.
     run_graph deletes its exec and torch graph), so the process group can be destroyed normally.  A watchdog still ends the
@@ -774,6 +783,9 @@ def leave(world, dist):
     torch.cuda.synchronize()
     dist.barrier()
     torch.cuda.synchronize()
+    from dskd_b200 import peer
+    peer.close_all()            # unmap the peers' NVLink buffers while everybody is still alive
+    dist.barrier()
     sys.stdout.flush()
     sys.stderr.flush()
 

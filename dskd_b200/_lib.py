@@ -115,6 +115,10 @@ SIGNATURES = {
     'dskd_f64_to_f32': [vp, vp, i32, f32, vp],
     'dskd_msda_forward': [vp, vp, i32, vp, vp, i32, i64, i32, i32, i64, i32, vp, vp],
     'dskd_msda_backward': [vp, vp, i32, vp, vp, vp, i32, i64, i32, i32, i64, i32, vp, vp, vp, vp],
+    'dskd_ipc_export': [vp, vp, C.POINTER(i64)],
+    'dskd_ipc_open': [vp, C.POINTER(vp)],
+    'dskd_ipc_close': [vp],
+    'dskd_peer_allreduce': [vp, i64, C.POINTER(vp), i32, i32, vp],
 }
 
 _lib = None
@@ -148,6 +152,8 @@ def load():
     lib.dskd_dsgfd_kl_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.POINTER(Level), C.c_int32]
     lib.dskd_qmem_workspace_bytes.restype = C.c_int64
     lib.dskd_qmem_workspace_bytes.argtypes = [C.c_int32, C.c_int64, C.c_int32, C.c_int32]
+    lib.dskd_peer_buffer_floats.restype = C.c_int64
+    lib.dskd_peer_buffer_floats.argtypes = [C.c_int64]
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes

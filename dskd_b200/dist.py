@@ -6,8 +6,9 @@ rank-local prototypes (gfl_deformable_detr_head_il.py:531-551).  The only cross-
 adds is the optional global prototype table: ONE all-reduce(sum) of the [2, num_classes, C+1] fp32 sums +
 counts between `dskd_bcdd_prototypes` and `dskd_bcdd_loss_and_grad`.
 
-Nothing here touches CUDA directly, so the same code runs under `gloo` on CPU tensors (tests/test_dist_gloo.py,
-world_size 2) and under NCCL over NVLink on the B200 box.
+The CPU-tensor path touches nothing but torch.distributed, so the same code runs under `gloo` (tests/test_dist_gloo.py,
+world_size 2); CUDA tables on one NVLink box go through the library's own peer-memory kernel (dskd_b200/peer.py), anything
+else through the NCCL all-reduce.
 """
 from typing import Optional, Sequence, Tuple
 
@@ -59,6 +60,14 @@ def allreduce_prototypes(proto: torch.Tensor, group=None, async_op: bool = False
         return 1.0, None
     if proto.dtype != torch.float32 or not proto.is_contiguous():
         raise ValueError('prototype table must be contiguous fp32')
+    if proto.is_cuda and not async_op:
+        # one kernel over NVLink peer memory instead of an NCCL launch (dskd_b200/peer.py); None when the ranks do not all
+        # sit on one host with peer access -- the same decision on every rank
+        from . import peer
+        exchange = peer.exchange_for(proto, group)
+        if exchange is not None:
+            exchange.allreduce(proto)
+            return float(dist.get_world_size(group)), None
     work = dist.all_reduce(proto, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
     return float(dist.get_world_size(group)), (work if async_op else None)
 

@@ -416,6 +416,29 @@ int dskd_graph_instantiate_prioritized(void* graph, int32_t big_grid_ctas, void*
 int dskd_graph_launch(void* exec, void* stream);
 int dskd_graph_exec_destroy(void* exec);
 
+/* ---------------------------------------------------------------------------------------------
+ * The exchange step of SURVEY.md section 8e over NVLink / NVSwitch peer memory (no reference counterpart: the reference's
+ * prototypes are rank-local, gfl_deformable_detr_head_il.py:531-551; north_star asks for global ones).  One process per
+ * GPU: every rank allocates a "symmetric" buffer of dskd_peer_buffer_floats(table_floats) floats, ZERO-FILLED, exports
+ * it with dskd_ipc_export (CUDA IPC handle of the allocation that holds the pointer + the pointer's byte offset in it),
+ * the handles travel through the caller's own channel (torch.distributed), and every rank maps the others with
+ * dskd_ipc_open (+ offset).  dskd_peer_allreduce then replaces `d_table` ([table_floats] fp32, a multiple of 4, 16-byte
+ * aligned) by its sum over ranks in ONE kernel launch: publish into the own buffer, raise a flag in every peer's buffer,
+ * wait for all flags, add the peers' tables in rank order (the result is bit-identical on every rank).  `bufs` is a HOST
+ * array of `world` device pointers (entry `rank` = the own buffer).  Collective: every rank must call it the same number
+ * of times; asynchronous on `stream`, capturable in a CUDA graph; a peer that does not arrive within about twenty seconds
+ * makes the kernel trap.
+ * ------------------------------------------------------------------------------------------- */
+#define DSKD_PEER_MAX_WORLD 16
+#define DSKD_PEER_CTRL_FLOATS 64 /* control words in front of the two table slots of a symmetric buffer */
+#define DSKD_IPC_HANDLE_BYTES 64
+int dskd_ipc_export(const void* d_ptr, void* handle_out /* DSKD_IPC_HANDLE_BYTES */, int64_t* offset_out);
+int dskd_ipc_open(const void* handle, void** base_out);
+int dskd_ipc_close(void* base);
+int64_t dskd_peer_buffer_floats(int64_t table_floats);
+int dskd_peer_allreduce(float* d_table, int64_t table_floats, void* const* bufs, int32_t world, int32_t rank,
+                        void* stream);
+
 /* x[i] *= *d_factor for i<n, skipped entirely when *d_factor == 1.0f (read on the device: no host
  * sync).  Used by autograd backward to apply grad_output to gradients staged by the fused kernels. */
 int dskd_scale_inplace(float* d_x, int64_t n, const float* d_factor, void* stream);

@@ -30,7 +30,7 @@ def test_binding_table_matches_header():
     names = set(declared_functions())
     bound = set(_lib.SIGNATURES) | {'dskd_last_error', 'dskd_launch_count', 'dskd_dsgfd_step_workspace_bytes',
                                    'dskd_dsgfd_step_workspace_bytes_for', 'dskd_dsgfd_kl_workspace_bytes',
-                                   'dskd_qmem_workspace_bytes', 'dskd_struct_size'}
+                                   'dskd_qmem_workspace_bytes', 'dskd_struct_size', 'dskd_peer_buffer_floats'}
     assert names == bound, (sorted(names - bound), sorted(bound - names))
 
 

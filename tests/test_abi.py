@@ -65,3 +65,24 @@ def test_struct_layout_matches_c():
     assert lib.dskd_struct_size(99) == -1
     # 300 queries -> two blocks of 160 resident rows; 100 -> one block of 112
     assert lib.dskd_qmem_workspace_bytes(2, 22223, 256, 300) > lib.dskd_qmem_workspace_bytes(2, 22223, 256, 100) > 0
+
+
+def test_peer_exchange_entry_points_validate_their_arguments():
+    """Host-side checks of the NVLink prototype exchange (csrc/peer.cu): buffer sizing and argument validation happen
+    before any CUDA call, so they run without a GPU."""
+    lib = _lib.load()
+    table = 2 * 80 * 257
+    assert lib.dskd_peer_buffer_floats(table) == 64 + 2 * table           # control words + two slots
+    assert lib.dskd_peer_buffer_floats(41121) == 64 + 2 * 41124           # slots are padded to 4 floats
+    assert lib.dskd_peer_buffer_floats(0) == -1
+    assert lib.dskd_ipc_export(None, None, None) == _lib.EINVAL
+    assert b'dskd_ipc_export' in lib.dskd_last_error()
+    assert lib.dskd_ipc_open(None, None) == _lib.EINVAL
+    assert lib.dskd_ipc_close(None) == _lib.OK
+    bufs = (ctypes.c_void_p * 2)(0x1000, 0x2000)
+    assert lib.dskd_peer_allreduce(None, table, bufs, 2, 0, None) == _lib.EINVAL
+    assert lib.dskd_peer_allreduce(0x1000, table, bufs, 17, 0, None) == _lib.EINVAL     # world above DSKD_PEER_MAX_WORLD
+    assert lib.dskd_peer_allreduce(0x1000, table, bufs, 2, 2, None) == _lib.EINVAL      # rank outside the world
+    assert lib.dskd_peer_allreduce(0x1000, table + 1, bufs, 2, 0, None) == _lib.EINVAL  # not a multiple of 4 floats
+    bad = (ctypes.c_void_p * 2)(0x1000, 0)
+    assert lib.dskd_peer_allreduce(0x1000, table, bad, 2, 0, None) == _lib.EINVAL       # a peer that was never mapped

@@ -312,6 +312,45 @@ def gen_assign():
     save('assign.npz', d)
 
 
+def run_head_fg_bk(seed=21):
+    """The area-mask MSE of the sibling head file (gfl_deformable_detr_head_il_fg_bk.py:534-578,611-625) through that
+    head's own `loss`: same seeded inputs as the other seed-21 cases, teacher detections from the same
+    `_get_bboxes_single`; stores loss_fg_feature and its gradient w.r.t. the student's encoder memory."""
+    from mmdet.models.dense_heads.gfl_deformable_detr_head_il_fg_bk import GFLDeformableDETRHead_il as HeadFgBk
+    inp = head_inputs(seed)
+    N, Q = inp['s_cls'].shape[1:3]
+    img_metas = [dict(img_shape=(inp['img_hw'][0], inp['img_hw'][1], 3), scale_factor=1.0)] * N
+    il = make_head('corr + fg_info + decode_v1', MSELoss(reduction='sum', loss_weight=1.0),
+                   MSELoss(reduction='mean', loss_weight=1.0))
+    teacher_cfg = dict(min_bbox_size=0, score_thr=0.3, max_per_img=100)
+    outs = [il._get_bboxes_single(inp['t_cls'][-1][i], inp['t_box'][-1][i], img_metas[i]['img_shape'],
+                                  1.0, rescale=False, cfg=teacher_cfg, need_logits=True) for i in range(N)]
+    pred_bboxes = [o[0][:, 0:4].detach() for o in outs]
+    pred_keepid = torch.cat([o[3].detach() + i * Q for i, o in enumerate(outs)])
+    h = object.__new__(HeadFgBk)
+    torch.nn.Module.__init__(h)
+    for k, v in il.__dict__.items():                      # the attributes `loss` / `loss_single` touch
+        if not k.startswith('_'):
+            setattr(h, k, v)
+    for k, v in il._modules.items():
+        setattr(h, k, v)
+    h.cates_distill, h.locat_distill, h.feats_distill = '', '', 'fg_info'
+    spatial_shapes = torch.tensor(inp['levels'], dtype=torch.long)
+    t_memory = torch.cat([f.flatten(2) for f in inp['t_feats']], 2).permute(2, 0, 1).contiguous()
+    s_mem = torch.cat([f.flatten(2) for f in inp['s_feats']], 2).permute(2, 0, 1).contiguous().requires_grad_(True)
+    teacher_info = dict(neck_feats=tuple(inp['t_feats']),
+                        head_outs=(inp['t_cls'], inp['t_box'], (t_memory, spatial_shapes), inp['hs_t']),
+                        pred_keepid=pred_keepid, pred_bboxes=pred_bboxes)
+    losses = h.loss(inp['s_cls'], inp['s_box'], (s_mem, spatial_shapes), None,
+                    [b.clone() for b in inp['gt_bboxes']], [l.clone() for l in inp['gt_labels']],
+                    img_metas, gt_bboxes_ignore=None, student_feat=[], teacher_info=teacher_info)
+    lf = losses['loss_fg_feature']
+    g_mem, = torch.autograd.grad(lf, [s_mem])
+    out = dict(seed=np.int64(seed), pred_bboxes=pred_bboxes, pred_keepid=pred_keepid, loss_fg_feature=lf)
+    out['fg.grad_mem'] = g_mem
+    save('head_fg_bk_mse.npz', out)
+
+
 def gen_incremental_settings():
     """BASELINE.json configs 3-4: the 50+30 and 60+20 settings (w_cls = 2.0 like the 40+40 config,
     chaosuan_gfl_deformable_detr_50/60_r50_8x4_1x_qoqo_il.py) through the unmodified head, KL criterion."""
@@ -325,6 +364,14 @@ if __name__ == '__main__':
     torch.set_num_threads(4)
     if sys.argv[1:] == ['incremental']:          # only the files added in round 2 (the others stay byte-identical)
         gen_incremental_settings()
+        sys.exit(0)
+    if sys.argv[1:] == ['kl_variants']:          # round 2: the shipped KL criterion through the sibling masks
+        _saved_inputs.add(21)                    # head_inputs_seed21.npz exists and stays byte-identical
+        run_head('fg_only', 'kl')
+        run_head('decode_v2', 'kl')
+        sys.exit(0)
+    if sys.argv[1:] == ['fg_bk']:                # round 2: the sibling head file's area-mask MSE
+        run_head_fg_bk()
         sys.exit(0)
     gen_losses()
     gen_boxes()

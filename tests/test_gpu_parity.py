@@ -475,7 +475,11 @@ GOLDEN_CASES = [('head_decode_v1_mse.npz', 'decode_v1', 'mse', 'neck'),
                 ('head_sg_out_mse.npz', 'sg_out', 'mse', 'memory'),
                 ('head_sg_out_kl.npz', 'sg_out', 'kl', 'neck'),
                 ('head_sg_out_kl.npz', 'sg_out', 'kl', 'memory'),     # the layout the reference views (head_il.py:879-880)
-                ('head_fg_only_mse.npz', 'fg_only', 'mse', 'memory')]
+                ('head_fg_only_mse.npz', 'fg_only', 'mse', 'memory'),
+                # the shipped KL criterion through the sibling masks (no gradient: constant mask, detached target)
+                ('head_fg_only_kl.npz', 'fg_only', 'kl', 'neck'),
+                ('head_fg_only_kl.npz', 'fg_only', 'kl', 'memory'),
+                ('head_decode_v2_kl.npz', 'decode_v2', 'kl', 'neck')]
 
 
 @pytest.mark.parametrize('name,mode,crit,source', GOLDEN_CASES)
@@ -513,6 +517,23 @@ def test_cuda_path_vs_reference_outputs(name, mode, crit, source):
     if source == 'neck' and not out.v('fg.grad_feats_is_none'):
         for got, ref in zip(grads[1:], out.lst('fg.grad_feats')):
             assert_grad(got, ref)
+
+
+def test_fg_bk_vs_reference_outputs():
+    """The sibling head file's area-mask MSE on encoder memory (_fg_bk.py:534-578,611-625), outputs of that head's own
+    `loss` (tests/golden/gen_golden.py fg_bk): loss and the gradient of the student's memory."""
+    inp, out = load_head_case('head_fg_bk_mse.npz')
+    N = inp.t('s_cls').shape[1]
+    img_hw = tuple(inp.t('img_hw').tolist())
+    a = dict(teacher_bboxes=[b.to(DEV) for b in out.lst('pred_bboxes')], img_shapes=[img_hw] * N)
+    shapes = inp.t('levels')
+    s_mem = torch.cat([f.flatten(2) for f in inp.lst('s_feats')], 2).permute(2, 0, 1).contiguous().to(DEV).requires_grad_(True)
+    t_mem = torch.cat([f.flatten(2) for f in inp.lst('t_feats')], 2).permute(2, 0, 1).contiguous().to(DEV)
+    mod = dskd_b200.DSGFeatureDistillLoss(criterion='mse', mask_mode='fg_bk', feature_source='memory')
+    loss = mod((s_mem, shapes), (t_mem, shapes), None, a)
+    assert_loss(loss, out.t('loss_fg_feature'))
+    loss.backward()
+    assert_grad(s_mem.grad, out.t('fg.grad_mem'))
 
 
 def test_assignment_vs_reference_outputs():

@@ -167,12 +167,27 @@ def _head_oracle(inp, out, mode, crit):
                 s_feats=s_feats, s_mem=s_mem)
 
 
+def test_fg_bk_area_mask_mse_vs_reference():
+    """`_fg_bk.py:534-578,611-625` run by the sibling head file's own `loss` (gen_golden.py fg_bk): loss and d / d memory."""
+    inp, out = load_head_case('head_fg_bk_mse.npz')
+    levels = [tuple(x) for x in inp.t('levels').tolist()]
+    img_hw = tuple(inp.t('img_hw').tolist())
+    N = inp.t('s_cls').shape[1]
+    s_mem = torch.cat([f.flatten(2) for f in inp.lst('s_feats')], 2).permute(2, 0, 1).contiguous().requires_grad_(True)
+    t_mem = torch.cat([f.flatten(2) for f in inp.lst('t_feats')], 2).permute(2, 0, 1).contiguous()
+    loss = od.fg_bk(s_mem, t_mem, levels, out.lst('pred_bboxes'), [img_hw] * N, ol.MSELoss('sum', 1.0))
+    close(loss, out.t('loss_fg_feature'), 1e-5, 1e-7)
+    loss.backward()
+    close(s_mem.grad, out.t('fg.grad_mem'), 1e-4, 1e-7)
+
+
 HEAD_CASES = [('head_decode_v1_mse.npz', 'decode_v1', 'mse'), ('head_decode_v1_mse_n1.npz', 'decode_v1', 'mse'),
               ('head_decode_v1_kl.npz', 'decode_v1', 'kl'), ('head_decode_v1_kl_l70.npz', 'decode_v1', 'kl'),
               ('head_decode_v1_kl_l50.npz', 'decode_v1', 'kl'), ('head_decode_v1_kl_l60.npz', 'decode_v1', 'kl'),
               ('head_decode_v2_mse.npz', 'decode_v2', 'mse'), ('head_decode_v2_mse_n1.npz', 'decode_v2', 'mse'),
               ('head_sg_out_mse.npz', 'sg_out', 'mse'), ('head_sg_out_kl.npz', 'sg_out', 'kl'),
-              ('head_fg_only_mse.npz', 'fg_only', 'mse')]
+              ('head_fg_only_mse.npz', 'fg_only', 'mse'),
+              ('head_fg_only_kl.npz', 'fg_only', 'kl'), ('head_decode_v2_kl.npz', 'decode_v2', 'kl')]
 
 
 @pytest.mark.parametrize('name,mode,crit', HEAD_CASES)

@@ -668,7 +668,7 @@ def test_images_without_teacher_boxes_and_empty_batch_of_boxes():
     feats, hs = gpu.clone_student()
     loss = dskd_b200.DSGFeatureDistillLoss(criterion='mse')(feats, gpu.teacher_feats, (hs, gpu.hs_teacher), gpu.assignments)
     loss.backward()
-    assert float(loss) == 0.0 and all(float(f.grad.abs().max()) == 0.0 for f in feats)
+    assert float(loss.detach()) == 0.0 and all(float(f.grad.abs().max()) == 0.0 for f in feats)
 
 
 def test_validate_raises_like_reference_when_pairs_are_missing():

@@ -57,4 +57,4 @@ for mode, crit, src in CASES:
     ts.sort()
     ms = ts[len(ts) // 2]
     alg = (3 if crit == 'mse' else 2) * 22223 * 256 * 4 * N
-    print(f'{mode:10s} {crit:3s} {src:6s}: {ms * 1e3:8.1f} us  {N / ms * 1e3:9.0f} img/s  algorithmic {alg / ms / 1e6:7.0f} GB/s  loss {float(loss):.5g}', flush=True)
+    print(f'{mode:10s} {crit:3s} {src:6s}: {ms * 1e3:8.1f} us  {N / ms * 1e3:9.0f} img/s  algorithmic {alg / ms / 1e6:7.0f} GB/s  loss {float(loss.detach()):.5g}', flush=True)

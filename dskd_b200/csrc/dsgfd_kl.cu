@@ -174,6 +174,9 @@ struct KlChan {
   int base;            // records parked so far (warp-uniform)
 };
 
+// NB = row blocks in a register ring (the loads of NB - 1 blocks in flight ahead of the arithmetic).  The kernel instantiates
+// NB = 1 only: a block is loaded and consumed in place at 64 registers / 32 warps per SM; NB = 2 needed 127 registers and
+// was slower at half the warps.
 template <bool CELL, bool GRAD, int R, int NB>
 __device__ __forceinline__ void kl_stream_pass(const KlTables& tb, KlChan& ch, const unsigned W, const int lane,
                                                const int nact, const float kscale, const unsigned pool_addr,

@@ -8,6 +8,9 @@ waits for their flags and adds the tables up in rank order -- no NCCL kernel, no
 graph.  Set-up is collective and happens on the first call for a table size (outside any graph capture); it is used only
 when every rank sits on the same host, every pair of devices has peer access and the process group runs on NCCL --
 otherwise the caller keeps the NCCL all-reduce.  DSKD_PROTO_TRANSPORT=nccl switches it off.
+
+One exchange object serves every table of its size on a device, and its calls must be ordered on one stream at a time
+(the slots and counters belong to the sequence of calls, like an NCCL communicator's operations).
 """
 import ctypes as C
 import os

@@ -545,7 +545,7 @@ def multi_rank_parity(sb, dist):
         if float(viol) > 0:
             return {'ok': False, 'loss_rel_err': loss_err, 'grad_max_err_over_max': worst, 'failed_rank': r}
     return {'ok': bool(loss_err <= 1e-4), 'loss_rel_err': loss_err, 'grad_max_err_over_max': worst, 'ranks': world,
-            'what': 'synced BCDD (NCCL prototype all-reduce, grad_scale = world) vs BetweenClassDistanceLoss on the '
+            'what': 'synced BCDD (prototype exchange over the ranks, grad_scale = world) vs BetweenClassDistanceLoss on the '
                     'concatenated batch; loss rtol 1e-4, grad / world rtol 1e-3'}
 
 

@@ -168,6 +168,11 @@ def _scale_by_grad_output(buf: Optional[torch.Tensor], grad_out: torch.Tensor):
             'dskd_scale_inplace')
 
 
+def _const(t: torch.Tensor):
+    """The tensor without its autograd history (the teacher side / detached targets); no new tensor object when it has none."""
+    return t.detach() if t.requires_grad else t
+
+
 def _as_scalar_grad(grad_out: torch.Tensor):
     if grad_out.dtype is torch.float32 and grad_out.dim() == 0:      # the usual case: d(loss) of a scalar fp32 loss
         return grad_out
@@ -229,8 +234,14 @@ class _DsgfdFn(torch.autograd.Function):
             offs.append(tot)
             tot += (sz + 3) // 4 * 4
         flat = torch.empty(tot, dtype=torch.float32, device=dev) if tot else None
+        pieces = None
+        if tot and hs_n % 4 == 0 and all(sz % 4 == 0 for sz in sizes):      # no padding: one split instead of a slice each
+            pieces = flat.split_with_sizes(([hs_n] if hs_n else []) + sizes)
         if want_feat_grad:
-            grad_feats = [flat[o:o + sz].view_as(f) for o, sz, f in zip(offs, sizes, s_feats)]
+            if pieces is not None:
+                grad_feats = [p.view(f.shape) for p, f in zip(pieces[1 if hs_n else 0:], s_feats)]
+            else:
+                grad_feats = [flat[o:o + sz].view_as(f) for o, sz, f in zip(offs, sizes, s_feats)]
         for l in range(nl):
             a.d_student[l] = s_feats[l].data_ptr()
             a.d_teacher[l] = t_feats[l].data_ptr()
@@ -247,7 +258,7 @@ class _DsgfdFn(torch.autograd.Function):
                 a.d_student_labels = plan.labels.data_ptr()
                 a.d_prev_mask = plan.prev_mask.data_ptr()
                 if want_hs_grad:
-                    grad_hs = flat[:hs_n].view_as(hs_student)
+                    grad_hs = (pieces[0] if pieces is not None else flat[:hs_n]).view(hs_student.shape)
                     a.d_grad_hs_student = grad_hs.data_ptr()
         a.num_classes = plan.num_classes
         a.d_boxes, a.d_box_start, a.d_img_hw = plan.boxes.data_ptr(), plan.box_start.data_ptr(), plan.img_hw.data_ptr()
@@ -352,7 +363,7 @@ class DSGFeatureDistillLoss(nn.Module):
         # ---- features
         if self.feature_source == 'neck':
             s_feats = [L.f32c(f) for f in student_feats]
-            t_feats = [L.f32c(f.detach()) for f in teacher_feats]
+            t_feats = [L.f32c(_const(f)) for f in teacher_feats]
             plan.layout = L.LAYOUT_NCHW
             plan.shapes = [tuple(f.shape[2:]) for f in s_feats]
             N, C = s_feats[0].shape[:2]
@@ -361,7 +372,7 @@ class DSGFeatureDistillLoss(nn.Module):
                     raise L.DskdError(f'student / teacher feature shapes differ: {tuple(fs.shape)} vs {tuple(ft.shape)}')
         else:
             (s_mem, shapes), (t_mem, _) = student_feats, teacher_feats
-            s_feats, t_feats = [L.f32c(s_mem)], [L.f32c(t_mem.detach())]
+            s_feats, t_feats = [L.f32c(s_mem)], [L.f32c(_const(t_mem))]
             if isinstance(shapes, torch.Tensor):
                 shapes = shapes.tolist()
             plan.layout = L.LAYOUT_SNC
@@ -415,17 +426,16 @@ class DSGFeatureDistillLoss(nn.Module):
                 plan.prev_mask = _prev_masks.get(assignments['prev_labels'], plan.num_classes, dev)
         # embeddings: the student's for decode_v1 only, the teacher's for decode_v1 / v2; the cell-mask modes use none
         # (head_il.py:860-925,1082-1129 never touch hs)
-        empty = torch.empty(0, dtype=torch.float32, device=dev)
-        hs_s, hs_t = empty, empty
         if self.mask_mode in _ROW_MODES:
             if hs_teacher is None or (self.mask_mode == 'decode_v1' and hs_student is None):
                 raise L.DskdError(f"mask_mode='{self.mask_mode}' needs queries=(hs_student, hs_teacher)")
-            hs_t = L.f32c(hs_teacher.detach())
-            if self.mask_mode == 'decode_v1':
-                hs_s = L.f32c(hs_student)
+            hs_t = L.f32c(_const(hs_teacher))
+            hs_s = L.f32c(hs_student) if self.mask_mode == 'decode_v1' else torch.empty(0, dtype=torch.float32, device=dev)
             for h in (hs_s, hs_t):
                 if h.numel() and h.shape[-1] != C:
                     raise L.DskdError(f'embedding width {h.shape[-1]} != feature channels {C} (head_il.py:706 broadcasts them)')
+        else:
+            hs_s = hs_t = torch.empty(0, dtype=torch.float32, device=dev)
         return _DsgfdFn.apply(plan, hs_s, hs_t, *s_feats, *t_feats)
 
 
@@ -454,7 +464,7 @@ class _BcddFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, cfg, hs_student, hs_teacher):
         lib = L.load()
-        (labels, keepid, t_labels, prev_mask, num_classes, num_prev, reduction, loss_weight, sync) = cfg
+        (labels, keepid, t_labels, prev_mask, num_classes, num_prev, reduction, loss_weight, sync, by_products) = cfg
         dev = hs_student.device
         st = L.stream_of(hs_student)
         C = hs_student.shape[-1]
@@ -483,14 +493,13 @@ class _BcddFn(torch.autograd.Function):
                                             L.ptr(labels), hs_s2.shape[0], L.ptr(prev_mask), L.ptr(dist), L.ptr(loss),
                                             L.ptr(grad_proto), L.ptr(grad_hs), st), 'dskd_bcdd_loss_and_grad')
         ctx.staged = grad_hs
-        ctx.mark_non_differentiable(dist, proto)
-        ctx.set_materialize_grads(False)    # no zero-filled gradients for `dist` / `proto` on every backward
-        return loss.reshape(()), dist, proto
+        # the distance matrices and prototype tables are by-products without a gradient: handed over on the side instead of
+        # as extra autograd outputs (two more wrapped outputs and two more backward arguments on every call)
+        by_products['dist'], by_products['proto'] = dist, proto
+        return loss.reshape(())
 
     @staticmethod
-    def backward(ctx, grad_out, _gd, _gp):
-        if grad_out is None:        # only the non-differentiable by-products were used downstream
-            return None, None, None
+    def backward(ctx, grad_out):
         if ctx.staged is None and ctx.needs_input_grad[1]:
             raise RuntimeError('BetweenClassDistanceLoss: staged gradients already consumed (single backward per forward)')
         grad_hs = ctx.staged
@@ -532,7 +541,7 @@ class BetweenClassDistanceLoss(nn.Module):
         if weight is not None:
             raise NotImplementedError('the head always calls loss_corr with weight=None (head_il.py:1220)')
         hs_student, hs_teacher = queries
-        hs_s, hs_t = L.f32c(hs_student), L.f32c(hs_teacher.detach())
+        hs_s, hs_t = L.f32c(hs_student), L.f32c(_const(hs_teacher))
         dev = hs_s.device
         L.require_device(hs_s)
         prev = list(assignments['prev_labels'])
@@ -551,9 +560,10 @@ class BetweenClassDistanceLoss(nn.Module):
                assignments['teacher_keepid'].to(dev, torch.int64).contiguous(),
                assignments['teacher_labels'].to(dev, torch.int64).contiguous(),
                _prev_masks.get(prev, num_classes, dev), num_classes, num_prev, red, loss_weight,
-               bool(self.sync_prototypes))
-        loss, dist, proto = _BcddFn.apply(cfg, hs_s, hs_t)
-        self.last_distances, self.last_prototypes = dist, proto
+               bool(self.sync_prototypes), {})
+        loss = _BcddFn.apply(cfg, hs_s, hs_t)
+        # plain instance attributes (nn.Module.__setattr__ walks its parameter / buffer / module tables on every store)
+        self.__dict__['last_distances'], self.__dict__['last_prototypes'] = cfg[-1]['dist'], cfg[-1]['proto']
         return loss
 
 

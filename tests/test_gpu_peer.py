@@ -95,7 +95,7 @@ def _worker(rank, world, port, results):
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs on one box')
 def test_peer_exchange_matches_nccl():
     import torch.multiprocessing as mp
-    world = min(torch.cuda.device_count(), 8)
+    world = 2          # the exchange is generic in the world size (bench.py checks 8 ranks); two keep the test light
     with mp.Manager() as manager:
         results = manager.dict()
         mp.spawn(_worker, args=(world, _free_port(), results), nprocs=world, join=True)

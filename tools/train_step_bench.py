@@ -52,6 +52,9 @@ def main():
     if world > 1:
         torch.cuda.synchronize()
         dist.barrier()
+        from dskd_b200 import peer
+        peer.close_all()            # unmap the peers' NVLink buffers before anybody leaves
+        dist.barrier()
         dist.destroy_process_group()
 
 
